@@ -1,0 +1,179 @@
+/*
+ * include/tsm.h -- C-ABI of the B200-native ADCensus / EpipolarRectify path.
+ *
+ * This is the drop-in boundary: plain pointers, sizes and int error codes, no
+ * C++ or torch types.  The C++20 facade (tea_stereo_matching_b200/cpp/stereo.h)
+ * keeps the reference's class signatures and calls only these entry points;
+ * INTEGRATION.md shows the binding a maintainer of the reference would add.
+ * Every entry point cites the reference interface it replaces (paths relative
+ * to the reference repository root).
+ *
+ * Threading: a tsm_ctx is bound to one CUDA device and one stream and is not
+ * thread-safe; use one ctx per worker thread per GPU (the reference's
+ * ADCensus object is likewise not re-entrant: mutable ADCensusImpl,
+ * source/ADCensus.cpp:275-296).  All functions return TSM_OK (0) or a
+ * TSM_E_* code; tsm_last_error() gives the message.  There is NO CPU
+ * fallback anywhere behind this header: without a CUDA device every call
+ * except tsm_version / tsm_last_error / tsm_status_string fails with TSM_E_CUDA.
+ */
+#ifndef TSM_H
+#define TSM_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TSM_VERSION 100 /* 0.1.0 */
+
+typedef struct tsm_ctx tsm_ctx;
+
+enum tsm_status {
+    TSM_OK = 0,
+    TSM_E_ARG = 1,         /* bad argument (NULL, size mismatch, empty image, min>=max, ...) */
+    TSM_E_CUDA = 2,        /* CUDA runtime / launch failure, or no device */
+    TSM_E_OOM = 3,         /* device or pinned-host allocation failed */
+    TSM_E_UNSUPPORTED = 4, /* valid in the reference but not built yet (HSI, roi/mask, minD != 0) */
+    TSM_E_STATE = 5        /* call sequence error (wait without enqueue, tap before run, ...) */
+};
+
+/* stereo::ColorModel, include/stereo_utils.h:191-195 */
+enum tsm_color_model { TSM_COLOR_RGB = 0, TSM_COLOR_HSI = 1 };
+
+/* The state ADCensus keeps between setters and compute():
+ *   setMinMaxDisparity  source/ADCensus.cpp:307-313
+ *   setMatchingStrategy source/ADCensus.cpp:315-321
+ *   setOffset           source/ADCensus.cpp:323-328
+ * Tunables (lambda, tau, L, pi, voting, Canny) are the RGB constants of
+ * ADCensusParams::setADCensusParams, source/stereo_utils.cpp:271-326. */
+typedef struct tsm_adcensus_config {
+    int32_t min_disparity; /* only 0 is built; others -> TSM_E_UNSUPPORTED */
+    int32_t max_disparity; /* Dn = max - min + 1 cost planes (ADCensus.cpp:345) */
+    int32_t color_model;   /* tsm_color_model; HSI -> TSM_E_UNSUPPORTED */
+    int32_t roi_matching;  /* != 0 -> TSM_E_UNSUPPORTED */
+    int32_t mask_matching; /* != 0 -> TSM_E_UNSUPPORTED */
+    int32_t offset;        /* only used by roi/mask modes */
+} tsm_adcensus_config;
+
+/* cv::Mat depth/channel codes of the rectify maps (EpipolarRectifyMap,
+ * include/stereo_utils.h:109-148): cv::initUndistortRectifyMap(..., CV_16SC2, ...)
+ * emits (CV_16SC2, CV_16UC1) (source/stereo_utils.cpp:164-167); YAML-loaded maps
+ * may be (CV_32FC1, CV_32FC1). */
+enum tsm_map_kind {
+    TSM_MAP_FIXED_16SC2_16UC1 = 0, /* map1 int16[H][W][2] (x,y), map2 uint16[H][W] */
+    TSM_MAP_FLOAT_32FC1_X2 = 1     /* map1 float[H][W] (x), map2 float[H][W] (y) */
+};
+
+int tsm_version(void);
+const char* tsm_status_string(int status);
+/* Message of the last failure on this ctx (ctx == NULL: last failure of tsm_create). */
+const char* tsm_last_error(const tsm_ctx* ctx);
+
+/* Lifetime.  tsm_create makes its own non-blocking stream on `device`.
+ * tsm_create_on_stream borrows the caller's cudaStream_t (e.g. the current
+ * torch stream) so the caller can time the kernels with its own events.
+ * Replaces ADCensus::ADCensus()/~ADCensus() (source/ADCensus.cpp:298-305). */
+int tsm_create(int device, tsm_ctx** out);
+int tsm_create_on_stream(int device, void* cuda_stream, tsm_ctx** out);
+void tsm_destroy(tsm_ctx* ctx);
+int tsm_device_count(int* count);
+int tsm_synchronize(tsm_ctx* ctx);
+
+/* ---- stereo::ADCensus::compute(left, right, disparity), source/ADCensus.cpp:330-407 ----
+ * left/right: host, CV_8UC3 BGR, H rows of W pixels, row strides lstep/rstep bytes.
+ * disparity : host, CV_32FC1, row stride dstep bytes.  Blocking: returns after the
+ * result has been copied back.  Valid pixels hold sub-pixel disparities in
+ * [min,max]; invalid ones are negative (-1 occlusion / -2 mismatch, median-mixed). */
+int tsm_adcensus_compute(tsm_ctx* ctx, const tsm_adcensus_config* cfg,
+                         const uint8_t* left, size_t lstep, const uint8_t* right, size_t rstep,
+                         int H, int W, float* disparity, size_t dstep);
+
+/* Same computation on device-resident inputs (packed BGR [H][W][3], packed float
+ * output), enqueued on the ctx stream without any host synchronisation.  This is
+ * the HBM-resident form bench.py times as `value`. */
+int tsm_adcensus_compute_device(tsm_ctx* ctx, const tsm_adcensus_config* cfg,
+                                const uint8_t* d_left, const uint8_t* d_right, int H, int W, float* d_disparity);
+
+/* Asynchronous pair for batches (frames are sharded over GPUs and
+ * several frames are in flight per GPU, one ctx each): enqueue copies the pair
+ * into pinned staging, H2D, kernels, D2H into pinned staging; wait blocks and
+ * copies the result into the caller's buffer. */
+int tsm_adcensus_enqueue(tsm_ctx* ctx, const tsm_adcensus_config* cfg,
+                         const uint8_t* left, size_t lstep, const uint8_t* right, size_t rstep, int H, int W);
+int tsm_adcensus_wait(tsm_ctx* ctx, float* disparity, size_t dstep);
+
+/* ---- stereo::EpipolarRectify::rectify(left, right, L, R), source/EpipolarRectify.cpp:87-101 ----
+ * One cv::remap(src, dst, map1, map2, INTER_LINEAR) (BORDER_CONSTANT 0) of a CV_8UC3
+ * image: src is sH x sW (row stride sstep), dst is H x W (the map size, row stride dstep). */
+int tsm_remap(tsm_ctx* ctx, const uint8_t* src, size_t sstep, int sH, int sW,
+              const void* map1, const void* map2, int map_kind, int H, int W, uint8_t* dst, size_t dstep);
+
+/* ---- stereo::EpipolarRectify::rectify(stereoImage, L, R), source/EpipolarRectify.cpp:68-85 ----
+ * Crops the side-by-side frame (H x 2W) into halves [0,W) / [W,2W) and remaps each with its
+ * own map pair (map00,map01) / (map10,map11). */
+int tsm_rectify_stereo(tsm_ctx* ctx, const uint8_t* stereo, size_t sstep, int H, int W,
+                       const void* map00, const void* map01, const void* map10, const void* map11, int map_kind,
+                       uint8_t* left, size_t lstep, uint8_t* right, size_t rstep);
+
+/* Fused rectify -> ADCensus (BASELINE config C4): the rectified pair never leaves
+ * the device.  Maps are cached on the device keyed by their host pointers + size;
+ * call tsm_invalidate_maps() if the host map contents change in place. */
+int tsm_rectify_adcensus(tsm_ctx* ctx, const tsm_adcensus_config* cfg,
+                         const uint8_t* stereo, size_t sstep, int H, int W,
+                         const void* map00, const void* map01, const void* map10, const void* map11, int map_kind,
+                         float* disparity, size_t dstep);
+void tsm_invalidate_maps(tsm_ctx* ctx);
+
+/* ---- parity taps: the analogue of the reference's writeProcess debug dumps
+ * (source/ADCensus.cpp:573-580, 785-792, 1003-1010).  tsm_stage_begin uploads a pair and
+ * sizes the arena; tsm_stage_run runs the stages in `mask` (TSM_STAGE_* bits, in pipeline
+ * order); tsm_tap / tsm_poke copy an intermediate buffer device->host / host->device so
+ * each kernel can be checked on the ORACLE's input for that stage. */
+enum tsm_stage {
+    TSM_STAGE_PREP = 1 << 0,     /* census signatures, arms, window sizes, similarity flags */
+    TSM_STAGE_INIT = 1 << 1,     /* costInitialize       ADCensus.cpp:522-581 */
+    TSM_STAGE_AGGREGATE = 1 << 2,/* costAggregate        ADCensus.cpp:753-793 */
+    TSM_STAGE_SCANLINE = 1 << 3, /* scanlineOptimize     ADCensus.cpp:997-1011 */
+    TSM_STAGE_WTA = 1 << 4,      /* cost2disparity x2    ADCensus.cpp:1394-1413 */
+    TSM_STAGE_LRC = 1 << 5,      /* outlierElimination   ADCensus.cpp:1013-1044 */
+    TSM_STAGE_VOTE = 1 << 6,     /* regionVoting x5      ADCensus.cpp:1046-1159 (arg = one call 0..4, -1 = all) */
+    TSM_STAGE_INTERP = 1 << 7,   /* properInterpolation  ADCensus.cpp:1161-1239 */
+    TSM_STAGE_DISCONT = 1 << 8,  /* discontinuityAdjust. ADCensus.cpp:1256-1342 */
+    TSM_STAGE_SUBPIXEL = 1 << 9, /* subpixelEnhancement  ADCensus.cpp:1344-1374 */
+    TSM_STAGE_ALL = (1 << 10) - 1
+};
+enum tsm_buffer {
+    TSM_BUF_VOL_LEFT = 0,  /* float [H][W][Dp], Dp = tsm_volume_pitch() */
+    TSM_BUF_VOL_RIGHT = 1,
+    TSM_BUF_ARMS_LEFT = 2, /* uint8 [H][W][4] = up, down, left, right */
+    TSM_BUF_ARMS_RIGHT = 3,
+    TSM_BUF_WTA_LEFT = 4,  /* int32 [H][W] */
+    TSM_BUF_WTA_RIGHT = 5,
+    TSM_BUF_DISP = 6,      /* int32 [H][W], the working disparity map (m_disparityMap) */
+    TSM_BUF_EDGES = 7,     /* uint8 [H][W], Canny output of discontinuityAdjustment */
+    TSM_BUF_FINAL = 8,     /* float [H][W] */
+    TSM_BUF_CENSUS_LEFT = 9,  /* uint64 [6][H][W]: lt_B, lt_G, lt_R, gt_B, gt_G, gt_R */
+    TSM_BUF_CENSUS_RIGHT = 10,
+    TSM_BUF_IMG_LEFT = 11, /* uint8 [H][W][3] */
+    TSM_BUF_IMG_RIGHT = 12
+};
+int tsm_stage_begin(tsm_ctx* ctx, const tsm_adcensus_config* cfg,
+                    const uint8_t* left, size_t lstep, const uint8_t* right, size_t rstep, int H, int W);
+int tsm_stage_run(tsm_ctx* ctx, int mask, int arg);
+int tsm_volume_pitch(const tsm_ctx* ctx); /* Dp, floats per pixel in the volumes (>= Dn) */
+size_t tsm_buffer_bytes(const tsm_ctx* ctx, int buffer);
+int tsm_tap(tsm_ctx* ctx, int buffer, void* dst, size_t bytes);
+int tsm_poke(tsm_ctx* ctx, int buffer, const void* src, size_t bytes);
+
+/* Per-stage device time of the last compute on this ctx, in milliseconds, measured
+ * with CUDA events on the ctx stream when profiling was enabled.  names/ms arrays of
+ * length *n; returns the number of stages actually filled in *n. */
+int tsm_set_profiling(tsm_ctx* ctx, int enabled);
+int tsm_get_stage_times(tsm_ctx* ctx, int* n, const char** names, float* ms);
+/* Number of kernels this library launched on the ctx since creation (bench.py's gpu_launches). */
+long long tsm_launch_count(const tsm_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,690 @@
+// k_post.cu -- disparity refinement chain (multiOptimize, reference
+// source/ADCensus.cpp:1376-1392): WTA, left-right check, region voting x5 (including
+// the reference's histogram leak), proper interpolation, depth-discontinuity
+// adjustment (equalizeHist -> blur -> Canny -> edge fix-up), sub-pixel + 3x3 median.
+// All integer stages are bit-exact restatements; see each kernel for the cited lines.
+#include "tsm_common.cuh"
+#include <cooperative_groups.h>
+#include <float.h>
+#include <limits.h>
+
+namespace cg = cooperative_groups;
+
+namespace tsm {
+
+// =========================================================================== a9
+// cost2disparity (ADCensus.cpp:1394-1413): first strict minimum over d = 0..Dn-1.
+__global__ void __launch_bounds__(256) k_wta(const float* __restrict__ vol, int32_t* __restrict__ disp, size_t npx, int Dn, int Dp)
+{
+    const size_t p = (size_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (p >= npx) return;
+    const float* c = vol + p * Dp;
+    float best = FLT_MAX;
+    int bd = INT_MAX;
+    for (int d = lane; d < Dn; d += 32) {
+        const float v = c[d];
+        if (best > v) { best = v; bd = d; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+        const int od = __shfl_xor_sync(0xffffffffu, bd, o);
+        if (ov < best || (ov == best && od < bd)) { best = ov; bd = od; }
+    }
+    if (lane == 0) disp[p] = bd == INT_MAX ? 0 : bd;
+}
+
+void wta(const Launcher& L, const Dims& d, const float* vol, int32_t* disp)
+{
+    const size_t npx = d.npx();
+    k_wta<<<(unsigned)((npx + 7) / 8), 256, 0, L.stream>>>(vol, disp, npx, d.Dn, d.Dp);
+    L.count(1);
+}
+
+// ========================================================================== a10
+// outlierElimination (ADCensus.cpp:1013-1044), dispTolerance = 0, minD = 0.
+__global__ void k_lrc(const int32_t* __restrict__ dl, const int32_t* __restrict__ dr, int32_t* __restrict__ out, int H, int W, int maxD)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= W) return;
+    const int32_t* rrow = dr + (size_t)y * W;
+    int disp = dl[(size_t)y * W + x];
+    if (x - disp < 0 || rrow[x - disp] != disp) {
+        bool occlusion = true;
+        const int dmax = min(maxD, x);
+        for (int d = 0; d <= dmax; ++d)
+            if (rrow[x - d] == d) { occlusion = false; break; }
+        disp = occlusion ? kOcclusion : kMismatch;
+    }
+    out[(size_t)y * W + x] = disp;
+}
+
+void lrc(const Launcher& L, const Dims& d, const int32_t* dl, const int32_t* dr, int32_t* out)
+{
+    dim3 g((d.W + 127) / 128, d.H);
+    k_lrc<<<g, 128, 0, L.stream>>>(dl, dr, out, d.H, d.W, d.Dn - 1);
+    L.count(1);
+}
+
+// ========================================================================== a11
+// regionVoting (ADCensus.cpp:1046-1159).  The reference walks pixels in raster order
+// with ONE histogram that is cleared only after a high-vote outlier (:1150), so the
+// votes of every low-vote outlier (vote <= 20) leak into the next high-vote outlier.
+// Exact parallel form:
+//   1. k_vote_count : per outlier, own vote count; low-vote ones publish their count
+//   2. exclusive sum-scan over raster order -> CSR offsets of the low-vote lists
+//   3. k_vote_mark + exclusive max-scan     -> start of the run of low-vote outliers
+//                                              preceding each high-vote outlier
+//   4. k_vote_fill  : low-vote outliers write their (<= 20) votes into the CSR payload
+//   5. k_vote_high  : per high-vote outlier, histogram of own region + leaked slice
+//                     [start, off), first arg-max, ratio test (float)h/(float)vote > 0.4f
+// Cross region of p (arms of the LEFT view): horizontal_first: rows y-up..y+down, each
+// with its own left/right arm; else columns x-left..x+right, each with its own up/down arm.
+
+// Calls f(valid, value) warp-synchronously for every pixel of the cross region of p.
+// Lanes always run along x so the disparity reads are coalesced.
+template <bool HF, typename F>
+__device__ __forceinline__ void for_each_region(const int32_t* __restrict__ disp, const uchar4* __restrict__ arms, int W,
+                                                size_t p, int lane, F f)
+{
+    const uchar4 a = arms[p];
+    if (HF) {
+        for (int o = -(int)a.x; o <= (int)a.y; ++o) {
+            const size_t c = p + (ptrdiff_t)o * W;
+            const uchar4 ac = arms[c];
+            for (int i0 = -(int)ac.z; i0 <= (int)ac.w; i0 += 32) {
+                const int i = i0 + lane;
+                const bool in = i <= (int)ac.w;
+                const int v = in ? disp[c + i] : -1;
+                f(in && v >= 0, v);
+            }
+        }
+    } else {
+        const int no = (int)a.z + (int)a.w + 1;
+        for (int o0 = 0; o0 < no; o0 += 32) {
+            const int o = o0 + lane - (int)a.z;
+            const bool oin = o <= (int)a.w;
+            const size_t c = p + (oin ? o : 0);
+            const uchar4 ac = arms[c];
+            int up = oin ? (int)ac.x : 0, down = oin ? (int)ac.y : 0;
+            int mup = up, mdown = down;
+#pragma unroll
+            for (int s = 16; s > 0; s >>= 1) {
+                mup = max(mup, __shfl_xor_sync(0xffffffffu, mup, s));
+                mdown = max(mdown, __shfl_xor_sync(0xffffffffu, mdown, s));
+            }
+            for (int i = -mup; i <= mdown; ++i) {
+                const bool in = oin && i >= -up && i <= down;
+                const int v = in ? disp[c + (ptrdiff_t)i * W] : -1;
+                f(in && v >= 0, v);
+            }
+        }
+    }
+}
+
+template <bool HF>
+__global__ void __launch_bounds__(256)
+k_vote_count(const int32_t* __restrict__ disp, const uchar4* __restrict__ arms, int32_t* __restrict__ vote,
+             int32_t* __restrict__ lowcnt, size_t npx, int W)
+{
+    const size_t p = (size_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (p >= npx) return;
+    if (disp[p] >= 0) {
+        if (lane == 0) { vote[p] = 0; lowcnt[p] = 0; }
+        return;
+    }
+    int cnt = 0;
+    for_each_region<HF>(disp, arms, W, p, lane, [&](bool valid, int) { cnt += __popc(__ballot_sync(0xffffffffu, valid)); });
+    if (lane == 0) {
+        vote[p] = cnt;
+        lowcnt[p] = cnt <= kVotingThresh ? cnt : 0;
+    }
+}
+
+__global__ void k_vote_mark(const int32_t* __restrict__ disp, const int32_t* __restrict__ vote, const int32_t* __restrict__ off,
+                            int32_t* __restrict__ mark, size_t npx)
+{
+    const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= npx) return;
+    mark[p] = (disp[p] < 0 && vote[p] > kVotingThresh) ? off[p] : 0;
+}
+
+template <bool HF>
+__global__ void __launch_bounds__(256)
+k_vote_fill(const int32_t* __restrict__ disp, const uchar4* __restrict__ arms, const int32_t* __restrict__ vote,
+            const int32_t* __restrict__ off, uint16_t* __restrict__ flat, size_t npx, int W)
+{
+    const size_t p = (size_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (p >= npx) return;
+    if (disp[p] >= 0) return;
+    const int n = vote[p];
+    if (n == 0 || n > kVotingThresh) return;
+    uint16_t* dst = flat + off[p];
+    int base = 0;
+    for_each_region<HF>(disp, arms, W, p, lane, [&](bool valid, int v) {
+        const unsigned b = __ballot_sync(0xffffffffu, valid);
+        if (valid) dst[base + __popc(b & ((1u << lane) - 1u))] = (uint16_t)v;
+        base += __popc(b);
+    });
+}
+
+constexpr int VOTE_WARPS = 8;
+template <bool HF>
+__global__ void __launch_bounds__(VOTE_WARPS * 32)
+k_vote_high(const int32_t* __restrict__ disp, const uchar4* __restrict__ arms, const int32_t* __restrict__ vote,
+            const int32_t* __restrict__ off, const int32_t* __restrict__ start, const uint16_t* __restrict__ flat,
+            int32_t* __restrict__ out, size_t npx, int W, int Dn)
+{
+    extern __shared__ int hist_all[];  // [VOTE_WARPS][Dn]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const size_t p = (size_t)blockIdx.x * VOTE_WARPS + warp;
+    if (p >= npx) return;
+    const int dp = disp[p];
+    const int n = vote[p];
+    if (dp >= 0 || n <= kVotingThresh) {  // valid pixel or low-vote outlier: unchanged (:1077-1080, :1132-1135)
+        if (lane == 0) out[p] = dp;
+        return;
+    }
+    int* hist = hist_all + warp * Dn;
+    for (int d = lane; d < Dn; d += 32) hist[d] = 0;
+    __syncwarp();
+    for_each_region<HF>(disp, arms, W, p, lane, [&](bool valid, int v) {
+        if (valid) atomicAdd(&hist[v], 1);
+    });
+    for (int i = start[p] + lane; i < off[p]; i += 32) atomicAdd(&hist[flat[i]], 1);  // the leak
+    __syncwarp();
+    int best = 0, bd = INT_MAX;
+    for (int d = lane; d < Dn; d += 32) {
+        const int h = hist[d];
+        if (h > best) { best = h; bd = d; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const int oh = __shfl_xor_sync(0xffffffffu, best, o);
+        const int od = __shfl_xor_sync(0xffffffffu, bd, o);
+        if (oh > best || (oh == best && od < bd)) { best = oh; bd = od; }
+    }
+    if (lane == 0) {
+        const float ratio = __fdiv_rn((float)best, (float)n);  // hist[d] / (float)vote, :1144
+        out[p] = (best > 0 && ratio > kVotingRatio) ? bd : dp;
+    }
+}
+
+// ---- exclusive scans over the raster order (sum / max), 3 phases --------------
+constexpr int SCAN_T = 256, SCAN_I = 8, SCAN_TILE = SCAN_T * SCAN_I;
+struct OpSum { __device__ static int apply(int a, int b) { return a + b; } };
+struct OpMax { __device__ static int apply(int a, int b) { return a > b ? a : b; } };
+
+template <typename Op>
+__device__ __forceinline__ int block_exclusive_scan(int v, int* total)
+{
+    // v >= 0; identity 0 for both ops.
+    __shared__ int wsum[SCAN_T / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc = Op::apply(inc, t);
+    }
+    if (lane == 31) wsum[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        int w = lane < SCAN_T / 32 ? wsum[lane] : 0;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, w, o);
+            if (lane >= o) w = Op::apply(w, t);
+        }
+        if (lane < SCAN_T / 32) wsum[lane] = w;
+    }
+    __syncthreads();
+    const int prefix = warp > 0 ? wsum[warp - 1] : 0;
+    int exc = __shfl_up_sync(0xffffffffu, inc, 1);
+    if (lane == 0) exc = 0;
+    if (total) *total = wsum[SCAN_T / 32 - 1];
+    const int r = Op::apply(prefix, exc);
+    __syncthreads();
+    return r;
+}
+
+template <typename Op>
+__global__ void __launch_bounds__(SCAN_T) k_scan_reduce(const int32_t* __restrict__ in, int32_t* __restrict__ sums, size_t n)
+{
+    const size_t base = (size_t)blockIdx.x * SCAN_TILE + (size_t)threadIdx.x * SCAN_I;
+    int acc = 0;
+#pragma unroll
+    for (int i = 0; i < SCAN_I; ++i)
+        if (base + i < n) acc = Op::apply(acc, in[base + i]);
+    int total;
+    block_exclusive_scan<Op>(acc, &total);
+    if (threadIdx.x == 0) sums[blockIdx.x] = total;
+}
+
+template <typename Op>
+__global__ void __launch_bounds__(SCAN_T) k_scan_sums(int32_t* __restrict__ sums, int nblocks)
+{
+    __shared__ int carry_s;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    for (int b0 = 0; b0 < nblocks; b0 += SCAN_T) {
+        const int i = b0 + threadIdx.x;
+        const int v = i < nblocks ? sums[i] : 0;
+        int total;
+        const int exc = block_exclusive_scan<Op>(v, &total);
+        const int carry = carry_s;
+        if (i < nblocks) sums[i] = Op::apply(carry, exc);
+        __syncthreads();
+        if (threadIdx.x == 0) carry_s = Op::apply(carry, total);
+        __syncthreads();
+    }
+}
+
+template <typename Op>
+__global__ void __launch_bounds__(SCAN_T)
+k_scan_apply(const int32_t* __restrict__ in, int32_t* __restrict__ out, const int32_t* __restrict__ sums, size_t n)
+{
+    const size_t base = (size_t)blockIdx.x * SCAN_TILE + (size_t)threadIdx.x * SCAN_I;
+    int v[SCAN_I];
+    int acc = 0;
+#pragma unroll
+    for (int i = 0; i < SCAN_I; ++i) {
+        v[i] = base + i < n ? in[base + i] : 0;
+        acc = Op::apply(acc, v[i]);
+    }
+    int run = Op::apply(sums[blockIdx.x], block_exclusive_scan<Op>(acc, nullptr));
+#pragma unroll
+    for (int i = 0; i < SCAN_I; ++i) {
+        if (base + i < n) out[base + i] = run;
+        run = Op::apply(run, v[i]);
+    }
+}
+
+template <typename Op>
+static void exclusive_scan(const Launcher& L, const int32_t* in, int32_t* out, int32_t* sums, size_t n)
+{
+    const int nb = (int)((n + SCAN_TILE - 1) / SCAN_TILE);
+    k_scan_reduce<Op><<<nb, SCAN_T, 0, L.stream>>>(in, sums, n);
+    k_scan_sums<Op><<<1, SCAN_T, 0, L.stream>>>(sums, nb);
+    k_scan_apply<Op><<<nb, SCAN_T, 0, L.stream>>>(in, out, sums, n);
+    L.count(3);
+}
+
+template <bool HF>
+static void region_voting_t(const Launcher& L, const Dims& d, const int32_t* disp_in, int32_t* disp_out, const uchar4* arms,
+                            const VoteScratch& s)
+{
+    const size_t npx = d.npx();
+    const unsigned wblocks = (unsigned)((npx + 7) / 8);
+    k_vote_count<HF><<<wblocks, 256, 0, L.stream>>>(disp_in, arms, s.vote, s.lowcnt, npx, d.W);
+    L.count(1);
+    exclusive_scan<OpSum>(L, s.lowcnt, s.off, s.blocksums, npx);
+    k_vote_mark<<<(unsigned)((npx + 255) / 256), 256, 0, L.stream>>>(disp_in, s.vote, s.off, s.mark, npx);
+    L.count(1);
+    exclusive_scan<OpMax>(L, s.mark, s.start, s.blocksums, npx);
+    k_vote_fill<HF><<<wblocks, 256, 0, L.stream>>>(disp_in, arms, s.vote, s.off, s.flat, npx, d.W);
+    const size_t smem = (size_t)VOTE_WARPS * d.Dn * sizeof(int);
+    k_vote_high<HF><<<(unsigned)((npx + VOTE_WARPS - 1) / VOTE_WARPS), VOTE_WARPS * 32, smem, L.stream>>>(
+        disp_in, arms, s.vote, s.off, s.start, s.flat, disp_out, npx, d.W, d.Dn);
+    L.count(2);
+}
+
+void region_voting(const Launcher& L, const Dims& d, const int32_t* disp_in, int32_t* disp_out, const uchar4* arms_left,
+                   bool horizontal_first, const VoteScratch& s)
+{
+    if (horizontal_first) region_voting_t<true>(L, d, disp_in, disp_out, arms_left, s);
+    else region_voting_t<false>(L, d, disp_in, disp_out, arms_left, s);
+}
+
+// ========================================================================== a12
+// properInterpolation (ADCensus.cpp:1161-1239).
+__constant__ int c_dirW[16] = {0, 2, 2, 2, 0, -2, -2, -2, 1, 2, 2, 1, -1, -2, -2, -1};
+__constant__ int c_dirH[16] = {2, 2, 0, -2, -2, -2, 0, 2, 2, 1, -1, -2, -2, -1, 1, 2};
+
+__global__ void k_interpolate(const int32_t* __restrict__ disp, int32_t* __restrict__ out, const uint32_t* __restrict__ img4, int H, int W)
+{
+    const int w = blockIdx.x * blockDim.x + threadIdx.x, h = blockIdx.y * blockDim.y + threadIdx.y;
+    if (w >= W || h >= H) return;
+    const size_t p = (size_t)h * W + w;
+    const int own = disp[p];
+    if (own >= 0) { out[p] = own; return; }
+    const uint32_t pc = img4[p];
+    // occlusion: min over the 16 entries, each initialised to the pixel's own value (:1180, :1211-1216)
+    int occ_min = own;
+    // mismatch: running pick (:1222-1231)
+    int md = own, mf = -1;
+#pragma unroll 1
+    for (int k = 0; k < 16; ++k) {
+        int hD = h, wD = w;
+        bool inside = true, got = false;
+        int nd = own, nf = -1;
+        const int dh = c_dirH[k], dw = c_dirW[k];
+        for (int s = 0; s < kMaxSearchDepth && inside && !got; ++s) {
+            if ((s & 1) == 0) { hD += dh / 2; wD += dw / 2; }
+            else { hD += dh - dh / 2; wD += dw - dw / 2; }
+            inside = hD >= 0 && hD < H && wD >= 0 && wD < W;
+            if (inside) {
+                const int v = disp[(size_t)hD * W + wD];
+                if (v >= 0) {
+                    nd = v;
+                    nf = color_diff_u32(pc, img4[(size_t)hD * W + wD]);
+                    got = true;
+                }
+            }
+        }
+        occ_min = min(occ_min, nd);
+        if (k == 0) { md = nd; mf = nf; }
+        else if (mf < 0 || (mf > nf && nf > 0)) { md = nd; mf = nf; }
+    }
+    out[p] = (own == kOcclusion) ? occ_min : md;
+}
+
+void proper_interpolation(const Launcher& L, const Dims& d, const int32_t* disp_in, int32_t* disp_out, const uint32_t* img4_left)
+{
+    dim3 b(32, 8), g((d.W + 31) / 32, (d.H + 7) / 8);
+    k_interpolate<<<g, b, 0, L.stream>>>(disp_in, disp_out, img4_left, d.H, d.W);
+    L.count(1);
+}
+
+// ========================================================================== a13
+// discontinuityAdjustment (ADCensus.cpp:1241-1342) with integer restatements of the
+// four OpenCV 4.13 calls (pinned against cv2 in tests/test_cvport.py):
+//   gray = disp < 0 ? 0 : (uchar)disp   (wraps mod 256, :1249) -> equalizeHist (:1252)
+//   -> blur 3x3 (:1263) -> Canny(30, 90, 3) (:1264) -> per-edge-pixel fix-up (:1268-1339).
+
+__global__ void __launch_bounds__(256) k_gray_hist(const int32_t* __restrict__ disp, uint8_t* __restrict__ gray, int32_t* __restrict__ hist, size_t npx)
+{
+    __shared__ int sh[256];
+    sh[threadIdx.x] = 0;
+    __syncthreads();
+    for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < npx; p += (size_t)gridDim.x * blockDim.x) {
+        const int d = disp[p];
+        const uint8_t g = d < 0 ? 0 : (uint8_t)d;
+        gray[p] = g;
+        atomicAdd(&sh[g], 1);
+    }
+    __syncthreads();
+    if (sh[threadIdx.x]) atomicAdd(&hist[threadIdx.x], sh[threadIdx.x]);
+}
+
+// cv::equalizeHist LUT: scale = 255.f/(total - hist[first]); lut[j] = sat_u8(rint(sum * scale)).
+__global__ void k_eq_lut(const int32_t* __restrict__ hist, int32_t* __restrict__ lut, int total)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    int i = 0;
+    while (i < 255 && !hist[i]) ++i;
+    for (int j = 0; j < 256; ++j) lut[j] = 0;
+    if (hist[i] == total) { lut[i] = i; return; }
+    const float scale = __fdiv_rn(255.f, (float)(total - hist[i]));
+    int sum = 0;
+    for (lut[i++] = 0; i < 256; ++i) {
+        sum += hist[i];
+        int r = __float2int_rn(__fmul_rn((float)sum, scale));
+        lut[i] = min(max(r, 0), 255);
+    }
+}
+
+__device__ __forceinline__ int reflect101(int p, int n)
+{
+    if (p < 0) p = -p;
+    if (p >= n) p = 2 * n - 2 - p;
+    return p;
+}
+
+// cv::blur 3x3 of the equalised image: BORDER_REFLECT_101, round(sum/9) (never a tie).
+__global__ void k_eq_blur(const uint8_t* __restrict__ gray, const int32_t* __restrict__ lut, uint8_t* __restrict__ blurred, int H, int W)
+{
+    __shared__ int slut[256];
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+    if (tid < 256) slut[tid] = lut[tid];
+    __syncthreads();
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= W || y >= H) return;
+    int s = 0;
+#pragma unroll
+    for (int dy = -1; dy <= 1; ++dy) {
+        const uint8_t* row = gray + (size_t)reflect101(y + dy, H) * W;
+#pragma unroll
+        for (int dx = -1; dx <= 1; ++dx) s += slut[row[reflect101(x + dx, W)]];
+    }
+    blurred[(size_t)y * W + x] = (uint8_t)((2 * s + 9) / 18);
+}
+
+// Sobel 3x3 (BORDER_REPLICATE) and L1 magnitude.
+__global__ void k_sobel(const uint8_t* __restrict__ src, int16_t* __restrict__ gx, int16_t* __restrict__ gy, int32_t* __restrict__ mag, int H, int W)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= W || y >= H) return;
+    const int xm = max(x - 1, 0), xp = min(x + 1, W - 1), ym = max(y - 1, 0), yp = min(y + 1, H - 1);
+    const uint8_t *r0 = src + (size_t)ym * W, *r1 = src + (size_t)y * W, *r2 = src + (size_t)yp * W;
+    const int a = r0[xm], b = r0[x], c = r0[xp], d = r1[xm], f = r1[xp], g = r2[xm], h = r2[x], i = r2[xp];
+    const int dx = (c - a) + 2 * (f - d) + (i - g);
+    const int dy = (g - a) + 2 * (h - b) + (i - c);
+    const size_t p = (size_t)y * W + x;
+    gx[p] = (int16_t)dx;
+    gy[p] = (int16_t)dy;
+    mag[p] = abs(dx) + abs(dy);
+}
+
+// Non-maximum suppression + double threshold (imgproc/canny.cpp): 0 weak candidate, 1 none, 2 strong.
+__global__ void k_canny_nms(const int16_t* __restrict__ gx, const int16_t* __restrict__ gy, const int32_t* __restrict__ mag,
+                            uint8_t* __restrict__ map, int H, int W, int low, int high)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= W || y >= H) return;
+    auto M = [&](int yy, int xx) -> int { return (yy < 0 || yy >= H || xx < 0 || xx >= W) ? 0 : mag[(size_t)yy * W + xx]; };
+    const size_t p = (size_t)y * W + x;
+    const int m = mag[p];
+    uint8_t v = 1;
+    if (m > low) {
+        const int xs = gx[p], ys = gy[p];
+        const int ax = abs(xs), ay = abs(ys) << 15;
+        const int tg22x = ax * 13573;
+        bool is_max;
+        if (ay < tg22x) {
+            is_max = m > M(y, x - 1) && m >= M(y, x + 1);
+        } else {
+            const int tg67x = tg22x + (ax << 16);
+            if (ay > tg67x) {
+                is_max = m > M(y - 1, x) && m >= M(y + 1, x);
+            } else {
+                const int s = (xs ^ ys) < 0 ? -1 : 1;
+                is_max = m > M(y - 1, x - s) && m > M(y + 1, x + s);
+            }
+        }
+        if (is_max) v = m > high ? 2 : 0;
+    }
+    map[p] = v;
+}
+
+// Hysteresis: weak candidates 8-connected to a strong pixel become edges.  The result
+// is order independent.  Cooperative persistent kernel: every CTA relaxes 32x32 tiles to
+// a local fixed point in shared memory; grid-wide rounds repeat until no tile changed.
+constexpr int HY_T = 32;
+__global__ void __launch_bounds__(HY_T* HY_T) k_canny_hysteresis(uint8_t* __restrict__ map, int H, int W, int32_t* __restrict__ flags)
+{
+    cg::grid_group grid = cg::this_grid();
+    __shared__ uint8_t t[HY_T + 2][HY_T + 2];
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int tiles_x = (W + HY_T - 1) / HY_T, tiles_y = (H + HY_T - 1) / HY_T;
+    const int ntiles = tiles_x * tiles_y;
+    for (int round = 0;; ++round) {
+        if (blockIdx.x == 0 && tx == 0 && ty == 0) flags[(round + 1) % 3] = 0;
+        bool any_changed = false;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            const int x0 = (tile % tiles_x) * HY_T, y0 = (tile / tiles_x) * HY_T;
+            for (int i = ty * HY_T + tx; i < (HY_T + 2) * (HY_T + 2); i += HY_T * HY_T) {
+                const int ly = i / (HY_T + 2), lx = i % (HY_T + 2);
+                const int y = y0 + ly - 1, x = x0 + lx - 1;
+                t[ly][lx] = (y >= 0 && y < H && x >= 0 && x < W) ? map[(size_t)y * W + x] : 1;
+            }
+            __syncthreads();
+            const bool inimg = (y0 + ty < H) && (x0 + tx < W);
+            bool mine_changed = false;
+            bool weak = inimg && t[ty + 1][tx + 1] == 0;
+            if (__syncthreads_or(weak)) {
+                for (;;) {
+                    bool ch = false;
+                    if (weak) {
+                        const bool nb = t[ty][tx] == 2 || t[ty][tx + 1] == 2 || t[ty][tx + 2] == 2 || t[ty + 1][tx] == 2 ||
+                                        t[ty + 1][tx + 2] == 2 || t[ty + 2][tx] == 2 || t[ty + 2][tx + 1] == 2 ||
+                                        t[ty + 2][tx + 2] == 2;
+                        if (nb) { ch = true; weak = false; mine_changed = true; }
+                    }
+                    __syncthreads();
+                    if (ch) t[ty + 1][tx + 1] = 2;
+                    if (!__syncthreads_or(ch)) break;
+                }
+                if (mine_changed) map[(size_t)(y0 + ty) * W + (x0 + tx)] = 2;
+            }
+            any_changed |= (bool)__syncthreads_or(mine_changed);
+        }
+        if (any_changed && tx == 0 && ty == 0) atomicExch(&flags[round % 3], 1);
+        __threadfence();
+        grid.sync();
+        if (*((volatile int32_t*)&flags[round % 3]) == 0) break;
+    }
+}
+
+__global__ void k_edges_finalize(const uint8_t* __restrict__ map, uint8_t* __restrict__ edges, size_t npx)
+{
+    const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < npx) edges[p] = map[p] == 2 ? 255 : 0;
+}
+
+__constant__ int c_adjH[8] = {-1, 1, -1, 1, -1, 1, 0, 0};
+__constant__ int c_adjW[8] = {-1, 1, 0, 0, 1, -1, -1, 1};
+
+__global__ void k_discont_adjust(const int32_t* __restrict__ disp, int32_t* __restrict__ out, const uint8_t* __restrict__ E,
+                                 const float* __restrict__ vol, int H, int W, int Dp)
+{
+    const int w = blockIdx.x * blockDim.x + threadIdx.x, h = blockIdx.y * blockDim.y + threadIdx.y;
+    if (w >= W || h >= H) return;
+    const size_t p = (size_t)h * W + w;
+    int d = disp[p];
+    if (h >= 1 && h < H - 1 && w >= 1 && w < W - 1 && E[p] != 0) {
+        auto e = [&](int yy, int xx) -> bool { return E[(size_t)yy * W + xx] != 0; };
+        int dir = -1;
+        if (e(h - 1, w - 1) && e(h + 1, w + 1)) dir = 0;
+        else if (e(h - 1, w + 1) && e(h + 1, w - 1)) dir = 4;
+        else if (e(h - 1, w) || e(h + 1, w)) {
+            if (e(h - 1, w - 1) || e(h - 1, w) || e(h - 1, w + 1))
+                if (e(h + 1, w - 1) || e(h + 1, w) || e(h + 1, w + 1)) dir = 2;
+        } else {
+            if (e(h - 1, w - 1) || e(h, w - 1) || e(h + 1, w - 1))
+                if (e(h - 1, w + 1) || e(h, w + 1) || e(h + 1, w + 1)) dir = 6;
+        }
+        if (dir != -1 && d >= 0) {
+            dir = (dir + 4) % 8;
+            float cost = vol[p * Dp + d];
+            const size_t p1 = (size_t)(h + c_adjH[dir]) * W + (w + c_adjW[dir]);
+            const size_t p2 = (size_t)(h + c_adjH[dir + 1]) * W + (w + c_adjW[dir + 1]);
+            const int d1 = disp[p1], d2 = disp[p2];
+            const float c1 = d1 >= 0 ? vol[p1 * Dp + d1] : -1.f;
+            const float c2 = d2 >= 0 ? vol[p2 * Dp + d2] : -1.f;
+            if (c1 != -1.f && c1 < cost) { d = d1; cost = c1; }
+            if (c2 != -1.f && c2 < cost) { d = d2; }
+        }
+    }
+    out[p] = d;
+}
+
+cudaError_t discontinuity_adjustment(const Launcher& L, const Dims& d, const int32_t* disp_in, int32_t* disp_out,
+                                     const float* vol_left, const EdgeScratch& s)
+{
+    const size_t npx = d.npx();
+    dim3 b(32, 8), g((d.W + 31) / 32, (d.H + 7) / 8);
+    cudaMemsetAsync(s.hist, 0, 256 * sizeof(int32_t), L.stream);
+    k_gray_hist<<<592, 256, 0, L.stream>>>(disp_in, s.gray, s.hist, npx);
+    k_eq_lut<<<1, 32, 0, L.stream>>>(s.hist, s.lut, (int)npx);
+    k_eq_blur<<<g, b, 0, L.stream>>>(s.gray, s.lut, s.blurred, d.H, d.W);
+    k_sobel<<<g, b, 0, L.stream>>>(s.blurred, s.gx, s.gy, s.mag, d.H, d.W);
+    k_canny_nms<<<g, b, 0, L.stream>>>(s.gx, s.gy, s.mag, s.map, d.H, d.W, kCannyLow, kCannyHigh);
+    L.count(5);
+    {
+        static int coop_blocks = 0;
+        if (coop_blocks == 0) {
+            int dev = 0, sms = 0, per_sm = 0;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_canny_hysteresis, HY_T * HY_T, 0);
+            coop_blocks = sms * (per_sm > 0 ? 1 : 0);
+            if (coop_blocks == 0) return cudaErrorLaunchOutOfResources;
+        }
+        cudaMemsetAsync(s.changed, 0, 3 * sizeof(int32_t), L.stream);
+        uint8_t* map = s.map;
+        int H = d.H, W = d.W;
+        int32_t* flags = s.changed;
+        void* args[] = {&map, &H, &W, &flags};
+        cudaError_t e = cudaLaunchCooperativeKernel((void*)k_canny_hysteresis, dim3(coop_blocks), dim3(HY_T, HY_T), args, 0, L.stream);
+        if (e != cudaSuccess) return e;
+        L.count(1);
+    }
+    k_edges_finalize<<<(unsigned)((npx + 255) / 256), 256, 0, L.stream>>>(s.map, s.edges, npx);
+    k_discont_adjust<<<g, b, 0, L.stream>>>(disp_in, disp_out, s.edges, vol_left, d.H, d.W, d.Dp);
+    L.count(2);
+    return cudaSuccess;
+}
+
+// ========================================================================== a14
+// subpixelEnhancement (ADCensus.cpp:1344-1374): quadratic fit on the LEFT volume, then
+// cv::medianBlur 3x3 (BORDER_REPLICATE) over the float map including negative markers.
+__global__ void k_subpixel(const int32_t* __restrict__ disp, const float* __restrict__ vol, float* __restrict__ out, size_t npx, int Dn, int Dp)
+{
+    const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= npx) return;
+    const int d = disp[p];
+    float f = (float)d;
+    if (d > 0 && d < Dn - 1) {
+        const float* c = vol + p * Dp;
+        const float cost = c[d], cp = c[d + 1], cm = c[d - 1];
+        const float num = __fsub_rn(cp, cm);
+        const float den = __fmul_rn(2.f, __fsub_rn(__fadd_rn(cp, cm), __fmul_rn(2.f, cost)));
+        const float diff = __fdiv_rn(num, den);
+        if (diff > -1.f && diff < 1.f) f = __fsub_rn(f, diff);
+    }
+    out[p] = f;
+}
+
+__device__ __forceinline__ void sort2(float& a, float& b)
+{
+    const float lo = fminf(a, b), hi = fmaxf(a, b);
+    a = lo;
+    b = hi;
+}
+
+__global__ void k_median3(const float* __restrict__ src, float* __restrict__ dst, int H, int W)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= W || y >= H) return;
+    float p[9];
+    int k = 0;
+#pragma unroll
+    for (int dy = -1; dy <= 1; ++dy) {
+        const float* row = src + (size_t)min(max(y + dy, 0), H - 1) * W;
+#pragma unroll
+        for (int dx = -1; dx <= 1; ++dx) p[k++] = row[min(max(x + dx, 0), W - 1)];
+    }
+    sort2(p[1], p[2]); sort2(p[4], p[5]); sort2(p[7], p[8]);
+    sort2(p[0], p[1]); sort2(p[3], p[4]); sort2(p[6], p[7]);
+    sort2(p[1], p[2]); sort2(p[4], p[5]); sort2(p[7], p[8]);
+    sort2(p[0], p[3]); sort2(p[5], p[8]); sort2(p[4], p[7]);
+    sort2(p[3], p[6]); sort2(p[1], p[4]); sort2(p[2], p[5]);
+    sort2(p[4], p[7]); sort2(p[4], p[2]); sort2(p[6], p[4]);
+    sort2(p[4], p[2]);
+    dst[(size_t)y * W + x] = p[4];
+}
+
+void subpixel(const Launcher& L, const Dims& d, const int32_t* disp, const float* vol_left, float* tmp, float* out)
+{
+    const size_t npx = d.npx();
+    k_subpixel<<<(unsigned)((npx + 255) / 256), 256, 0, L.stream>>>(disp, vol_left, tmp, npx, d.Dn, d.Dp);
+    dim3 b(32, 8), g((d.W + 31) / 32, (d.H + 7) / 8);
+    k_median3<<<g, b, 0, L.stream>>>(tmp, out, d.H, d.W);
+    L.count(2);
+}
+
+}  // namespace tsm

@@ -1,0 +1,160 @@
+// k_prep.cu -- per-view O(H*W) preparation kernels: BGRx packing, ternary census
+// sign planes, cross arms, cross-window sizes and colour-similarity flags.
+//
+// Reference semantics (paths relative to the reference repo):
+//   census sign test      source/ADCensus.cpp:461-472   (a4)
+//   arm construction      source/ADCensus.cpp:604-659   (a6)
+//   window sizes          source/ADCensus.cpp:716,733   (a7, d-independent)
+//   P1/P2 similarity test source/ADCensus.cpp:927-934   (a8)
+#include "tsm_common.cuh"
+
+namespace tsm {
+
+// ---- BGR -> BGRx ---------------------------------------------------------
+__global__ void k_pack_bgrx(const uint8_t* __restrict__ img, uint32_t* __restrict__ img4, size_t npx)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npx) return;
+    const uint8_t* p = img + i * 3;
+    img4[i] = (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16);
+}
+
+// ---- census sign planes ---------------------------------------------------
+// One CTA = 32x8 pixel tile; the (8+6)x(32+8) BGRx window is staged in shared
+// memory once and every thread builds its six 63-bit planes from it.
+constexpr int CT_W = 32, CT_H = 8, CH_W = kCensusW / 2, CH_H = kCensusH / 2;
+constexpr int CS_W = CT_W + 2 * CH_W, CS_H = CT_H + 2 * CH_H;
+
+__global__ void __launch_bounds__(CT_W* CT_H)
+k_census(const uint32_t* __restrict__ img4, uint64_t* __restrict__ census, int H, int W)
+{
+    __shared__ uint32_t tile[CS_H][CS_W + 1];
+    const int x0 = blockIdx.x * CT_W, y0 = blockIdx.y * CT_H;
+    const int tid = threadIdx.y * CT_W + threadIdx.x;
+    for (int i = tid; i < CS_H * CS_W; i += CT_W * CT_H) {
+        int ty = i / CS_W, tx = i % CS_W;
+        int y = y0 + ty - CH_H, x = x0 + tx - CH_W;
+        tile[ty][tx] = (y >= 0 && y < H && x >= 0 && x < W) ? img4[(size_t)y * W + x] : 0u;
+    }
+    __syncthreads();
+    const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
+    if (x >= W || y >= H) return;
+    uint64_t lt[3] = {0, 0, 0}, gt[3] = {0, 0, 0};
+    if (y - CH_H >= 0 && y + CH_H < H && x - CH_W >= 0 && x + CH_W < W) {
+        const uint32_t c = tile[threadIdx.y + CH_H][threadIdx.x + CH_W];
+        const int cb = c & 0xff, cg = (c >> 8) & 0xff, cr = (c >> 16) & 0xff;
+        int bit = 0;
+#pragma unroll
+        for (int i = 0; i < kCensusH; ++i)
+#pragma unroll
+            for (int j = 0; j < kCensusW; ++j, ++bit) {
+                const uint32_t a = tile[threadIdx.y + i][threadIdx.x + j];
+                const int ab = a & 0xff, ag = (a >> 8) & 0xff, ar = (a >> 16) & 0xff;
+                const uint64_t m = 1ull << bit;
+                if (ab < cb) lt[0] |= m;
+                if (ab > cb) gt[0] |= m;
+                if (ag < cg) lt[1] |= m;
+                if (ag > cg) gt[1] |= m;
+                if (ar < cr) lt[2] |= m;
+                if (ar > cr) gt[2] |= m;
+            }
+    }
+    const size_t npx = (size_t)H * W, p = (size_t)y * W + x;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        census[(size_t)c * npx + p] = lt[c];
+        census[(size_t)(3 + c) * npx + p] = gt[c];
+    }
+}
+
+// ---- cross arms -------------------------------------------------------------
+__device__ __forceinline__ int arm_length(const uint32_t* __restrict__ img4, int H, int W, int y, int x, int dy, int dx)
+{
+    // Literal walk of computeLimit (RGB): ADCensus.cpp:609-658.
+    const uint32_t p = img4[(size_t)y * W + x];
+    int d = 1;
+    int y1 = y + dy, x1 = x + dx;
+    uint32_t p2 = p;
+    bool inside = (0 <= y1) && (y1 < H) && (0 <= x1) && (x1 < W);
+    if (inside) {
+        bool color_cond = true, wlimit_cond = true, fcolor_cond = true;
+        while (color_cond && wlimit_cond && fcolor_cond && inside) {
+            const uint32_t p1 = img4[(size_t)y1 * W + x1];
+            const int cd = color_diff_u32(p, p1);
+            color_cond = cd < kTau1 && color_diff_u32(p1, p2) < kTau1;
+            wlimit_cond = d < kL1;
+            fcolor_cond = (d <= kL2) || (cd < kTau2);
+            p2 = p1;
+            y1 += dy;
+            x1 += dx;
+            inside = (0 <= y1) && (y1 < H) && (0 <= x1) && (x1 < W);
+            d++;
+        }
+        d--;
+    }
+    return d - 1;
+}
+
+__global__ void k_arms(const uint32_t* __restrict__ img4, uchar4* __restrict__ arms, int H, int W)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= W || y >= H) return;
+    uchar4 a;
+    a.x = (unsigned char)arm_length(img4, H, W, y, x, -1, 0);
+    a.y = (unsigned char)arm_length(img4, H, W, y, x, 1, 0);
+    a.z = (unsigned char)arm_length(img4, H, W, y, x, 0, -1);
+    a.w = (unsigned char)arm_length(img4, H, W, y, x, 0, 1);
+    arms[(size_t)y * W + x] = a;
+}
+
+// ---- cross-window sizes -----------------------------------------------------
+// aggregation1D propagates the window size like a cost (ADCensus.cpp:716) starting
+// from all ones (:733): horizontal-first -> N = sum over the vertical arm of the row
+// lengths; vertical-first -> sum over the horizontal arm of the column lengths.
+__global__ void k_wsize(const uchar4* __restrict__ arms, float* __restrict__ wsize, int H, int W)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= W || y >= H) return;
+    const size_t npx = (size_t)H * W, p = (size_t)y * W + x;
+    const uchar4 a = arms[p];
+    int nh = 0, nv = 0;
+    for (int j = -(int)a.x; j <= (int)a.y; ++j) {
+        const uchar4 q = arms[p + (ptrdiff_t)j * W];
+        nh += q.z + q.w + 1;
+    }
+    for (int j = -(int)a.z; j <= (int)a.w; ++j) {
+        const uchar4 q = arms[p + j];
+        nv += q.x + q.y + 1;
+    }
+    wsize[p] = (float)nh;
+    wsize[npx + p] = (float)nv;
+}
+
+// ---- similarity flags ---------------------------------------------------------
+__global__ void k_flags(const uint32_t* __restrict__ img4, uint8_t* __restrict__ flags, int H, int W)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= W || y >= H) return;
+    const size_t p = (size_t)y * W + x;
+    const uint32_t c = img4[p];
+    uint8_t f = 0;
+    if (y > 0 && color_diff_u32(c, img4[p - W]) < kColorDiff) f |= 1;
+    if (x > 0 && color_diff_u32(c, img4[p - 1]) < kColorDiff) f |= 2;
+    flags[p] = f;
+}
+
+void prep_view(const Launcher& L, const Dims& d, const uint8_t* img, uint32_t* img4, uint64_t* census, uchar4* arms,
+               float* wsize, uint8_t* flags)
+{
+    const size_t npx = d.npx();
+    k_pack_bgrx<<<(unsigned)((npx + 255) / 256), 256, 0, L.stream>>>(img, img4, npx);
+    dim3 cb(CT_W, CT_H), cg((d.W + CT_W - 1) / CT_W, (d.H + CT_H - 1) / CT_H);
+    k_census<<<cg, cb, 0, L.stream>>>(img4, census, d.H, d.W);
+    dim3 b(32, 8), g((d.W + 31) / 32, (d.H + 7) / 8);
+    k_arms<<<g, b, 0, L.stream>>>(img4, arms, d.H, d.W);
+    k_wsize<<<g, b, 0, L.stream>>>(arms, wsize, d.H, d.W);
+    k_flags<<<g, b, 0, L.stream>>>(img4, flags, d.H, d.W);
+    L.count(5);
+}
+
+}  // namespace tsm

@@ -1,0 +1,753 @@
+// tsm_capi.cu -- the C-ABI of include/tsm.h: context, device arena, stage
+// orchestration.  Mirrors the call sequence of stereo::ADCensus::compute
+// (reference source/ADCensus.cpp:330-407) and multiOptimize (:1376-1392).
+#include "tsm_common.cuh"
+#include <limits.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include <vector>
+
+using namespace tsm;
+
+namespace {
+thread_local std::string g_create_error;
+
+struct Buf {
+    void* p = nullptr;
+    size_t bytes = 0;
+};
+
+struct StageTimer {
+    const char* name;
+    cudaEvent_t beg, end;
+};
+}  // namespace
+
+struct tsm_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    std::string err;
+    long long launches = 0;
+
+    // geometry of the arena
+    Dims dm{0, 0, 0, 0};
+    tsm_adcensus_config cfg{};
+    bool have_pair = false;
+
+    // device buffers
+    Buf img[2], img4[2], census[2], arms[2], wsize[2], flags[2], vol[2], wta_[2];
+    Buf disp[2], fin, ftmp;
+    Buf v_vote, v_lowcnt, v_off, v_mark, v_start, v_sums, v_flat;
+    Buf e_gray, e_blur, e_mag, e_gx, e_gy, e_map, e_edges, e_hist, e_lut, e_changed;
+    Buf tab_ad, tab_c;
+    int disp_cur = 0;  // which of disp[2] holds the working map
+    float p1_lo = 0.f, p2_lo = 0.f;
+    bool tables_ready = false;
+
+    // pinned staging
+    uint8_t* h_pair = nullptr;  // left | right packed
+    float* h_out = nullptr;
+    size_t h_pair_bytes = 0, h_out_bytes = 0;
+    bool pending = false;
+
+    // rectify
+    Buf r_src, r_map1[2], r_map2[2], r_fmap[2][2];
+    const void* map_key[4] = {nullptr, nullptr, nullptr, nullptr};
+    int map_kind = -1, map_H = 0, map_W = 0;
+    uint8_t* h_stereo = nullptr;
+    size_t h_stereo_bytes = 0;
+
+    // profiling
+    bool profiling = false;
+    std::vector<StageTimer> timers;
+    size_t timers_used = 0;
+};
+
+namespace {
+
+int fail(tsm_ctx* c, int code, const char* fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (c) c->err = buf;
+    else g_create_error = buf;
+    return code;
+}
+
+#define CK(c, call)                                                                                      \
+    do {                                                                                                 \
+        cudaError_t e__ = (call);                                                                        \
+        if (e__ != cudaSuccess)                                                                          \
+            return fail((c), e__ == cudaErrorMemoryAllocation ? TSM_E_OOM : TSM_E_CUDA, "%s: %s", #call, \
+                        cudaGetErrorString(e__));                                                        \
+    } while (0)
+
+int ensure(tsm_ctx* c, Buf& b, size_t bytes, bool zero = false)
+{
+    if (b.bytes >= bytes && b.p) return TSM_OK;
+    if (b.p) cudaFree(b.p);
+    b.p = nullptr;
+    b.bytes = 0;
+    cudaError_t e = cudaMalloc(&b.p, bytes);
+    if (e != cudaSuccess) return fail(c, TSM_E_OOM, "cudaMalloc(%zu bytes): %s", bytes, cudaGetErrorString(e));
+    b.bytes = bytes;
+    if (zero) {
+        e = cudaMemsetAsync(b.p, 0, bytes, c->stream);
+        if (e != cudaSuccess) return fail(c, TSM_E_CUDA, "cudaMemsetAsync: %s", cudaGetErrorString(e));
+    }
+    return TSM_OK;
+}
+void release(Buf& b)
+{
+    if (b.p) cudaFree(b.p);
+    b.p = nullptr;
+    b.bytes = 0;
+}
+
+int ensure_pinned(tsm_ctx* c, void** p, size_t* have, size_t bytes)
+{
+    if (*p && *have >= bytes) return TSM_OK;
+    if (*p) cudaFreeHost(*p);
+    *p = nullptr;
+    *have = 0;
+    cudaError_t e = cudaMallocHost(p, bytes);
+    if (e != cudaSuccess) return fail(c, TSM_E_OOM, "cudaMallocHost(%zu bytes): %s", bytes, cudaGetErrorString(e));
+    *have = bytes;
+    return TSM_OK;
+}
+
+int check_cfg(tsm_ctx* c, const tsm_adcensus_config* cfg, int H, int W)
+{
+    if (!cfg) return fail(c, TSM_E_ARG, "[ADCensus] config is NULL");
+    // setMinMaxDisparity, ADCensus.cpp:309-310
+    if ((long long)cfg->min_disparity * cfg->max_disparity < 0 || cfg->min_disparity >= cfg->max_disparity)
+        return fail(c, TSM_E_ARG, "[ADCensus] Set MinMaxDisparity error.");
+    if (cfg->offset < 0) return fail(c, TSM_E_ARG, "[ADCensus] Offset must be positive.");  // ADCensus.cpp:325-326
+    if (cfg->color_model != TSM_COLOR_RGB)
+        return fail(c, TSM_E_UNSUPPORTED, "[ADCensus] HSI colour model is not built yet (SURVEY 8(f) row f1)");
+    if (cfg->roi_matching || cfg->mask_matching)
+        return fail(c, TSM_E_UNSUPPORTED, "[ADCensus] ROI / mask matching modes are not built yet (SURVEY 8(f) row f1)");
+    if (cfg->min_disparity != 0)
+        return fail(c, TSM_E_UNSUPPORTED, "[ADCensus] min_disparity != 0 is not built yet");
+    if (cfg->max_disparity + 1 > 512) return fail(c, TSM_E_UNSUPPORTED, "[ADCensus] more than 512 disparity levels");
+    if (H <= 0 || W <= 0) return fail(c, TSM_E_ARG, "[ADCensus] Image error.");  // ADCensus.cpp:332-333
+    if (cfg->max_disparity > 65535) return fail(c, TSM_E_ARG, "[ADCensus] max_disparity too large");
+    return TSM_OK;
+}
+
+// Host-side LUTs with the host's own expf, in the reference's expression order:
+//   expf(-((float)s / 3.f) / 10.f)  (ADCensus.cpp:435, :518)  and  expf(-(float)n / 30.f).
+int ensure_tables(tsm_ctx* c)
+{
+    if (c->tables_ready) return TSM_OK;
+    float tab_ad[766], tab_c[192];
+    const volatile float lambda_ad = 10.f, lambda_c = 30.f, three = 3.f;
+    for (int s = 0; s < 766; ++s) {
+        volatile float ad = (float)s / three;
+        tab_ad[s] = expf(-ad / lambda_ad);
+    }
+    for (int n = 0; n < 192; ++n) {
+        volatile float cn = (float)n;
+        tab_c[n] = expf(-cn / lambda_c);
+    }
+    const volatile float pi1 = 1.f, pi2 = 3.f, ten = 10.f;
+    c->p1_lo = pi1 / ten;  // ADCensus.cpp:976-977
+    c->p2_lo = pi2 / ten;
+    int rc;
+    if ((rc = ensure(c, c->tab_ad, sizeof tab_ad))) return rc;
+    if ((rc = ensure(c, c->tab_c, sizeof tab_c))) return rc;
+    CK(c, cudaMemcpyAsync(c->tab_ad.p, tab_ad, sizeof tab_ad, cudaMemcpyHostToDevice, c->stream));
+    CK(c, cudaMemcpyAsync(c->tab_c.p, tab_c, sizeof tab_c, cudaMemcpyHostToDevice, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));  // the host arrays are on this stack frame
+    c->tables_ready = true;
+    return TSM_OK;
+}
+
+int ensure_arena(tsm_ctx* c, const tsm_adcensus_config* cfg, int H, int W)
+{
+    int rc = check_cfg(c, cfg, H, W);
+    if (rc) return rc;
+    CK(c, cudaSetDevice(c->device));
+    if ((rc = ensure_tables(c))) return rc;
+    Dims d;
+    d.H = H;
+    d.W = W;
+    d.Dn = cfg->max_disparity - cfg->min_disparity + 1;
+    d.Dp = (d.Dn + 3) & ~3;
+    c->dm = d;
+    c->cfg = *cfg;
+    const size_t npx = d.npx();
+    for (int k = 0; k < 2; ++k) {
+        if ((rc = ensure(c, c->img[k], npx * 3))) return rc;
+        if ((rc = ensure(c, c->img4[k], npx * 4))) return rc;
+        if ((rc = ensure(c, c->census[k], npx * 6 * 8))) return rc;
+        if ((rc = ensure(c, c->arms[k], npx * 4))) return rc;
+        if ((rc = ensure(c, c->wsize[k], npx * 2 * 4))) return rc;
+        if ((rc = ensure(c, c->flags[k], npx))) return rc;
+        if ((rc = ensure(c, c->vol[k], d.ncell() * 4, true))) return rc;
+        if ((rc = ensure(c, c->wta_[k], npx * 4))) return rc;
+        if ((rc = ensure(c, c->disp[k], npx * 4))) return rc;
+    }
+    if ((rc = ensure(c, c->fin, npx * 4))) return rc;
+    if ((rc = ensure(c, c->ftmp, npx * 4))) return rc;
+    if ((rc = ensure(c, c->v_vote, npx * 4))) return rc;
+    if ((rc = ensure(c, c->v_lowcnt, npx * 4))) return rc;
+    if ((rc = ensure(c, c->v_off, npx * 4))) return rc;
+    if ((rc = ensure(c, c->v_mark, npx * 4))) return rc;
+    if ((rc = ensure(c, c->v_start, npx * 4))) return rc;
+    if ((rc = ensure(c, c->v_sums, (npx / 2048 + 2) * 4))) return rc;
+    if ((rc = ensure(c, c->v_flat, npx * kVotingThresh * 2))) return rc;
+    if ((rc = ensure(c, c->e_gray, npx))) return rc;
+    if ((rc = ensure(c, c->e_blur, npx))) return rc;
+    if ((rc = ensure(c, c->e_mag, npx * 4))) return rc;
+    if ((rc = ensure(c, c->e_gx, npx * 2))) return rc;
+    if ((rc = ensure(c, c->e_gy, npx * 2))) return rc;
+    if ((rc = ensure(c, c->e_map, npx))) return rc;
+    if ((rc = ensure(c, c->e_edges, npx))) return rc;
+    if ((rc = ensure(c, c->e_hist, 256 * 4))) return rc;
+    if ((rc = ensure(c, c->e_lut, 256 * 4))) return rc;
+    if ((rc = ensure(c, c->e_changed, 4 * 4))) return rc;
+    return TSM_OK;
+}
+
+ViewPtrs view_ptrs(tsm_ctx* c, int k)
+{
+    ViewPtrs v;
+    v.img = (const uint8_t*)c->img[k].p;
+    v.img4 = (const uint32_t*)c->img4[k].p;
+    v.census = (const uint64_t*)c->census[k].p;
+    v.arms = (const uchar4*)c->arms[k].p;
+    v.wsize = (const float*)c->wsize[k].p;
+    v.flags = (const uint8_t*)c->flags[k].p;
+    v.vol = (float*)c->vol[k].p;
+    return v;
+}
+
+struct ScopedStage {
+    tsm_ctx* c;
+    size_t idx = (size_t)-1;
+    ScopedStage(tsm_ctx* ctx, const char* name) : c(ctx)
+    {
+        if (!c->profiling) return;
+        if (c->timers_used == c->timers.size()) {
+            StageTimer t;
+            t.name = name;
+            cudaEventCreate(&t.beg);
+            cudaEventCreate(&t.end);
+            c->timers.push_back(t);
+        }
+        idx = c->timers_used++;
+        c->timers[idx].name = name;
+        cudaEventRecord(c->timers[idx].beg, c->stream);
+    }
+    ~ScopedStage()
+    {
+        if (idx != (size_t)-1) cudaEventRecord(c->timers[idx].end, c->stream);
+    }
+};
+
+// Runs the stages in `mask` on the current arena, in pipeline order.
+int run_stages(tsm_ctx* c, int mask, int arg)
+{
+    const Dims& d = c->dm;
+    Launcher L{c->stream, &c->launches};
+    ViewPtrs vl = view_ptrs(c, 0), vr = view_ptrs(c, 1);
+    if (c->profiling && mask == TSM_STAGE_ALL) c->timers_used = 0;
+    if (mask & TSM_STAGE_PREP) {
+        ScopedStage s(c, "prep");
+        for (int k = 0; k < 2; ++k)
+            prep_view(L, d, (const uint8_t*)c->img[k].p, (uint32_t*)c->img4[k].p, (uint64_t*)c->census[k].p,
+                      (uchar4*)c->arms[k].p, (float*)c->wsize[k].p, (uint8_t*)c->flags[k].p);
+    }
+    if (mask & TSM_STAGE_INIT) {
+        ScopedStage s(c, "cost_init");
+        cost_init(L, d, vl, vr, (const float*)c->tab_ad.p, (const float*)c->tab_c.p);
+    }
+    if (mask & TSM_STAGE_AGGREGATE) {
+        ScopedStage s(c, "aggregate");
+        aggregate(L, d, vl, vr);
+    }
+    if (mask & TSM_STAGE_SCANLINE) {
+        ScopedStage s(c, "scanline");
+        scanline(L, d, vl, vr, c->p1_lo, c->p2_lo);
+    }
+    if (mask & TSM_STAGE_WTA) {
+        ScopedStage s(c, "wta");
+        wta(L, d, vl.vol, (int32_t*)c->wta_[0].p);
+        wta(L, d, vr.vol, (int32_t*)c->wta_[1].p);
+    }
+    if (mask & TSM_STAGE_LRC) {
+        ScopedStage s(c, "lrc");
+        c->disp_cur = 0;
+        lrc(L, d, (const int32_t*)c->wta_[0].p, (const int32_t*)c->wta_[1].p, (int32_t*)c->disp[0].p);
+    }
+    if (mask & TSM_STAGE_VOTE) {
+        ScopedStage s(c, "region_voting");
+        VoteScratch vs;
+        vs.vote = (int32_t*)c->v_vote.p;
+        vs.lowcnt = (int32_t*)c->v_lowcnt.p;
+        vs.off = (int32_t*)c->v_off.p;
+        vs.mark = (int32_t*)c->v_mark.p;
+        vs.start = (int32_t*)c->v_start.p;
+        vs.blocksums = (int32_t*)c->v_sums.p;
+        vs.flat = (uint16_t*)c->v_flat.p;
+        vs.flat_capacity = c->v_flat.bytes / 2;
+        // multiOptimize: 5 calls, horizontalFirst = F,T,F,T,F (ADCensus.cpp:1382-1387)
+        for (int i = 0; i < 5; ++i) {
+            if (arg >= 0 && arg != i) continue;
+            const bool hf = (i & 1) != 0;
+            region_voting(L, d, (const int32_t*)c->disp[c->disp_cur].p, (int32_t*)c->disp[c->disp_cur ^ 1].p, vl.arms, hf, vs);
+            c->disp_cur ^= 1;
+        }
+    }
+    if (mask & TSM_STAGE_INTERP) {
+        ScopedStage s(c, "interpolation");
+        proper_interpolation(L, d, (const int32_t*)c->disp[c->disp_cur].p, (int32_t*)c->disp[c->disp_cur ^ 1].p, vl.img4);
+        c->disp_cur ^= 1;
+    }
+    if (mask & TSM_STAGE_DISCONT) {
+        ScopedStage s(c, "discontinuity");
+        EdgeScratch es;
+        es.gray = (uint8_t*)c->e_gray.p;
+        es.blurred = (uint8_t*)c->e_blur.p;
+        es.mag = (int32_t*)c->e_mag.p;
+        es.gx = (int16_t*)c->e_gx.p;
+        es.gy = (int16_t*)c->e_gy.p;
+        es.map = (uint8_t*)c->e_map.p;
+        es.edges = (uint8_t*)c->e_edges.p;
+        es.hist = (int32_t*)c->e_hist.p;
+        es.lut = (int32_t*)c->e_lut.p;
+        es.changed = (int32_t*)c->e_changed.p;
+        es.h_changed = nullptr;
+        cudaError_t e = discontinuity_adjustment(L, d, (const int32_t*)c->disp[c->disp_cur].p,
+                                                 (int32_t*)c->disp[c->disp_cur ^ 1].p, vl.vol, es);
+        if (e != cudaSuccess) return fail(c, TSM_E_CUDA, "discontinuity_adjustment: %s", cudaGetErrorString(e));
+        c->disp_cur ^= 1;
+    }
+    if (mask & TSM_STAGE_SUBPIXEL) {
+        ScopedStage s(c, "subpixel");
+        subpixel(L, d, (const int32_t*)c->disp[c->disp_cur].p, vl.vol, (float*)c->ftmp.p, (float*)c->fin.p);
+    }
+    CK(c, cudaGetLastError());
+    return TSM_OK;
+}
+
+int upload_pair_host(tsm_ctx* c, const uint8_t* left, size_t lstep, const uint8_t* right, size_t rstep, int H, int W)
+{
+    const size_t row = (size_t)W * 3, img_bytes = row * H;
+    int rc = ensure_pinned(c, (void**)&c->h_pair, &c->h_pair_bytes, 2 * img_bytes);
+    if (rc) return rc;
+    for (int y = 0; y < H; ++y) {
+        memcpy(c->h_pair + (size_t)y * row, left + (size_t)y * lstep, row);
+        memcpy(c->h_pair + img_bytes + (size_t)y * row, right + (size_t)y * rstep, row);
+    }
+    CK(c, cudaMemcpyAsync(c->img[0].p, c->h_pair, img_bytes, cudaMemcpyHostToDevice, c->stream));
+    CK(c, cudaMemcpyAsync(c->img[1].p, c->h_pair + img_bytes, img_bytes, cudaMemcpyHostToDevice, c->stream));
+    return TSM_OK;
+}
+
+int check_images(tsm_ctx* c, const void* left, size_t lstep, const void* right, size_t rstep, int H, int W)
+{
+    if (!left || !right || H <= 0 || W <= 0) return fail(c, TSM_E_ARG, "[ADCensus] Image error.");
+    if (lstep < (size_t)W * 3 || rstep < (size_t)W * 3) return fail(c, TSM_E_ARG, "[ADCensus] Image error (row stride < 3*W).");
+    return TSM_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int tsm_version(void) { return TSM_VERSION; }
+
+const char* tsm_status_string(int s)
+{
+    switch (s) {
+        case TSM_OK: return "ok";
+        case TSM_E_ARG: return "invalid argument";
+        case TSM_E_CUDA: return "CUDA error";
+        case TSM_E_OOM: return "out of memory";
+        case TSM_E_UNSUPPORTED: return "unsupported configuration";
+        case TSM_E_STATE: return "invalid call sequence";
+        default: return "unknown status";
+    }
+}
+
+const char* tsm_last_error(const tsm_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int tsm_device_count(int* count)
+{
+    if (!count) return TSM_E_ARG;
+    cudaError_t e = cudaGetDeviceCount(count);
+    if (e != cudaSuccess) {
+        *count = 0;
+        return fail(nullptr, TSM_E_CUDA, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+    }
+    return TSM_OK;
+}
+
+int tsm_create_on_stream(int device, void* cuda_stream, tsm_ctx** out)
+{
+    if (!out) return fail(nullptr, TSM_E_ARG, "tsm_create: out is NULL");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fail(nullptr, TSM_E_CUDA, "tsm_create: no CUDA device (%s); this library has no CPU fallback",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    if (device < 0 || device >= n) return fail(nullptr, TSM_E_ARG, "tsm_create: device %d out of range [0,%d)", device, n);
+    e = cudaSetDevice(device);
+    if (e != cudaSuccess) return fail(nullptr, TSM_E_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
+    tsm_ctx* c = new tsm_ctx();
+    c->device = device;
+    if (cuda_stream) {
+        c->stream = (cudaStream_t)cuda_stream;
+    } else {
+        e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+        if (e != cudaSuccess) {
+            delete c;
+            return fail(nullptr, TSM_E_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));
+        }
+        c->own_stream = true;
+    }
+    *out = c;
+    return TSM_OK;
+}
+
+int tsm_create(int device, tsm_ctx** out) { return tsm_create_on_stream(device, nullptr, out); }
+
+void tsm_destroy(tsm_ctx* c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    Buf* all[] = {&c->img[0], &c->img[1], &c->img4[0], &c->img4[1], &c->census[0], &c->census[1], &c->arms[0], &c->arms[1],
+                  &c->wsize[0], &c->wsize[1], &c->flags[0], &c->flags[1], &c->vol[0], &c->vol[1], &c->wta_[0], &c->wta_[1],
+                  &c->disp[0], &c->disp[1], &c->fin, &c->ftmp, &c->v_vote, &c->v_lowcnt, &c->v_off, &c->v_mark, &c->v_start,
+                  &c->v_sums, &c->v_flat, &c->e_gray, &c->e_blur, &c->e_mag, &c->e_gx, &c->e_gy, &c->e_map, &c->e_edges,
+                  &c->e_hist, &c->e_lut, &c->e_changed, &c->tab_ad, &c->tab_c, &c->r_src, &c->r_map1[0], &c->r_map1[1],
+                  &c->r_map2[0], &c->r_map2[1], &c->r_fmap[0][0], &c->r_fmap[0][1], &c->r_fmap[1][0], &c->r_fmap[1][1]};
+    for (Buf* b : all) release(*b);
+    if (c->h_pair) cudaFreeHost(c->h_pair);
+    if (c->h_out) cudaFreeHost(c->h_out);
+    if (c->h_stereo) cudaFreeHost(c->h_stereo);
+    for (auto& t : c->timers) {
+        cudaEventDestroy(t.beg);
+        cudaEventDestroy(t.end);
+    }
+    if (c->own_stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int tsm_synchronize(tsm_ctx* c)
+{
+    if (!c) return TSM_E_ARG;
+    CK(c, cudaStreamSynchronize(c->stream));
+    return TSM_OK;
+}
+
+int tsm_adcensus_compute_device(tsm_ctx* c, const tsm_adcensus_config* cfg, const uint8_t* d_left, const uint8_t* d_right,
+                                int H, int W, float* d_disparity)
+{
+    if (!c) return TSM_E_ARG;
+    if (!d_left || !d_right || !d_disparity) return fail(c, TSM_E_ARG, "[ADCensus] Image error.");
+    int rc = ensure_arena(c, cfg, H, W);
+    if (rc) return rc;
+    const size_t img_bytes = (size_t)H * W * 3;
+    CK(c, cudaMemcpyAsync(c->img[0].p, d_left, img_bytes, cudaMemcpyDeviceToDevice, c->stream));
+    CK(c, cudaMemcpyAsync(c->img[1].p, d_right, img_bytes, cudaMemcpyDeviceToDevice, c->stream));
+    c->have_pair = true;
+    if ((rc = run_stages(c, TSM_STAGE_ALL, -1))) return rc;
+    CK(c, cudaMemcpyAsync(d_disparity, c->fin.p, (size_t)H * W * 4, cudaMemcpyDeviceToDevice, c->stream));
+    return TSM_OK;
+}
+
+int tsm_adcensus_enqueue(tsm_ctx* c, const tsm_adcensus_config* cfg, const uint8_t* left, size_t lstep, const uint8_t* right,
+                         size_t rstep, int H, int W)
+{
+    if (!c) return TSM_E_ARG;
+    int rc = check_images(c, left, lstep, right, rstep, H, W);
+    if (rc) return rc;
+    if (c->pending) return fail(c, TSM_E_STATE, "tsm_adcensus_enqueue: previous pair not waited for");
+    if ((rc = ensure_arena(c, cfg, H, W))) return rc;
+    if ((rc = upload_pair_host(c, left, lstep, right, rstep, H, W))) return rc;
+    c->have_pair = true;
+    if ((rc = run_stages(c, TSM_STAGE_ALL, -1))) return rc;
+    if ((rc = ensure_pinned(c, (void**)&c->h_out, &c->h_out_bytes, (size_t)H * W * 4))) return rc;
+    CK(c, cudaMemcpyAsync(c->h_out, c->fin.p, (size_t)H * W * 4, cudaMemcpyDeviceToHost, c->stream));
+    c->pending = true;
+    return TSM_OK;
+}
+
+int tsm_adcensus_wait(tsm_ctx* c, float* disparity, size_t dstep)
+{
+    if (!c) return TSM_E_ARG;
+    if (!c->pending) return fail(c, TSM_E_STATE, "tsm_adcensus_wait: nothing enqueued");
+    const int H = c->dm.H, W = c->dm.W;
+    if (!disparity || dstep < (size_t)W * 4) return fail(c, TSM_E_ARG, "[ADCensus] disparity buffer error.");
+    c->pending = false;
+    CK(c, cudaStreamSynchronize(c->stream));
+    for (int y = 0; y < H; ++y) memcpy((uint8_t*)disparity + (size_t)y * dstep, c->h_out + (size_t)y * W, (size_t)W * 4);
+    return TSM_OK;
+}
+
+int tsm_adcensus_compute(tsm_ctx* c, const tsm_adcensus_config* cfg, const uint8_t* left, size_t lstep, const uint8_t* right,
+                         size_t rstep, int H, int W, float* disparity, size_t dstep)
+{
+    if (!c) return TSM_E_ARG;
+    if (!disparity || dstep < (size_t)W * 4) return fail(c, TSM_E_ARG, "[ADCensus] disparity buffer error.");
+    int rc = tsm_adcensus_enqueue(c, cfg, left, lstep, right, rstep, H, W);
+    if (rc) return rc;
+    return tsm_adcensus_wait(c, disparity, dstep);
+}
+
+// ------------------------------------------------------------------ rectify
+static int upload_maps(tsm_ctx* c, int slot, const void* m1, const void* m2, int kind, int H, int W)
+{
+    const size_t n = (size_t)H * W;
+    int rc;
+    if ((rc = ensure(c, c->r_map1[slot], n * 4))) return rc;
+    if ((rc = ensure(c, c->r_map2[slot], n * 2))) return rc;
+    if (kind == TSM_MAP_FIXED_16SC2_16UC1) {
+        CK(c, cudaMemcpyAsync(c->r_map1[slot].p, m1, n * 4, cudaMemcpyHostToDevice, c->stream));
+        CK(c, cudaMemcpyAsync(c->r_map2[slot].p, m2, n * 2, cudaMemcpyHostToDevice, c->stream));
+    } else if (kind == TSM_MAP_FLOAT_32FC1_X2) {
+        if ((rc = ensure(c, c->r_fmap[slot][0], n * 4))) return rc;
+        if ((rc = ensure(c, c->r_fmap[slot][1], n * 4))) return rc;
+        CK(c, cudaMemcpyAsync(c->r_fmap[slot][0].p, m1, n * 4, cudaMemcpyHostToDevice, c->stream));
+        CK(c, cudaMemcpyAsync(c->r_fmap[slot][1].p, m2, n * 4, cudaMemcpyHostToDevice, c->stream));
+        Launcher L{c->stream, &c->launches};
+        convert_maps(L, (const float*)c->r_fmap[slot][0].p, (const float*)c->r_fmap[slot][1].p, H, W,
+                     (int16_t*)c->r_map1[slot].p, (uint16_t*)c->r_map2[slot].p);
+    } else {
+        return fail(c, TSM_E_ARG, "[EpipolarRectify] unknown map kind %d", kind);
+    }
+    // pageable host memory: the copies above are staged synchronously by the runtime.
+    return TSM_OK;
+}
+
+int tsm_remap(tsm_ctx* c, const uint8_t* src, size_t sstep, int sH, int sW, const void* map1, const void* map2, int map_kind,
+              int H, int W, uint8_t* dst, size_t dstep)
+{
+    if (!c) return TSM_E_ARG;
+    if (!map1 || !map2) return fail(c, TSM_E_ARG, "Stereo epipolar rectify params is empty, please load it first.");
+    if (!src || sH <= 0 || sW <= 0 || sstep < (size_t)sW * 3) return fail(c, TSM_E_ARG, "Left or Right image is empty.");
+    if (!dst || H <= 0 || W <= 0 || dstep < (size_t)W * 3) return fail(c, TSM_E_ARG, "[EpipolarRectify] destination error.");
+    CK(c, cudaSetDevice(c->device));
+    int rc;
+    tsm_invalidate_maps(c);
+    if ((rc = upload_maps(c, 0, map1, map2, map_kind, H, W))) return rc;
+    if ((rc = ensure(c, c->r_src, sstep * sH + (size_t)W * 3 * H))) return rc;
+    uint8_t* d_src = (uint8_t*)c->r_src.p;
+    uint8_t* d_dst = d_src + sstep * sH;
+    CK(c, cudaMemcpyAsync(d_src, src, sstep * sH, cudaMemcpyHostToDevice, c->stream));
+    Launcher L{c->stream, &c->launches};
+    remap_bilinear(L, d_src, sstep, sH, sW, (const int16_t*)c->r_map1[0].p, (const uint16_t*)c->r_map2[0].p, H, W, d_dst,
+                   (size_t)W * 3);
+    CK(c, cudaGetLastError());
+    CK(c, cudaMemcpy2DAsync(dst, dstep, d_dst, (size_t)W * 3, (size_t)W * 3, H, cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    return TSM_OK;
+}
+
+void tsm_invalidate_maps(tsm_ctx* c)
+{
+    if (!c) return;
+    for (auto& k : c->map_key) k = nullptr;
+    c->map_kind = -1;
+}
+
+static int ensure_map_cache(tsm_ctx* c, const void* m00, const void* m01, const void* m10, const void* m11, int kind, int H, int W)
+{
+    if (!m00 || !m01 || !m10 || !m11)
+        return fail(c, TSM_E_ARG, "Stereo epipolar rectify params is empty, please load it first.");
+    if (c->map_key[0] == m00 && c->map_key[1] == m01 && c->map_key[2] == m10 && c->map_key[3] == m11 && c->map_kind == kind &&
+        c->map_H == H && c->map_W == W)
+        return TSM_OK;
+    int rc;
+    if ((rc = upload_maps(c, 0, m00, m01, kind, H, W))) return rc;
+    if ((rc = upload_maps(c, 1, m10, m11, kind, H, W))) return rc;
+    c->map_key[0] = m00; c->map_key[1] = m01; c->map_key[2] = m10; c->map_key[3] = m11;
+    c->map_kind = kind; c->map_H = H; c->map_W = W;
+    return TSM_OK;
+}
+
+// Uploads the side-by-side frame and remaps both halves into d_left / d_right (packed BGR).
+static int rectify_to_device(tsm_ctx* c, const uint8_t* stereo, size_t sstep, int H, int W, const void* m00, const void* m01,
+                             const void* m10, const void* m11, int kind, uint8_t* d_left, uint8_t* d_right)
+{
+    if (!stereo || H <= 0 || W <= 0 || sstep < (size_t)W * 6) return fail(c, TSM_E_ARG, "Stereo image is empty.");
+    CK(c, cudaSetDevice(c->device));
+    int rc;
+    if ((rc = ensure_map_cache(c, m00, m01, m10, m11, kind, H, W))) return rc;
+    const size_t row = (size_t)W * 6;
+    if ((rc = ensure_pinned(c, (void**)&c->h_stereo, &c->h_stereo_bytes, row * H))) return rc;
+    for (int y = 0; y < H; ++y) memcpy(c->h_stereo + (size_t)y * row, stereo + (size_t)y * sstep, row);
+    if ((rc = ensure(c, c->r_src, row * H + (size_t)W * 3 * H))) return rc;
+    uint8_t* d_src = (uint8_t*)c->r_src.p;
+    CK(c, cudaMemcpyAsync(d_src, c->h_stereo, row * H, cudaMemcpyHostToDevice, c->stream));
+    Launcher L{c->stream, &c->launches};
+    // halves [0,W) and [W,2W) of the frame (EpipolarRectify.cpp:81-82): same rows, column offset 3*W bytes
+    remap_bilinear(L, d_src, row, H, W, (const int16_t*)c->r_map1[0].p, (const uint16_t*)c->r_map2[0].p, H, W, d_left, (size_t)W * 3);
+    remap_bilinear(L, d_src + (size_t)W * 3, row, H, W, (const int16_t*)c->r_map1[1].p, (const uint16_t*)c->r_map2[1].p, H, W,
+                   d_right, (size_t)W * 3);
+    CK(c, cudaGetLastError());
+    return TSM_OK;
+}
+
+int tsm_rectify_stereo(tsm_ctx* c, const uint8_t* stereo, size_t sstep, int H, int W, const void* map00, const void* map01,
+                       const void* map10, const void* map11, int map_kind, uint8_t* left, size_t lstep, uint8_t* right,
+                       size_t rstep)
+{
+    if (!c) return TSM_E_ARG;
+    if (!left || !right || lstep < (size_t)W * 3 || rstep < (size_t)W * 3)
+        return fail(c, TSM_E_ARG, "[EpipolarRectify] destination error.");
+    int rc;
+    const size_t img_bytes = (size_t)H * W * 3;
+    if ((rc = ensure(c, c->img[0], img_bytes))) return rc;
+    if ((rc = ensure(c, c->img[1], img_bytes))) return rc;
+    if ((rc = rectify_to_device(c, stereo, sstep, H, W, map00, map01, map10, map11, map_kind, (uint8_t*)c->img[0].p,
+                                (uint8_t*)c->img[1].p)))
+        return rc;
+    CK(c, cudaMemcpy2DAsync(left, lstep, c->img[0].p, (size_t)W * 3, (size_t)W * 3, H, cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaMemcpy2DAsync(right, rstep, c->img[1].p, (size_t)W * 3, (size_t)W * 3, H, cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    return TSM_OK;
+}
+
+int tsm_rectify_adcensus(tsm_ctx* c, const tsm_adcensus_config* cfg, const uint8_t* stereo, size_t sstep, int H, int W,
+                         const void* map00, const void* map01, const void* map10, const void* map11, int map_kind,
+                         float* disparity, size_t dstep)
+{
+    if (!c) return TSM_E_ARG;
+    if (!disparity || dstep < (size_t)W * 4) return fail(c, TSM_E_ARG, "[ADCensus] disparity buffer error.");
+    int rc = ensure_arena(c, cfg, H, W);
+    if (rc) return rc;
+    if ((rc = rectify_to_device(c, stereo, sstep, H, W, map00, map01, map10, map11, map_kind, (uint8_t*)c->img[0].p,
+                                (uint8_t*)c->img[1].p)))
+        return rc;
+    c->have_pair = true;
+    if ((rc = run_stages(c, TSM_STAGE_ALL, -1))) return rc;
+    if ((rc = ensure_pinned(c, (void**)&c->h_out, &c->h_out_bytes, (size_t)H * W * 4))) return rc;
+    CK(c, cudaMemcpyAsync(c->h_out, c->fin.p, (size_t)H * W * 4, cudaMemcpyDeviceToHost, c->stream));
+    c->pending = true;
+    return tsm_adcensus_wait(c, disparity, dstep);
+}
+
+// --------------------------------------------------------------------- taps
+int tsm_stage_begin(tsm_ctx* c, const tsm_adcensus_config* cfg, const uint8_t* left, size_t lstep, const uint8_t* right,
+                    size_t rstep, int H, int W)
+{
+    if (!c) return TSM_E_ARG;
+    int rc = check_images(c, left, lstep, right, rstep, H, W);
+    if (rc) return rc;
+    if ((rc = ensure_arena(c, cfg, H, W))) return rc;
+    if ((rc = upload_pair_host(c, left, lstep, right, rstep, H, W))) return rc;
+    CK(c, cudaStreamSynchronize(c->stream));
+    c->have_pair = true;
+    c->disp_cur = 0;
+    return TSM_OK;
+}
+
+int tsm_stage_run(tsm_ctx* c, int mask, int arg)
+{
+    if (!c) return TSM_E_ARG;
+    if (!c->have_pair) return fail(c, TSM_E_STATE, "tsm_stage_run: call tsm_stage_begin first");
+    CK(c, cudaSetDevice(c->device));
+    int rc = run_stages(c, mask, arg);
+    if (rc) return rc;
+    CK(c, cudaStreamSynchronize(c->stream));
+    return TSM_OK;
+}
+
+int tsm_volume_pitch(const tsm_ctx* c) { return c ? c->dm.Dp : 0; }
+
+static Buf* tap_buffer(tsm_ctx* c, int id, size_t* bytes)
+{
+    const size_t npx = c->dm.npx();
+    switch (id) {
+        case TSM_BUF_VOL_LEFT: *bytes = c->dm.ncell() * 4; return &c->vol[0];
+        case TSM_BUF_VOL_RIGHT: *bytes = c->dm.ncell() * 4; return &c->vol[1];
+        case TSM_BUF_ARMS_LEFT: *bytes = npx * 4; return &c->arms[0];
+        case TSM_BUF_ARMS_RIGHT: *bytes = npx * 4; return &c->arms[1];
+        case TSM_BUF_WTA_LEFT: *bytes = npx * 4; return &c->wta_[0];
+        case TSM_BUF_WTA_RIGHT: *bytes = npx * 4; return &c->wta_[1];
+        case TSM_BUF_DISP: *bytes = npx * 4; return &c->disp[c->disp_cur];
+        case TSM_BUF_EDGES: *bytes = npx; return &c->e_edges;
+        case TSM_BUF_FINAL: *bytes = npx * 4; return &c->fin;
+        case TSM_BUF_CENSUS_LEFT: *bytes = npx * 48; return &c->census[0];
+        case TSM_BUF_CENSUS_RIGHT: *bytes = npx * 48; return &c->census[1];
+        case TSM_BUF_IMG_LEFT: *bytes = npx * 3; return &c->img[0];
+        case TSM_BUF_IMG_RIGHT: *bytes = npx * 3; return &c->img[1];
+        default: return nullptr;
+    }
+}
+
+size_t tsm_buffer_bytes(const tsm_ctx* c, int buffer)
+{
+    if (!c) return 0;
+    size_t bytes = 0;
+    return tap_buffer(const_cast<tsm_ctx*>(c), buffer, &bytes) ? bytes : 0;
+}
+
+int tsm_tap(tsm_ctx* c, int buffer, void* dst, size_t bytes)
+{
+    if (!c || !dst) return TSM_E_ARG;
+    if (!c->have_pair) return fail(c, TSM_E_STATE, "tsm_tap: nothing computed yet");
+    size_t need = 0;
+    Buf* b = tap_buffer(c, buffer, &need);
+    if (!b || !b->p) return fail(c, TSM_E_ARG, "tsm_tap: unknown buffer %d", buffer);
+    if (bytes != need) return fail(c, TSM_E_ARG, "tsm_tap: buffer %d holds %zu bytes, caller passed %zu", buffer, need, bytes);
+    CK(c, cudaSetDevice(c->device));
+    CK(c, cudaMemcpyAsync(dst, b->p, need, cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    return TSM_OK;
+}
+
+int tsm_poke(tsm_ctx* c, int buffer, const void* src, size_t bytes)
+{
+    if (!c || !src) return TSM_E_ARG;
+    if (!c->have_pair) return fail(c, TSM_E_STATE, "tsm_poke: call tsm_stage_begin first");
+    size_t need = 0;
+    Buf* b = tap_buffer(c, buffer, &need);
+    if (!b || !b->p) return fail(c, TSM_E_ARG, "tsm_poke: unknown buffer %d", buffer);
+    if (bytes != need) return fail(c, TSM_E_ARG, "tsm_poke: buffer %d holds %zu bytes, caller passed %zu", buffer, need, bytes);
+    CK(c, cudaSetDevice(c->device));
+    CK(c, cudaMemcpyAsync(b->p, src, need, cudaMemcpyHostToDevice, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    return TSM_OK;
+}
+
+int tsm_set_profiling(tsm_ctx* c, int enabled)
+{
+    if (!c) return TSM_E_ARG;
+    c->profiling = enabled != 0;
+    c->timers_used = 0;
+    return TSM_OK;
+}
+
+int tsm_get_stage_times(tsm_ctx* c, int* n, const char** names, float* ms)
+{
+    if (!c || !n) return TSM_E_ARG;
+    CK(c, cudaStreamSynchronize(c->stream));
+    int filled = 0;
+    for (size_t i = 0; i < c->timers_used && filled < *n; ++i) {
+        float t = 0.f;
+        if (cudaEventElapsedTime(&t, c->timers[i].beg, c->timers[i].end) != cudaSuccess) continue;
+        if (names) names[filled] = c->timers[i].name;
+        if (ms) ms[filled] = t;
+        ++filled;
+    }
+    *n = filled;
+    return TSM_OK;
+}
+
+long long tsm_launch_count(const tsm_ctx* c) { return c ? c->launches : 0; }
+
+}  // extern "C"

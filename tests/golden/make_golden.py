@@ -1,0 +1,110 @@
+#!/usr/bin/env python
+"""Generates the committed golden vectors under tests/golden/.
+
+Run in the dev container (needs /root/reference and python cv2 4.13.0):
+    python tests/golden/make_golden.py
+
+* pair_0600_320x180.npz  -- the reference's demo pair demo-imgs/0600-{Left,Right}.bmp,
+  area-downscaled x4 with cv2 (inputs only; BGR uint8).
+* ref_0600_320x180_d48.npz -- every stage output of the UNMODIFIED reference
+  source/ADCensus.cpp (oracle/_ref/libadcensus_ref.so, serial-scanline semantics) on that
+  pair, D = 0..48: integer maps in full, float volumes as SHA-256 digests plus strided
+  samples (the full volumes are 11 MB each).
+* ref_synth_96x128_d24.npz -- same for a tiny synthetic pair (synth_v1 seed 7), with the
+  full volumes (small enough) so the CUDA kernels can be checked cell by cell on a box
+  without /root/reference.
+* cv_golden.npz -- cv2 4.13.0 outputs of equalizeHist / blur / Canny / medianBlur / remap /
+  convertMaps on fixed random inputs, for oracle/cvport.c.
+"""
+import hashlib
+import sys
+from pathlib import Path
+
+import cv2
+import numpy as np
+
+ROOT = Path(__file__).resolve().parents[2]
+sys.path.insert(0, str(ROOT))
+import oracle  # noqa: E402
+from tea_stereo_matching_b200.synth import synth_v1  # noqa: E402
+
+OUT = Path(__file__).resolve().parent
+REF_IMGS = Path("/root/reference/demo-imgs")
+
+
+def sha(a: np.ndarray) -> str:
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def stage_dict(st, full_volumes: bool):
+    d = {}
+    for name in ("vol_init", "vol_agg", "vol_scan"):
+        for k in range(2):
+            v = getattr(st, name)[k]
+            d[f"{name}{k}_sha256"] = np.array(sha(v))
+            d[f"{name}{k}_sample"] = v[::7, ::5, :].copy()
+            if full_volumes:
+                d[f"{name}{k}"] = v
+    for k in range(2):
+        d[f"arms{k}"] = np.stack(st.arms[k], axis=2).astype(np.uint8)
+        d[f"wta{k}"] = st.wta[k].astype(np.int16)
+    d["lrc"] = st.lrc.astype(np.int16)
+    for i in range(5):
+        d[f"vote{i}"] = st.vote[i].astype(np.int16)
+    d["interp"] = st.interp.astype(np.int16)
+    d["discont"] = st.discont.astype(np.int16)
+    d["final"] = st.final
+    return d
+
+
+def main():
+    assert cv2.__version__.startswith("4.13"), cv2.__version__
+    oracle.build()
+    ref = oracle.Ref()
+
+    L = cv2.imread(str(REF_IMGS / "0600-Left.bmp"))
+    R = cv2.imread(str(REF_IMGS / "0600-Right.bmp"))
+    Ls = cv2.resize(L, (320, 180), interpolation=cv2.INTER_AREA)
+    Rs = cv2.resize(R, (320, 180), interpolation=cv2.INTER_AREA)
+    np.savez_compressed(OUT / "pair_0600_320x180.npz", left=Ls, right=Rs)
+    st = ref.run(Ls, Rs, 48, serial_scanline=True)
+    np.savez_compressed(OUT / "ref_0600_320x180_d48.npz", max_disparity=48, **stage_dict(st, False))
+
+    sl, sr = synth_v1(96, 128, 24, seed=7)
+    st = ref.run(sl, sr, 24, serial_scanline=True)
+    np.savez_compressed(OUT / "ref_synth_96x128_d24.npz", left=sl, right=sr, max_disparity=24, **stage_dict(st, True))
+
+    # ---- cv2 golden vectors ----
+    rng = np.random.default_rng(20261018)
+    g = {}
+    H, W = 61, 83
+    img_a = rng.integers(0, 256, (H, W), dtype=np.uint8)
+    img_b = cv2.GaussianBlur(rng.integers(0, 256, (H, W)).astype(np.float32), (0, 0), 3).astype(np.uint8)
+    img_c = np.zeros((H, W), np.uint8)
+    img_c[H // 3:, W // 4:] = 140
+    img_c[: H // 2, : W // 2] += rng.integers(0, 60, (H // 2, W // 2), dtype=np.uint8)
+    for name, img in (("a", img_a), ("b", img_b), ("c", img_c)):
+        g[f"u8_{name}"] = img
+        g[f"eq_{name}"] = cv2.equalizeHist(img)
+        g[f"blur_{name}"] = cv2.blur(img, (3, 3))
+        g[f"canny_{name}"] = cv2.Canny(img, 30, 90, apertureSize=3)
+    f = rng.normal(0, 20, (H, W)).astype(np.float32)
+    f[rng.random((H, W)) < 0.2] = -1
+    f[rng.random((H, W)) < 0.1] = -2
+    g["f32"] = f
+    g["median"] = cv2.medianBlur(f, 3)
+    sH, sW = 47, 65
+    src = rng.integers(0, 256, (sH, sW, 3), dtype=np.uint8)
+    mx = rng.uniform(-3, sW + 3, (H, W)).astype(np.float32)
+    my = rng.uniform(-3, sH + 3, (H, W)).astype(np.float32)
+    m1, m2 = cv2.convertMaps(mx, my, cv2.CV_16SC2)
+    g["remap_src"], g["remap_mx"], g["remap_my"], g["remap_m1"], g["remap_m2"] = src, mx, my, m1, m2
+    g["remap_fixed"] = cv2.remap(src, m1, m2, cv2.INTER_LINEAR)
+    g["remap_float"] = cv2.remap(src, mx, my, cv2.INTER_LINEAR)
+    np.savez_compressed(OUT / "cv_golden.npz", **g)
+    for p in sorted(OUT.glob("*.npz")):
+        print(p.name, p.stat().st_size)
+
+
+if __name__ == "__main__":
+    main()
