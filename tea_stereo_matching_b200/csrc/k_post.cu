@@ -352,8 +352,9 @@ __global__ void k_interpolate(const int32_t* __restrict__ disp, int32_t* __restr
     const int own = disp[p];
     if (own >= 0) { out[p] = own; return; }
     const uint32_t pc = img4[p];
-    // occlusion: min over the 16 entries, each initialised to the pixel's own value (:1180, :1211-1216)
-    int occ_min = own;
+    // occlusion: min over the 16 entries, each initialised to the pixel's own value (:1180, :1211-1216),
+    // so a single direction without a hit keeps the pixel at -1
+    int occ_min = INT_MAX;
     // mismatch: running pick (:1222-1231)
     int md = own, mf = -1;
 #pragma unroll 1
