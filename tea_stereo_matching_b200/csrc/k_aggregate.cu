@@ -4,79 +4,240 @@
 // One aggregation1D pass is  out(p) = sum_{j=-a(p)}^{b(p)} in(p + j*r)  along a line
 // (ADCensus.cpp:711-718); after the second pass of an iteration the plane is divided
 // by the cross-window size (:743-749).  The reference adds in fp32 in ascending order;
-// here every (line, d) chain is one thread that walks the line once, keeps a running
-// fp64 prefix sum P and emits  P[o+b+1] - P[o-a]  with a lag of 33 (= max arm), the
-// last 68 prefixes living in a shared-memory ring.  fp64 prefix differences are within
-// ~4e-7 relative of the reference's sequential fp32 sums after all 4 iterations
-// (fp32 prefixes are not).  Each cell is read once and written once per
-// pass, in place, with lanes over d (coalesced 128-byte rows).
+// here every (line, d) chain walks its line once, keeps a running fp64 prefix sum P and
+// emits  P[o+b+1] - P[o-a]  with a lag of 33 (= max arm); the last 72 prefixes live in a
+// shared-memory ring.  fp64 prefix differences stay within ~4e-7 relative of the
+// reference's sequential fp32 sums after all 4 iterations (fp32 prefixes do not;
+// SURVEY 0.6).  Each cell is read once and written once per pass, in place.
 //
-// The division is the reference's own IEEE fp32 divide of the fp32-rounded sum by
-// (float)N (ADCensus.cpp:747).
+// Thread mapping (k_agg_walk): one thread owns TWO adjacent disparities (d, d+1) of one
+// line: 8-byte global accesses, 16-byte ring entries, and the per-step index arithmetic
+// (ring slots, arm decode, pointers) is paid once per two cells.  Lanes run over d, so a
+// warp reads 256 contiguous bytes per step.  Inputs do not depend on the recurrence:
+// they are loaded AGG_PF steps ahead into a register ring, so every warp keeps AGG_PF
+// 256-byte loads in flight and the only loop-carried dependency is the fp64 prefix add.
+// The main loop is unrolled AGG_PF times and the ring length is a multiple of AGG_PF,
+// so ring slots of the pushes are compile-time offsets and the wrap test runs once per
+// AGG_PF steps.
+//
+// Division: the reference divides the fp32 sum by (float)N with an IEEE fp32 divide
+// (ADCensus.cpp:747).  q = fl32( (double)fl32(sum) * fl64(1/N) ) is the same number:
+// the sum has 24 significant bits and N < 2^13, so sum/N is either exactly representable
+// or at least 2^-38 (relative) away from any fp32 rounding boundary, far more than the
+// 2^-52 error of the fp64 product.
 #include "tsm_common.cuh"
 
 namespace tsm {
 
-constexpr int AGG_BLOCK = 128;
-constexpr int AGG_LAG = kMaxArm;       // 33
-constexpr int AGG_RING = 2 * kMaxArm + 2;  // 68 prefixes: P[o-33] .. P[o+34]
-constexpr int AGG_U = 4;               // steps per batch (loads issued together)
+constexpr int AGG_BLOCK = 64;             // threads per CTA, 2 chains each
+constexpr int AGG_LAG = kMaxArm;          // 33
+constexpr int AGG_PF = 8;                 // prefetch distance = unroll factor
+constexpr int AGG_RING = 72;              // >= 68 prefixes, multiple of AGG_PF
+constexpr int AGG_SLOT = AGG_BLOCK * 16;  // bytes between consecutive ring slots
+constexpr int AGG_RING_BYTES = AGG_RING * AGG_SLOT;
+// P[i] lives in slot (i + AGG_P0) mod AGG_RING, chosen so that P[AGG_LAG + 1] (the first
+// prefix written in the main loop) sits on a multiple of AGG_PF.
+constexpr int AGG_P0 = (AGG_PF - (AGG_LAG + 1) % AGG_PF) % AGG_PF;
+static_assert(AGG_RING % AGG_PF == 0 && AGG_RING >= 2 * kMaxArm + 2, "ring geometry");
+static_assert(AGG_PF <= AGG_LAG, "arm prefetch must stay inside the line");
+static_assert(AGG_LAG % AGG_PF == 1, "fill phase assumes LAG = k*PF + 1");
 
+__device__ __forceinline__ void st_ring(uint32_t addr, double a, double b)
+{
+    asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(addr), "d"(a), "d"(b) : "memory");
+}
+__device__ __forceinline__ void ld_ring(uint32_t addr, double& a, double& b)
+{
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(a), "=d"(b) : "r"(addr) : "memory");
+}
+
+// (neg, pos) arm pair of this pass from a packed uchar4 (up, down, left, right).
+template <bool VERT>
+__device__ __forceinline__ void arm_pair(uint32_t packed, int& a, int& b)
+{
+    if (VERT) { a = packed & 0xff; b = (packed >> 8) & 0xff; }
+    else { a = (packed >> 16) & 0xff; b = packed >> 24; }
+}
+
+// Requires len >= AGG_LAG + 1 (host-checked) and AGG_PF positions of over-read slack
+// behind every line end (the volumes are allocated with it).
 template <bool VERT, bool NORM>
 __global__ void __launch_bounds__(AGG_BLOCK)
 k_agg_walk(Dims dm, ViewPtrs v0, ViewPtrs v1, int wsel)
 {
-    extern __shared__ double ring[];  // [AGG_RING][AGG_BLOCK]
+    extern __shared__ __align__(16) unsigned char ring_raw[];  // [AGG_RING][AGG_BLOCK] x double2
+    const ViewPtrs& v = blockIdx.y ? v1 : v0;
+    const int H = dm.H, W = dm.W, Dp = dm.Dp;
+    const int npair = (dm.Dn + 1) >> 1;
+    const int nlines = VERT ? W : H, len = VERT ? H : W;
+    const long long chain = (long long)blockIdx.x * AGG_BLOCK + threadIdx.x;
+    if (chain >= (long long)nlines * npair) return;
+    const int line = (int)(chain / npair), d = 2 * (int)(chain % npair);
+
+    const size_t cstride = VERT ? (size_t)W * Dp : (size_t)Dp;  // floats between consecutive positions
+    const size_t astride = VERT ? (size_t)W : 1;
+    const size_t line_px = VERT ? (size_t)line : (size_t)line * W;
+    const float* in_ptr = v.vol + line_px * Dp + d;
+    float* out_ptr = v.vol + line_px * Dp + d;
+    const uint32_t* arm_line = reinterpret_cast<const uint32_t*>(v.arms) + line_px;
+    const double* inv_line = v.inv_wsize + (size_t)wsel * H * W + line_px;
+    const uint32_t* arm_ptr = arm_line;
+    const double* inv_ptr = inv_line;
+
+    const uint32_t ring0 = (uint32_t)__cvta_generic_to_shared(ring_raw) + threadIdx.x * 16;
+    double P0 = 0.0, P1 = 0.0;
+    st_ring(ring0 + AGG_P0 * AGG_SLOT, 0.0, 0.0);  // P[0]
+
+    // register prefetch rings: values for the next AGG_PF pushes, arms / 1/N for the next AGG_PF outputs
+    float2 vin[AGG_PF];
+    uint32_t av[AGG_PF];
+    double iv[AGG_PF];
+#pragma unroll
+    for (int u = 0; u < AGG_PF; ++u) {
+        vin[u] = *reinterpret_cast<const float2*>(in_ptr + (size_t)u * cstride);
+        av[u] = arm_ptr[(size_t)u * astride];
+        iv[u] = NORM ? inv_ptr[(size_t)u * astride] : 0.0;
+    }
+    in_ptr += (size_t)AGG_PF * cstride;
+    arm_ptr += (size_t)AGG_PF * astride;
+    inv_ptr += (size_t)AGG_PF * astride;
+
+    // output o, given the (possibly virtual) slot byte offset `top` of P[o + 34]
+    auto output = [&](uint32_t top, uint32_t armw, double inv) {
+        int a, b;
+        arm_pair<VERT>(armw, a, b);
+        int s1 = (int)top - (AGG_LAG - b) * AGG_SLOT;      // P[o + b + 1]
+        int s0 = (int)top - (AGG_LAG + 1 + a) * AGG_SLOT;  // P[o - a]
+        s1 += (s1 < 0) ? AGG_RING_BYTES : 0;
+        s0 += (s0 < 0) ? AGG_RING_BYTES : 0;
+        double h0, h1, l0, l1;
+        ld_ring(ring0 + s1, h0, h1);
+        ld_ring(ring0 + s0, l0, l1);
+        float r0 = __double2float_rn(h0 - l0), r1 = __double2float_rn(h1 - l1);
+        if (NORM) {
+            r0 = __double2float_rn((double)r0 * inv);
+            r1 = __double2float_rn((double)r1 * inv);
+        }
+        *reinterpret_cast<float2*>(out_ptr) = make_float2(r0, r1);
+        out_ptr += cstride;
+    };
+
+    // ---- fill: pushes t = 0 .. AGG_LAG-1 (P[1..33] -> slots AGG_P0+1 .. AGG_P0+33, no wrap) ----
+    uint32_t hs = AGG_P0 * AGG_SLOT;  // slot of the newest prefix
+    for (int t = 0; t + AGG_PF <= AGG_LAG; t += AGG_PF) {
+#pragma unroll
+        for (int u = 0; u < AGG_PF; ++u) {
+            const float2 x = vin[u];
+            vin[u] = *reinterpret_cast<const float2*>(in_ptr + (size_t)u * cstride);
+            P0 += (double)x.x;
+            P1 += (double)x.y;
+            hs += AGG_SLOT;
+            st_ring(ring0 + hs, P0, P1);
+        }
+        in_ptr += (size_t)AGG_PF * cstride;
+    }
+    {   // the odd push (t = AGG_LAG - 1); rotate the value ring so that vin[0] is the next value again
+        const float2 x = vin[0];
+#pragma unroll
+        for (int u = 0; u + 1 < AGG_PF; ++u) vin[u] = vin[u + 1];
+        vin[AGG_PF - 1] = *reinterpret_cast<const float2*>(in_ptr);
+        in_ptr += cstride;
+        P0 += (double)x.x;
+        P1 += (double)x.y;
+        hs += AGG_SLOT;
+        st_ring(ring0 + hs, P0, P1);
+    }
+    // newest = P[33] at slot AGG_P0 + 33; the next prefix P[34] goes to a multiple of AGG_PF.
+    uint32_t nx = hs + AGG_SLOT;  // slot of the next prefix to be written, multiple of AGG_PF slots
+    if (nx == AGG_RING_BYTES) nx = 0;
+
+    // ---- main: steps t = AGG_LAG .. len-1: push in[t] -> P[t+1], emit o = t - AGG_LAG ----
+    const int nB = len - AGG_LAG;
+    int done = 0;
+    for (; done + AGG_PF <= nB; done += AGG_PF) {
+#pragma unroll
+        for (int u = 0; u < AGG_PF; ++u) {
+            const float2 x = vin[u];
+            const uint32_t armw = av[u];
+            const double inv = iv[u];
+            vin[u] = *reinterpret_cast<const float2*>(in_ptr + (size_t)u * cstride);
+            av[u] = arm_ptr[(size_t)u * astride];
+            if (NORM) iv[u] = inv_ptr[(size_t)u * astride];
+            P0 += (double)x.x;
+            P1 += (double)x.y;
+            const uint32_t slot = nx + u * AGG_SLOT;
+            st_ring(ring0 + slot, P0, P1);
+            output(slot, armw, inv);
+        }
+        in_ptr += (size_t)AGG_PF * cstride;
+        arm_ptr += (size_t)AGG_PF * astride;
+        inv_ptr += (size_t)AGG_PF * astride;
+        nx += AGG_PF * AGG_SLOT;
+        if (nx == AGG_RING_BYTES) nx = 0;
+    }
+    // ---- tail of main (< AGG_PF steps): operands are already in the register rings ----
+    const int rem = nB - done;
+    uint32_t newest = (nx == 0 ? AGG_RING_BYTES : nx) - AGG_SLOT;  // slot of the newest prefix
+#pragma unroll
+    for (int u = 0; u < AGG_PF; ++u) {
+        if (u < rem) {
+            P0 += (double)vin[u].x;
+            P1 += (double)vin[u].y;
+            newest = nx + u * AGG_SLOT;
+            st_ring(ring0 + newest, P0, P1);
+            output(newest, av[u], iv[u]);
+        }
+    }
+    // ---- drain: o = len-LAG .. len-1.  Newest prefix stays P[len]; the virtual slot of P[o+34]
+    // is (j+1) slots past it.  Only real slots (<= o+b+1 <= len) are read.
+    for (int j = 0; j < AGG_LAG; ++j) {
+        const int o = len - AGG_LAG + j;
+        uint32_t top = newest + (uint32_t)(j + 1) * AGG_SLOT;
+        top -= (top >= AGG_RING_BYTES) ? AGG_RING_BYTES : 0;
+        output(top, arm_line[(size_t)o * astride], NORM ? inv_line[(size_t)o * astride] : 0.0);
+    }
+}
+
+// Generic guarded variant for lines shorter than AGG_LAG + 1 + AGG_PF (tiny images): one
+// chain per thread, 68-entry ring, no prefetch.  Same arithmetic as k_agg_walk.
+constexpr int AGS_BLOCK = 128, AGS_RING = 2 * kMaxArm + 2;
+template <bool VERT, bool NORM>
+__global__ void __launch_bounds__(AGS_BLOCK)
+k_agg_small(Dims dm, ViewPtrs v0, ViewPtrs v1, int wsel)
+{
+    extern __shared__ double sring[];  // [AGS_RING][AGS_BLOCK]
     const ViewPtrs& v = blockIdx.y ? v1 : v0;
     const int H = dm.H, W = dm.W, Dn = dm.Dn, Dp = dm.Dp;
     const int nlines = VERT ? W : H, len = VERT ? H : W;
-    const long long chain = (long long)blockIdx.x * AGG_BLOCK + threadIdx.x;
+    const long long chain = (long long)blockIdx.x * AGS_BLOCK + threadIdx.x;
     if (chain >= (long long)nlines * Dn) return;
     const int line = (int)(chain / Dn), d = (int)(chain % Dn);
-
-    float* __restrict__ cell = v.vol + (VERT ? (size_t)line * Dp : (size_t)line * W * Dp) + d;
-    const size_t cstride = VERT ? (size_t)W * Dp : (size_t)Dp;
-    const uchar4* __restrict__ arm = v.arms + (VERT ? (size_t)line : (size_t)line * W);
-    const size_t astride = VERT ? (size_t)W : 1;
-    const float* __restrict__ wn = v.wsize + (size_t)wsel * H * W + (VERT ? (size_t)line : (size_t)line * W);
-
-    double* my = ring + threadIdx.x;
-    my[0] = 0.0;  // P[0]
+    const size_t line_px = VERT ? (size_t)line : (size_t)line * W;
+    float* cell = v.vol + line_px * Dp + d;
+    const size_t cstride = VERT ? (size_t)W * Dp : (size_t)Dp, astride = VERT ? (size_t)W : 1;
+    const uint32_t* arm = reinterpret_cast<const uint32_t*>(v.arms) + line_px;
+    const double* inv = v.inv_wsize + (size_t)wsel * H * W + line_px;
+    double* my = sring + threadIdx.x;
+    my[0] = 0.0;
     double P = 0.0;
-    int head = 0;  // slot of P[t] at the start of step t
-
-    for (int t0 = 0; t0 < len + AGG_LAG; t0 += AGG_U) {
-        float vin[AGG_U];
-        uchar4 av[AGG_U];
-        float nn[AGG_U];
-#pragma unroll
-        for (int u = 0; u < AGG_U; ++u) {
-            const int t = t0 + u, o = t - AGG_LAG;
-            vin[u] = (t < len) ? cell[(size_t)t * cstride] : 0.f;
-            av[u] = (o >= 0 && o < len) ? arm[(size_t)o * astride] : make_uchar4(0, 0, 0, 0);
-            if (NORM) nn[u] = (o >= 0 && o < len) ? wn[(size_t)o * astride] : 1.f;
+    int head = 0;
+    for (int t = 0; t < len + AGG_LAG; ++t) {
+        const int o = t - AGG_LAG;
+        if (t < len) {
+            P += (double)cell[(size_t)t * cstride];
+            head = (head + 1 == AGS_RING) ? 0 : head + 1;
+            my[head * AGS_BLOCK] = P;
         }
-#pragma unroll
-        for (int u = 0; u < AGG_U; ++u) {
-            const int t = t0 + u, o = t - AGG_LAG;
-            if (t < len) {
-                P += (double)vin[u];
-                head = (head + 1 == AGG_RING) ? 0 : head + 1;  // slot of P[t+1]
-                my[head * AGG_BLOCK] = P;
-            }
-            if (o >= 0 && o < len) {
-                const int a = VERT ? av[u].x : av[u].z, b = VERT ? av[u].y : av[u].w;
-                // newest stored prefix is P[min(t+1,len)] at slot `head`
-                const int newest = (t < len) ? t + 1 : len;
-                int s1 = head - (newest - (o + b + 1));
-                int s0 = head - (newest - (o - a));
-                s1 += (s1 < 0) ? AGG_RING : 0;
-                s0 += (s0 < 0) ? AGG_RING : 0;
-                const double sum = my[s1 * AGG_BLOCK] - my[s0 * AGG_BLOCK];
-                float r = __double2float_rn(sum);
-                if (NORM) r = __fdiv_rn(r, nn[u]);
-                cell[(size_t)o * cstride] = r;
-            }
+        if (o >= 0 && o < len) {
+            int a, b;
+            arm_pair<VERT>(arm[(size_t)o * astride], a, b);
+            const int newest = (t < len) ? t + 1 : len;
+            int s1 = head - (newest - (o + b + 1)), s0 = head - (newest - (o - a));
+            s1 += (s1 < 0) ? AGS_RING : 0;
+            s0 += (s0 < 0) ? AGS_RING : 0;
+            float r = __double2float_rn(my[s1 * AGS_BLOCK] - my[s0 * AGS_BLOCK]);
+            if (NORM) r = __double2float_rn((double)r * inv[(size_t)o * astride]);
+            cell[(size_t)o * cstride] = r;
         }
     }
 }
@@ -84,16 +245,35 @@ k_agg_walk(Dims dm, ViewPtrs v0, ViewPtrs v1, int wsel)
 template <bool VERT, bool NORM>
 static void launch_walk(const Launcher& L, const Dims& d, const ViewPtrs& left, const ViewPtrs& right, int wsel)
 {
-    static bool attr_set = false;
-    const size_t smem = (size_t)AGG_RING * AGG_BLOCK * sizeof(double);
-    if (!attr_set) {
-        cudaFuncSetAttribute(k_agg_walk<VERT, NORM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        attr_set = true;
+    const int len = VERT ? d.H : d.W;
+    if (len >= AGG_LAG + 1 + AGG_PF) {
+        static bool attr_set = false;
+        if (!attr_set) {
+            cudaFuncSetAttribute(k_agg_walk<VERT, NORM>, cudaFuncAttributeMaxDynamicSharedMemorySize, AGG_RING_BYTES);
+            attr_set = true;
+        }
+        const long long chains = (long long)(VERT ? d.W : d.H) * ((d.Dn + 1) / 2);
+        dim3 grid((unsigned)((chains + AGG_BLOCK - 1) / AGG_BLOCK), 2);
+        k_agg_walk<VERT, NORM><<<grid, AGG_BLOCK, AGG_RING_BYTES, L.stream>>>(d, left, right, wsel);
+    } else {
+        static bool attr_set = false;
+        const size_t smem = (size_t)AGS_RING * AGS_BLOCK * sizeof(double);
+        if (!attr_set) {
+            cudaFuncSetAttribute(k_agg_small<VERT, NORM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            attr_set = true;
+        }
+        const long long chains = (long long)(VERT ? d.W : d.H) * d.Dn;
+        dim3 grid((unsigned)((chains + AGS_BLOCK - 1) / AGS_BLOCK), 2);
+        k_agg_small<VERT, NORM><<<grid, AGS_BLOCK, smem, L.stream>>>(d, left, right, wsel);
     }
-    const long long chains = (long long)(VERT ? d.W : d.H) * d.Dn;
-    dim3 grid((unsigned)((chains + AGG_BLOCK - 1) / AGG_BLOCK), 2);
-    k_agg_walk<VERT, NORM><<<grid, AGG_BLOCK, smem, L.stream>>>(d, left, right, wsel);
     L.count(1);
+}
+
+size_t aggregate_overread_floats(const Dims& d)
+{
+    // k_agg_walk prefetches AGG_PF positions past the end of a line; the vertical pass
+    // therefore touches up to AGG_PF rows behind the volume.
+    return (size_t)(AGG_PF + 1) * d.W * d.Dp;
 }
 
 void aggregate(const Launcher& L, const Dims& d, const ViewPtrs& left, const ViewPtrs& right)

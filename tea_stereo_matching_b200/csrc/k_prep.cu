@@ -111,7 +111,7 @@ __global__ void k_arms(const uint32_t* __restrict__ img4, uchar4* __restrict__ a
 // aggregation1D propagates the window size like a cost (ADCensus.cpp:716) starting
 // from all ones (:733): horizontal-first -> N = sum over the vertical arm of the row
 // lengths; vertical-first -> sum over the horizontal arm of the column lengths.
-__global__ void k_wsize(const uchar4* __restrict__ arms, float* __restrict__ wsize, int H, int W)
+__global__ void k_wsize(const uchar4* __restrict__ arms, double* __restrict__ inv_wsize, int H, int W)
 {
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
     if (x >= W || y >= H) return;
@@ -126,8 +126,8 @@ __global__ void k_wsize(const uchar4* __restrict__ arms, float* __restrict__ wsi
         const uchar4 q = arms[p + j];
         nv += q.x + q.y + 1;
     }
-    wsize[p] = (float)nh;
-    wsize[npx + p] = (float)nv;
+    inv_wsize[p] = __drcp_rn((double)nh);
+    inv_wsize[npx + p] = __drcp_rn((double)nv);
 }
 
 // ---- similarity flags ---------------------------------------------------------
@@ -143,8 +143,31 @@ __global__ void k_flags(const uint32_t* __restrict__ img4, uint8_t* __restrict__
     flags[p] = f;
 }
 
-void prep_view(const Launcher& L, const Dims& d, const uint8_t* img, uint32_t* img4, uint64_t* census, uchar4* arms,
-               float* wsize, uint8_t* flags)
+// ---- strided flag tables for the scanline kernels ---------------------------------
+// tflags[plane][y][kTfPad + c] bit k = flag bit `plane` of pixel (y, c + s*32k), 0 outside
+// the image, for c in [-kTfPad, W + kTfPad).  A lane of the scanline warp that handles
+// d = lane + 32k (k = 0..K-1) then gets all its K similarity bits with one 16-bit load.
+__global__ void k_tflags(const uint8_t* __restrict__ flags, uint16_t* __restrict__ tflags, int H, int W, int s, int K)
+{
+    const int Wp = W + 2 * kTfPad;
+    const int cx = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (cx >= Wp) return;
+    const int c = cx - kTfPad;
+    unsigned tv = 0, th = 0;
+    for (int k = 0; k < K; ++k) {
+        const int x = c + s * 32 * k;
+        if (x >= 0 && x < W) {
+            const unsigned f = flags[(size_t)y * W + x];
+            tv |= (f & 1u) << k;
+            th |= ((f >> 1) & 1u) << k;
+        }
+    }
+    tflags[(size_t)y * Wp + cx] = (uint16_t)tv;
+    tflags[(size_t)H * Wp + (size_t)y * Wp + cx] = (uint16_t)th;
+}
+
+void prep_view(const Launcher& L, const Dims& d, int view, const uint8_t* img, uint32_t* img4, uint64_t* census,
+               uchar4* arms, double* inv_wsize, uint8_t* flags, uint16_t* tflags)
 {
     const size_t npx = d.npx();
     k_pack_bgrx<<<(unsigned)((npx + 255) / 256), 256, 0, L.stream>>>(img, img4, npx);
@@ -152,9 +175,12 @@ void prep_view(const Launcher& L, const Dims& d, const uint8_t* img, uint32_t* i
     k_census<<<cg, cb, 0, L.stream>>>(img4, census, d.H, d.W);
     dim3 b(32, 8), g((d.W + 31) / 32, (d.H + 7) / 8);
     k_arms<<<g, b, 0, L.stream>>>(img4, arms, d.H, d.W);
-    k_wsize<<<g, b, 0, L.stream>>>(arms, wsize, d.H, d.W);
+    k_wsize<<<g, b, 0, L.stream>>>(arms, inv_wsize, d.H, d.W);
     k_flags<<<g, b, 0, L.stream>>>(img4, flags, d.H, d.W);
-    L.count(5);
+    // the LEFT image's table is read by the right volume at x - d (s = -1), the right one's at x + d
+    dim3 tg((d.W + 2 * kTfPad + 127) / 128, d.H);
+    k_tflags<<<tg, 128, 0, L.stream>>>(flags, tflags, d.H, d.W, view == 0 ? -1 : 1, (d.Dn + 31) / 32);
+    L.count(6);
 }
 
 }  // namespace tsm

@@ -39,7 +39,8 @@ struct tsm_ctx {
     bool have_pair = false;
 
     // device buffers
-    Buf img[2], img4[2], census[2], arms[2], wsize[2], flags[2], vol[2], wta_[2];
+    Buf img[2], img4[2], census[2], arms[2], wsize[2], flags[2], tflags[2], vol[2], wta_[2];
+    bool stage_mode = false;  // tsm_stage_run: keep every tap-able buffer complete
     Buf disp[2], fin, ftmp;
     Buf v_vote, v_lowcnt, v_off, v_mark, v_start, v_sums, v_flat;
     Buf e_gray, e_blur, e_mag, e_gx, e_gy, e_map, e_edges, e_hist, e_lut, e_changed;
@@ -189,9 +190,10 @@ int ensure_arena(tsm_ctx* c, const tsm_adcensus_config* cfg, int H, int W)
         if ((rc = ensure(c, c->img4[k], npx * 4))) return rc;
         if ((rc = ensure(c, c->census[k], npx * 6 * 8))) return rc;
         if ((rc = ensure(c, c->arms[k], npx * 4))) return rc;
-        if ((rc = ensure(c, c->wsize[k], npx * 2 * 4))) return rc;
+        if ((rc = ensure(c, c->wsize[k], npx * 2 * 8))) return rc;
         if ((rc = ensure(c, c->flags[k], npx))) return rc;
-        if ((rc = ensure(c, c->vol[k], d.ncell() * 4, true))) return rc;
+        if ((rc = ensure(c, c->tflags[k], (size_t)2 * H * (W + 2 * kTfPad) * 2))) return rc;
+        if ((rc = ensure(c, c->vol[k], (d.ncell() + aggregate_overread_floats(d)) * 4, true))) return rc;
         if ((rc = ensure(c, c->wta_[k], npx * 4))) return rc;
         if ((rc = ensure(c, c->disp[k], npx * 4))) return rc;
     }
@@ -224,8 +226,9 @@ ViewPtrs view_ptrs(tsm_ctx* c, int k)
     v.img4 = (const uint32_t*)c->img4[k].p;
     v.census = (const uint64_t*)c->census[k].p;
     v.arms = (const uchar4*)c->arms[k].p;
-    v.wsize = (const float*)c->wsize[k].p;
+    v.inv_wsize = (const double*)c->wsize[k].p;
     v.flags = (const uint8_t*)c->flags[k].p;
+    v.tflags = (const uint16_t*)c->tflags[k].p;
     v.vol = (float*)c->vol[k].p;
     return v;
 }
@@ -263,8 +266,8 @@ int run_stages(tsm_ctx* c, int mask, int arg)
     if (mask & TSM_STAGE_PREP) {
         ScopedStage s(c, "prep");
         for (int k = 0; k < 2; ++k)
-            prep_view(L, d, (const uint8_t*)c->img[k].p, (uint32_t*)c->img4[k].p, (uint64_t*)c->census[k].p,
-                      (uchar4*)c->arms[k].p, (float*)c->wsize[k].p, (uint8_t*)c->flags[k].p);
+            prep_view(L, d, k, (const uint8_t*)c->img[k].p, (uint32_t*)c->img4[k].p, (uint64_t*)c->census[k].p,
+                      (uchar4*)c->arms[k].p, (double*)c->wsize[k].p, (uint8_t*)c->flags[k].p, (uint16_t*)c->tflags[k].p);
     }
     if (mask & TSM_STAGE_INIT) {
         ScopedStage s(c, "cost_init");
@@ -276,9 +279,10 @@ int run_stages(tsm_ctx* c, int mask, int arg)
     }
     if (mask & TSM_STAGE_SCANLINE) {
         ScopedStage s(c, "scanline");
-        scanline(L, d, vl, vr, c->p1_lo, c->p2_lo);
+        // the last (leftward) pass also writes both WTA maps (cost2disparity fused)
+        scanline(L, d, vl, vr, c->p1_lo, c->p2_lo, (int32_t*)c->wta_[0].p, (int32_t*)c->wta_[1].p, c->stage_mode);
     }
-    if (mask & TSM_STAGE_WTA) {
+    if ((mask & TSM_STAGE_WTA) && !(mask & TSM_STAGE_SCANLINE)) {
         ScopedStage s(c, "wta");
         wta(L, d, vl.vol, (int32_t*)c->wta_[0].p);
         wta(L, d, vr.vol, (int32_t*)c->wta_[1].p);
@@ -428,7 +432,7 @@ void tsm_destroy(tsm_ctx* c)
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     Buf* all[] = {&c->img[0], &c->img[1], &c->img4[0], &c->img4[1], &c->census[0], &c->census[1], &c->arms[0], &c->arms[1],
-                  &c->wsize[0], &c->wsize[1], &c->flags[0], &c->flags[1], &c->vol[0], &c->vol[1], &c->wta_[0], &c->wta_[1],
+                  &c->wsize[0], &c->wsize[1], &c->flags[0], &c->flags[1], &c->tflags[0], &c->tflags[1], &c->vol[0], &c->vol[1], &c->wta_[0], &c->wta_[1],
                   &c->disp[0], &c->disp[1], &c->fin, &c->ftmp, &c->v_vote, &c->v_lowcnt, &c->v_off, &c->v_mark, &c->v_start,
                   &c->v_sums, &c->v_flat, &c->e_gray, &c->e_blur, &c->e_mag, &c->e_gx, &c->e_gy, &c->e_map, &c->e_edges,
                   &c->e_hist, &c->e_lut, &c->e_changed, &c->tab_ad, &c->tab_c, &c->r_src, &c->r_map1[0], &c->r_map1[1],
@@ -660,7 +664,9 @@ int tsm_stage_run(tsm_ctx* c, int mask, int arg)
     if (!c) return TSM_E_ARG;
     if (!c->have_pair) return fail(c, TSM_E_STATE, "tsm_stage_run: call tsm_stage_begin first");
     CK(c, cudaSetDevice(c->device));
+    c->stage_mode = true;
     int rc = run_stages(c, mask, arg);
+    c->stage_mode = false;
     if (rc) return rc;
     CK(c, cudaStreamSynchronize(c->stream));
     return TSM_OK;

@@ -94,6 +94,8 @@ def test_scanline_bit_exact(cases):
         for view in range(2):
             got = run.volume(view)
             assert np.array_equal(got, st.vol_scan[view]), (name, view, int((got != st.vol_scan[view]).sum()))
+            # the last pass also emits the WTA map (cost2disparity fused into the leftward pass)
+            assert np.array_equal(run.wta(view), st.wta[view]), (name, "fused wta", view)
         run.close()
 
 
