@@ -31,7 +31,11 @@ namespace tsm {
 
 constexpr int AGG_BLOCK = 64;             // threads per CTA, 2 chains each
 constexpr int AGG_LAG = kMaxArm;          // 33
-constexpr int AGG_PF = 8;                 // prefetch distance = unroll factor
+#ifndef TSM_AGG_PF
+#define TSM_AGG_PF 12
+#endif
+constexpr int AGG_PF = TSM_AGG_PF;        // prefetch distance
+constexpr int AGG_U = 2 * AGG_PF;         // steps per main-loop iteration (two batches)
 constexpr int AGG_RING = 72;              // >= 68 prefixes, multiple of AGG_PF
 constexpr int AGG_SLOT = AGG_BLOCK * 16;  // bytes between consecutive ring slots
 constexpr int AGG_RING_BYTES = AGG_RING * AGG_SLOT;
@@ -40,7 +44,6 @@ constexpr int AGG_RING_BYTES = AGG_RING * AGG_SLOT;
 constexpr int AGG_P0 = (AGG_PF - (AGG_LAG + 1) % AGG_PF) % AGG_PF;
 static_assert(AGG_RING % AGG_PF == 0 && AGG_RING >= 2 * kMaxArm + 2, "ring geometry");
 static_assert(AGG_PF <= AGG_LAG, "arm prefetch must stay inside the line");
-static_assert(AGG_LAG % AGG_PF == 1, "fill phase assumes LAG = k*PF + 1");
 
 __device__ __forceinline__ void st_ring(uint32_t addr, double a, double b)
 {
@@ -49,6 +52,19 @@ __device__ __forceinline__ void st_ring(uint32_t addr, double a, double b)
 __device__ __forceinline__ void ld_ring(uint32_t addr, double& a, double& b)
 {
     asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(a), "=d"(b) : "r"(addr) : "memory");
+}
+
+// Streaming accesses of the cost volume: every cell is touched exactly once per pass, so the
+// lines must not occupy the (small, shared-memory-carved) L1.
+__device__ __forceinline__ float2 ld_stream(const float* p)
+{
+    float2 v;
+    asm volatile("ld.global.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void st_stream(float* p, float a, float b)
+{
+    asm volatile("st.global.L1::no_allocate.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(a), "f"(b) : "memory");
 }
 
 // (neg, pos) arm pair of this pass from a packed uchar4 (up, down, left, right).
@@ -88,20 +104,6 @@ k_agg_walk(Dims dm, ViewPtrs v0, ViewPtrs v1, int wsel)
     double P0 = 0.0, P1 = 0.0;
     st_ring(ring0 + AGG_P0 * AGG_SLOT, 0.0, 0.0);  // P[0]
 
-    // register prefetch rings: values for the next AGG_PF pushes, arms / 1/N for the next AGG_PF outputs
-    float2 vin[AGG_PF];
-    uint32_t av[AGG_PF];
-    double iv[AGG_PF];
-#pragma unroll
-    for (int u = 0; u < AGG_PF; ++u) {
-        vin[u] = *reinterpret_cast<const float2*>(in_ptr + (size_t)u * cstride);
-        av[u] = arm_ptr[(size_t)u * astride];
-        iv[u] = NORM ? inv_ptr[(size_t)u * astride] : 0.0;
-    }
-    in_ptr += (size_t)AGG_PF * cstride;
-    arm_ptr += (size_t)AGG_PF * astride;
-    inv_ptr += (size_t)AGG_PF * astride;
-
     // output o, given the (possibly virtual) slot byte offset `top` of P[o + 34]
     auto output = [&](uint32_t top, uint32_t armw, double inv) {
         int a, b;
@@ -118,74 +120,91 @@ k_agg_walk(Dims dm, ViewPtrs v0, ViewPtrs v1, int wsel)
             r0 = __double2float_rn((double)r0 * inv);
             r1 = __double2float_rn((double)r1 * inv);
         }
-        *reinterpret_cast<float2*>(out_ptr) = make_float2(r0, r1);
+        st_stream(out_ptr, r0, r1);
         out_ptr += cstride;
     };
 
-    // ---- fill: pushes t = 0 .. AGG_LAG-1 (P[1..33] -> slots AGG_P0+1 .. AGG_P0+33, no wrap) ----
+    // ---- fill: pushes t = 0 .. AGG_LAG-1 (P[1..33] -> slots AGG_P0+1 .. AGG_P0+33, no wrap),
+    // values fetched in 3 batches of 11 ----
     uint32_t hs = AGG_P0 * AGG_SLOT;  // slot of the newest prefix
-    for (int t = 0; t + AGG_PF <= AGG_LAG; t += AGG_PF) {
+    static_assert(AGG_LAG == 33, "fill batches");
+#pragma unroll 1
+    for (int g = 0; g < 3; ++g) {
+        float2 tmp[11];
 #pragma unroll
-        for (int u = 0; u < AGG_PF; ++u) {
-            const float2 x = vin[u];
-            vin[u] = *reinterpret_cast<const float2*>(in_ptr + (size_t)u * cstride);
-            P0 += (double)x.x;
-            P1 += (double)x.y;
+        for (int u = 0; u < 11; ++u) tmp[u] = ld_stream(in_ptr + (size_t)u * cstride);
+        in_ptr += (size_t)11 * cstride;
+#pragma unroll
+        for (int u = 0; u < 11; ++u) {
+            P0 += (double)tmp[u].x;
+            P1 += (double)tmp[u].y;
             hs += AGG_SLOT;
             st_ring(ring0 + hs, P0, P1);
         }
-        in_ptr += (size_t)AGG_PF * cstride;
-    }
-    {   // the odd push (t = AGG_LAG - 1); rotate the value ring so that vin[0] is the next value again
-        const float2 x = vin[0];
-#pragma unroll
-        for (int u = 0; u + 1 < AGG_PF; ++u) vin[u] = vin[u + 1];
-        vin[AGG_PF - 1] = *reinterpret_cast<const float2*>(in_ptr);
-        in_ptr += cstride;
-        P0 += (double)x.x;
-        P1 += (double)x.y;
-        hs += AGG_SLOT;
-        st_ring(ring0 + hs, P0, P1);
     }
     // newest = P[33] at slot AGG_P0 + 33; the next prefix P[34] goes to a multiple of AGG_PF.
     uint32_t nx = hs + AGG_SLOT;  // slot of the next prefix to be written, multiple of AGG_PF slots
     if (nx == AGG_RING_BYTES) nx = 0;
 
     // ---- main: steps t = AGG_LAG .. len-1: push in[t] -> P[t+1], emit o = t - AGG_LAG ----
-    const int nB = len - AGG_LAG;
-    int done = 0;
-    for (; done + AGG_PF <= nB; done += AGG_PF) {
+    // Software pipeline in BATCHES of AGG_PF steps with two register buffers: all loads of batch
+    // i+1 are issued back to back, then batch i (whose loads were issued one batch earlier) is
+    // processed.  Batching matters: a warp has only six scoreboard slots and a slot completes
+    // when ALL loads charged to it have landed, so independent loads must be grouped by the
+    // time they are needed, not interleaved one per step.
+    float2 vin[2][AGG_PF];
+    uint32_t av[2][AGG_PF];
+    double iv[2][AGG_PF];
+    auto load_batch = [&](int buf) {
 #pragma unroll
         for (int u = 0; u < AGG_PF; ++u) {
-            const float2 x = vin[u];
-            const uint32_t armw = av[u];
-            const double inv = iv[u];
-            vin[u] = *reinterpret_cast<const float2*>(in_ptr + (size_t)u * cstride);
-            av[u] = arm_ptr[(size_t)u * astride];
-            if (NORM) iv[u] = inv_ptr[(size_t)u * astride];
-            P0 += (double)x.x;
-            P1 += (double)x.y;
-            const uint32_t slot = nx + u * AGG_SLOT;
-            st_ring(ring0 + slot, P0, P1);
-            output(slot, armw, inv);
+            vin[buf][u] = ld_stream(in_ptr + (size_t)u * cstride);
+            av[buf][u] = arm_ptr[(size_t)u * astride];
+            iv[buf][u] = NORM ? inv_ptr[(size_t)u * astride] : 0.0;
         }
         in_ptr += (size_t)AGG_PF * cstride;
         arm_ptr += (size_t)AGG_PF * astride;
         inv_ptr += (size_t)AGG_PF * astride;
+    };
+    auto run_batch = [&](int buf, int nsteps) {  // nsteps == AGG_PF in the steady state
+#pragma unroll
+        for (int u = 0; u < AGG_PF; ++u) {
+            if (u < nsteps) {
+                P0 += (double)vin[buf][u].x;
+                P1 += (double)vin[buf][u].y;
+                const uint32_t slot = nx + u * AGG_SLOT;
+                st_ring(ring0 + slot, P0, P1);
+                output(slot, av[buf][u], iv[buf][u]);
+            }
+        }
+    };
+    const int nB = len - AGG_LAG;
+    uint32_t newest = hs;  // slot of the newest prefix
+    int done = 0;
+    load_batch(0);
+    for (; done + 2 * AGG_PF <= nB; done += 2 * AGG_PF) {
+        load_batch(1);
+        run_batch(0, AGG_PF);
+        nx += AGG_PF * AGG_SLOT;
+        if (nx == AGG_RING_BYTES) nx = 0;
+        load_batch(0);
+        run_batch(1, AGG_PF);
         nx += AGG_PF * AGG_SLOT;
         if (nx == AGG_RING_BYTES) nx = 0;
     }
-    // ---- tail of main (< AGG_PF steps): operands are already in the register rings ----
-    const int rem = nB - done;
-    uint32_t newest = (nx == 0 ? AGG_RING_BYTES : nx) - AGG_SLOT;  // slot of the newest prefix
-#pragma unroll
-    for (int u = 0; u < AGG_PF; ++u) {
-        if (u < rem) {
-            P0 += (double)vin[u].x;
-            P1 += (double)vin[u].y;
-            newest = nx + u * AGG_SLOT;
-            st_ring(ring0 + newest, P0, P1);
-            output(newest, av[u], iv[u]);
+    // tail: fewer than 2*AGG_PF steps left; buffer 0 is loaded (possibly over-reading the slack)
+    {
+        int rem = nB - done;
+        if (rem > AGG_PF) load_batch(1);
+        const int n0 = rem < AGG_PF ? rem : AGG_PF;
+        run_batch(0, n0);
+        if (n0 > 0) newest = nx + (uint32_t)(n0 - 1) * AGG_SLOT;
+        else newest = (nx == 0 ? AGG_RING_BYTES : nx) - AGG_SLOT;
+        if (rem > AGG_PF) {
+            nx += AGG_PF * AGG_SLOT;
+            if (nx == AGG_RING_BYTES) nx = 0;
+            run_batch(1, rem - AGG_PF);
+            newest = nx + (uint32_t)(rem - AGG_PF - 1) * AGG_SLOT;
         }
     }
     // ---- drain: o = len-LAG .. len-1.  Newest prefix stays P[len]; the virtual slot of P[o+34]
@@ -246,7 +265,7 @@ template <bool VERT, bool NORM>
 static void launch_walk(const Launcher& L, const Dims& d, const ViewPtrs& left, const ViewPtrs& right, int wsel)
 {
     const int len = VERT ? d.H : d.W;
-    if (len >= AGG_LAG + 1 + AGG_PF) {
+    if (len >= AGG_LAG + 1 + AGG_U) {
         static bool attr_set = false;
         if (!attr_set) {
             cudaFuncSetAttribute(k_agg_walk<VERT, NORM>, cudaFuncAttributeMaxDynamicSharedMemorySize, AGG_RING_BYTES);

@@ -30,7 +30,8 @@
 namespace tsm {
 
 constexpr int SCAN_WARPS = 4;
-constexpr int SCAN_PF = 4;  // prefetch distance = unroll factor
+constexpr int SCAN_PF = 4;           // prefetch distance
+constexpr int SCAN_U = 2 * SCAN_PF;  // unroll factor = length of the register rings
 
 struct ScanParams {
     float p1[3];
@@ -146,8 +147,17 @@ __device__ __forceinline__ void scan_dir(float (&prev)[K], float* __restrict__ v
     float* dst = vol + ((size_t)y0 * W + x0) * Dp;
     int32_t* wdst = WTA ? wta_out + (size_t)y0 * W + x0 : nullptr;
 
-    float cur[SCAN_PF][K];
-    unsigned tf[SCAN_PF], own[SCAN_PF];
+    // Register rings of 2*SCAN_PF entries: step i consumes entry i mod 2PF and refills entry
+    // (i + PF) mod 2PF (consumed PF steps earlier), so a load never targets a live register.
+    float cur[SCAN_U][K];
+    unsigned tf[SCAN_U], own[SCAN_U];
+#pragma unroll
+    for (int u = 0; u < SCAN_U; ++u) {
+        tf[u] = 0u;
+        own[u] = 0u;
+#pragma unroll
+        for (int k = 0; k < K; ++k) cur[u][k] = 0.f;
+    }
 #pragma unroll
     for (int u = 0; u < SCAN_PF; ++u) {
         if (u < count) load_step<K>(cur[u], tf[u], own[u], nxt, lane, sgn, ownbit, lastvalid);
@@ -155,16 +165,17 @@ __device__ __forceinline__ void scan_dir(float (&prev)[K], float* __restrict__ v
         nxt.own += fstep;
         nxt.tf += tstep;
     }
-    for (int i0 = 0; i0 < count; i0 += SCAN_PF) {
+    for (int i0 = 0; i0 < count; i0 += SCAN_U) {
 #pragma unroll
-        for (int u = 0; u < SCAN_PF; ++u) {
+        for (int u = 0; u < SCAN_U; ++u) {
             const int i = i0 + u;
             if (i < count) {
-                const bool changed = scan_step<K>(prev, cur[u], tf[u], own[u], lane, sp);
-                if (i + SCAN_PF < count) load_step<K>(cur[u], tf[u], own[u], nxt, lane, sgn, ownbit, lastvalid);
+                const int w = (u + SCAN_PF) % SCAN_U;
+                if (i + SCAN_PF < count) load_step<K>(cur[w], tf[w], own[w], nxt, lane, sgn, ownbit, lastvalid);
                 nxt.src += vstep;
                 nxt.own += fstep;
                 nxt.tf += tstep;
+                const bool changed = scan_step<K>(prev, cur[u], tf[u], own[u], lane, sp);
                 if (changed && do_store) store_vec<K>(dst, prev, lane, lastvalid);
                 dst += vstep;
                 if (WTA) {
