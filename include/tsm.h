@@ -143,7 +143,7 @@ enum tsm_stage {
     TSM_STAGE_ALL = (1 << 10) - 1
 };
 enum tsm_buffer {
-    TSM_BUF_VOL_LEFT = 0,  /* float [H][W][Dp], Dp = tsm_volume_pitch() */
+    TSM_BUF_VOL_LEFT = 0,  /* float [H][W][Dn] dense (the device keeps a split, 128-byte aligned layout) */
     TSM_BUF_VOL_RIGHT = 1,
     TSM_BUF_ARMS_LEFT = 2, /* uint8 [H][W][4] = up, down, left, right */
     TSM_BUF_ARMS_RIGHT = 3,
@@ -160,7 +160,7 @@ enum tsm_buffer {
 int tsm_stage_begin(tsm_ctx* ctx, const tsm_adcensus_config* cfg,
                     const uint8_t* left, size_t lstep, const uint8_t* right, size_t rstep, int H, int W);
 int tsm_stage_run(tsm_ctx* ctx, int mask, int arg);
-int tsm_volume_pitch(const tsm_ctx* ctx); /* Dp, floats per pixel in the volumes (>= Dn) */
+int tsm_volume_pitch(const tsm_ctx* ctx); /* floats per pixel of a tapped volume (= Dn) */
 size_t tsm_buffer_bytes(const tsm_ctx* ctx, int buffer);
 int tsm_tap(tsm_ctx* ctx, int buffer, void* dst, size_t bytes);
 int tsm_poke(tsm_ctx* ctx, int buffer, const void* src, size_t bytes);

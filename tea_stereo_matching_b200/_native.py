@@ -12,7 +12,7 @@ import subprocess
 from pathlib import Path
 
 PKG_DIR = Path(__file__).resolve().parent
-LIB_PATH = PKG_DIR / "libtsm_b200.so"
+LIB_PATH = Path(os.environ.get("TSM_LIB", PKG_DIR / "libtsm_b200.so"))  # TSM_LIB: kernel experiments only
 CSRC_DIR = PKG_DIR / "csrc"
 
 TSM_OK, TSM_E_ARG, TSM_E_CUDA, TSM_E_OOM, TSM_E_UNSUPPORTED, TSM_E_STATE = range(6)

@@ -29,7 +29,11 @@
 
 namespace tsm {
 
-constexpr int AGG_BLOCK = 64;             // threads per CTA, 2 chains each
+#ifndef TSM_AGG_NC
+#define TSM_AGG_NC 2
+#endif
+constexpr int AGG_NC = TSM_AGG_NC;        // adjacent disparities (chains) per thread: 1 or 2
+constexpr int AGG_BLOCK = 128 / AGG_NC;   // threads per CTA
 constexpr int AGG_LAG = kMaxArm;          // 33
 #ifndef TSM_AGG_PF
 #define TSM_AGG_PF 12
@@ -37,7 +41,7 @@ constexpr int AGG_LAG = kMaxArm;          // 33
 constexpr int AGG_PF = TSM_AGG_PF;        // prefetch distance
 constexpr int AGG_U = 2 * AGG_PF;         // steps per main-loop iteration (two batches)
 constexpr int AGG_RING = 72;              // >= 68 prefixes, multiple of AGG_PF
-constexpr int AGG_SLOT = AGG_BLOCK * 16;  // bytes between consecutive ring slots
+constexpr int AGG_SLOT = AGG_BLOCK * 8 * AGG_NC;  // bytes between consecutive ring slots
 constexpr int AGG_RING_BYTES = AGG_RING * AGG_SLOT;
 // P[i] lives in slot (i + AGG_P0) mod AGG_RING, chosen so that P[AGG_LAG + 1] (the first
 // prefix written in the main loop) sits on a multiple of AGG_PF.
@@ -47,11 +51,13 @@ static_assert(AGG_PF <= AGG_LAG, "arm prefetch must stay inside the line");
 
 __device__ __forceinline__ void st_ring(uint32_t addr, double a, double b)
 {
-    asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(addr), "d"(a), "d"(b) : "memory");
+    if (AGG_NC == 2) asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(addr), "d"(a), "d"(b) : "memory");
+    else asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(a) : "memory");
 }
 __device__ __forceinline__ void ld_ring(uint32_t addr, double& a, double& b)
 {
-    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(a), "=d"(b) : "r"(addr) : "memory");
+    if (AGG_NC == 2) asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(a), "=d"(b) : "r"(addr) : "memory");
+    else { asm volatile("ld.shared.f64 %0, [%1];" : "=d"(a) : "r"(addr) : "memory"); b = 0.0; }
 }
 
 // Streaming accesses of the cost volume: every cell is touched exactly once per pass, so the
@@ -59,12 +65,14 @@ __device__ __forceinline__ void ld_ring(uint32_t addr, double& a, double& b)
 __device__ __forceinline__ float2 ld_stream(const float* p)
 {
     float2 v;
-    asm volatile("ld.global.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+    if (AGG_NC == 2) asm volatile("ld.global.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+    else { asm volatile("ld.global.L1::no_allocate.f32 %0, [%1];" : "=f"(v.x) : "l"(p)); v.y = 0.f; }
     return v;
 }
 __device__ __forceinline__ void st_stream(float* p, float a, float b)
 {
-    asm volatile("st.global.L1::no_allocate.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(a), "f"(b) : "memory");
+    if (AGG_NC == 2) asm volatile("st.global.L1::no_allocate.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(a), "f"(b) : "memory");
+    else asm volatile("st.global.L1::no_allocate.f32 [%0], %1;" ::"l"(p), "f"(a) : "memory");
 }
 
 // (neg, pos) arm pair of this pass from a packed uchar4 (up, down, left, right).
@@ -79,28 +87,37 @@ __device__ __forceinline__ void arm_pair(uint32_t packed, int& a, int& b)
 // behind every line end (the volumes are allocated with it).
 template <bool VERT, bool NORM>
 __global__ void __launch_bounds__(AGG_BLOCK)
-k_agg_walk(Dims dm, ViewPtrs v0, ViewPtrs v1, int wsel)
+k_agg_walk(Dims dm, ViewPtrs v0, ViewPtrs v1, int wsel, int nb_main)
 {
     extern __shared__ __align__(16) unsigned char ring_raw[];  // [AGG_RING][AGG_BLOCK] x double2
     const ViewPtrs& v = blockIdx.y ? v1 : v0;
-    const int H = dm.H, W = dm.W, Dp = dm.Dp;
-    const int npair = (dm.Dn + 1) >> 1;
+    const int H = dm.H, W = dm.W;
     const int nlines = VERT ? W : H, len = VERT ? H : W;
-    const long long chain = (long long)blockIdx.x * AGG_BLOCK + threadIdx.x;
+    // chains of the 128-byte aligned main part first, then (blocks >= nb_main) those of the tail part
+    float* part;
+    int pitch, npair;
+    long long chain;
+    if ((int)blockIdx.x < nb_main) {
+        part = v.vol.main; pitch = dm.Dm; npair = dm.Dm / AGG_NC;
+        chain = (long long)blockIdx.x * AGG_BLOCK + threadIdx.x;
+    } else {
+        part = v.vol.tail; pitch = dm.Rp; npair = (dm.tail() + AGG_NC - 1) / AGG_NC;
+        chain = (long long)((int)blockIdx.x - nb_main) * AGG_BLOCK + threadIdx.x;
+    }
     if (chain >= (long long)nlines * npair) return;
-    const int line = (int)(chain / npair), d = 2 * (int)(chain % npair);
+    const int line = (int)(chain / npair), d = AGG_NC * (int)(chain % npair);
 
-    const size_t cstride = VERT ? (size_t)W * Dp : (size_t)Dp;  // floats between consecutive positions
+    const size_t cstride = VERT ? (size_t)W * pitch : (size_t)pitch;  // floats between consecutive positions
     const size_t astride = VERT ? (size_t)W : 1;
     const size_t line_px = VERT ? (size_t)line : (size_t)line * W;
-    const float* in_ptr = v.vol + line_px * Dp + d;
-    float* out_ptr = v.vol + line_px * Dp + d;
+    const float* in_ptr = part + line_px * pitch + d;
+    float* out_ptr = part + line_px * pitch + d;
     const uint32_t* arm_line = reinterpret_cast<const uint32_t*>(v.arms) + line_px;
     const double* inv_line = v.inv_wsize + (size_t)wsel * H * W + line_px;
     const uint32_t* arm_ptr = arm_line;
     const double* inv_ptr = inv_line;
 
-    const uint32_t ring0 = (uint32_t)__cvta_generic_to_shared(ring_raw) + threadIdx.x * 16;
+    const uint32_t ring0 = (uint32_t)__cvta_generic_to_shared(ring_raw) + threadIdx.x * (8 * AGG_NC);
     double P0 = 0.0, P1 = 0.0;
     st_ring(ring0 + AGG_P0 * AGG_SLOT, 0.0, 0.0);  // P[0]
 
@@ -222,18 +239,27 @@ k_agg_walk(Dims dm, ViewPtrs v0, ViewPtrs v1, int wsel)
 constexpr int AGS_BLOCK = 128, AGS_RING = 2 * kMaxArm + 2;
 template <bool VERT, bool NORM>
 __global__ void __launch_bounds__(AGS_BLOCK)
-k_agg_small(Dims dm, ViewPtrs v0, ViewPtrs v1, int wsel)
+k_agg_small(Dims dm, ViewPtrs v0, ViewPtrs v1, int wsel, int nb_main)
 {
     extern __shared__ double sring[];  // [AGS_RING][AGS_BLOCK]
     const ViewPtrs& v = blockIdx.y ? v1 : v0;
-    const int H = dm.H, W = dm.W, Dn = dm.Dn, Dp = dm.Dp;
+    const int H = dm.H, W = dm.W;
     const int nlines = VERT ? W : H, len = VERT ? H : W;
-    const long long chain = (long long)blockIdx.x * AGS_BLOCK + threadIdx.x;
-    if (chain >= (long long)nlines * Dn) return;
-    const int line = (int)(chain / Dn), d = (int)(chain % Dn);
+    float* part;
+    int pitch, nd;
+    long long chain;
+    if ((int)blockIdx.x < nb_main) {
+        part = v.vol.main; pitch = dm.Dm; nd = dm.Dm;
+        chain = (long long)blockIdx.x * AGS_BLOCK + threadIdx.x;
+    } else {
+        part = v.vol.tail; pitch = dm.Rp; nd = dm.tail();
+        chain = (long long)((int)blockIdx.x - nb_main) * AGS_BLOCK + threadIdx.x;
+    }
+    if (chain >= (long long)nlines * nd) return;
+    const int line = (int)(chain / nd), d = (int)(chain % nd);
     const size_t line_px = VERT ? (size_t)line : (size_t)line * W;
-    float* cell = v.vol + line_px * Dp + d;
-    const size_t cstride = VERT ? (size_t)W * Dp : (size_t)Dp, astride = VERT ? (size_t)W : 1;
+    float* cell = part + line_px * pitch + d;
+    const size_t cstride = VERT ? (size_t)W * pitch : (size_t)pitch, astride = VERT ? (size_t)W : 1;
     const uint32_t* arm = reinterpret_cast<const uint32_t*>(v.arms) + line_px;
     const double* inv = v.inv_wsize + (size_t)wsel * H * W + line_px;
     double* my = sring + threadIdx.x;
@@ -271,9 +297,11 @@ static void launch_walk(const Launcher& L, const Dims& d, const ViewPtrs& left, 
             cudaFuncSetAttribute(k_agg_walk<VERT, NORM>, cudaFuncAttributeMaxDynamicSharedMemorySize, AGG_RING_BYTES);
             attr_set = true;
         }
-        const long long chains = (long long)(VERT ? d.W : d.H) * ((d.Dn + 1) / 2);
-        dim3 grid((unsigned)((chains + AGG_BLOCK - 1) / AGG_BLOCK), 2);
-        k_agg_walk<VERT, NORM><<<grid, AGG_BLOCK, AGG_RING_BYTES, L.stream>>>(d, left, right, wsel);
+        const long long nl = VERT ? d.W : d.H;
+        const int nb_main = (int)((nl * (d.Dm / AGG_NC) + AGG_BLOCK - 1) / AGG_BLOCK);
+        const int nb_tail = (int)((nl * ((d.tail() + AGG_NC - 1) / AGG_NC) + AGG_BLOCK - 1) / AGG_BLOCK);
+        dim3 grid((unsigned)(nb_main + nb_tail), 2);
+        k_agg_walk<VERT, NORM><<<grid, AGG_BLOCK, AGG_RING_BYTES, L.stream>>>(d, left, right, wsel, nb_main);
     } else {
         static bool attr_set = false;
         const size_t smem = (size_t)AGS_RING * AGS_BLOCK * sizeof(double);
@@ -281,18 +309,20 @@ static void launch_walk(const Launcher& L, const Dims& d, const ViewPtrs& left, 
             cudaFuncSetAttribute(k_agg_small<VERT, NORM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             attr_set = true;
         }
-        const long long chains = (long long)(VERT ? d.W : d.H) * d.Dn;
-        dim3 grid((unsigned)((chains + AGS_BLOCK - 1) / AGS_BLOCK), 2);
-        k_agg_small<VERT, NORM><<<grid, AGS_BLOCK, smem, L.stream>>>(d, left, right, wsel);
+        const long long nl = VERT ? d.W : d.H;
+        const int nb_main = (int)((nl * d.Dm + AGS_BLOCK - 1) / AGS_BLOCK);
+        const int nb_tail = (int)((nl * d.tail() + AGS_BLOCK - 1) / AGS_BLOCK);
+        dim3 grid((unsigned)(nb_main + nb_tail), 2);
+        k_agg_small<VERT, NORM><<<grid, AGS_BLOCK, smem, L.stream>>>(d, left, right, wsel, nb_main);
     }
     L.count(1);
 }
 
 size_t aggregate_overread_floats(const Dims& d)
 {
-    // k_agg_walk prefetches AGG_PF positions past the end of a line; the vertical pass
-    // therefore touches up to AGG_PF rows behind the volume.
-    return (size_t)(AGG_PF + 1) * d.W * d.Dp;
+    // k_agg_walk prefetches up to 2*AGG_PF positions past the end of a line; the vertical pass
+    // therefore touches that many rows behind each part of the volume (pitch <= max(Dm, Rp)).
+    return (size_t)(2 * AGG_PF + 1) * d.W * (size_t)(d.Dm > d.Rp ? d.Dm : d.Rp);
 }
 
 void aggregate(const Launcher& L, const Dims& d, const ViewPtrs& left, const ViewPtrs& right)

@@ -33,20 +33,21 @@ k_cost_init(Dims dm, ViewPtrs vl, ViewPtrs vr, const float* __restrict__ g_tab_a
     const int view = blockIdx.z;
     const int y = blockIdx.y;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int H = dm.H, W = dm.W, Dn = dm.Dn, Dp = dm.Dp;
+    const int H = dm.H, W = dm.W, Dn = dm.Dn;
     const size_t npx = (size_t)H * W;
     const size_t row = (size_t)y * W;
     // fixed view = the view whose pixel stays at x; moving view is sampled at x -/+ d.
     const ViewPtrs& vf = view == 0 ? vl : vr;
     const ViewPtrs& vm = view == 0 ? vr : vl;
     const int sgn = view == 0 ? -1 : 1;
-    float* __restrict__ vol = vf.vol;
+    const Vol vol = vf.vol;
     const bool yout = (y - kCensusH / 2 < 0) || (y + kCensusH / 2 >= H);
     const int hw = kCensusW / 2;
 
     const int xbeg = blockIdx.x * COST_PIX_PER_BLOCK;
     for (int x = xbeg + warp; x < min(xbeg + COST_PIX_PER_BLOCK, W); x += COST_WARPS) {
-        float* out = vol + (row + x) * Dp;
+        float* out_main = vol.main + (row + x) * dm.Dm;
+        float* out_tail = vol.tail + (row + x) * dm.Rp - dm.Dm;
         const bool fout = yout || (x - hw < 0) || (x + hw >= W);
         uint64_t fl[3], fg[3];
         uint32_t fpix = 0;
@@ -73,7 +74,7 @@ k_cost_init(Dims dm, ViewPtrs vl, ViewPtrs vr, const float* __restrict__ g_tab_a
                 }
                 cost = __fsub_rn(__fsub_rn(2.f, tab_ad[ad3]), tab_c[cen]);
             }
-            out[d] = cost;
+            (d < dm.Dm ? out_main : out_tail)[d] = cost;
         }
     }
 }

@@ -14,16 +14,17 @@ namespace tsm {
 
 // =========================================================================== a9
 // cost2disparity (ADCensus.cpp:1394-1413): first strict minimum over d = 0..Dn-1.
-__global__ void __launch_bounds__(256) k_wta(const float* __restrict__ vol, int32_t* __restrict__ disp, size_t npx, int Dn, int Dp)
+__global__ void __launch_bounds__(256) k_wta(Vol vol, Dims dm, int32_t* __restrict__ disp)
 {
+    const size_t npx = dm.npx();
+    const int Dn = dm.Dn;
     const size_t p = (size_t)blockIdx.x * 8 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (p >= npx) return;
-    const float* c = vol + p * Dp;
     float best = FLT_MAX;
     int bd = INT_MAX;
     for (int d = lane; d < Dn; d += 32) {
-        const float v = c[d];
+        const float v = *cell_ptr(vol, dm, p, d);
         if (best > v) { best = v; bd = d; }
     }
 #pragma unroll
@@ -35,10 +36,35 @@ __global__ void __launch_bounds__(256) k_wta(const float* __restrict__ vol, int3
     if (lane == 0) disp[p] = bd == INT_MAX ? 0 : bd;
 }
 
-void wta(const Launcher& L, const Dims& d, const float* vol, int32_t* disp)
+void wta(const Launcher& L, const Dims& d, const Vol& vol, int32_t* disp)
 {
     const size_t npx = d.npx();
-    k_wta<<<(unsigned)((npx + 7) / 8), 256, 0, L.stream>>>(vol, disp, npx, d.Dn, d.Dp);
+    k_wta<<<(unsigned)((npx + 7) / 8), 256, 0, L.stream>>>(vol, d, disp);
+    L.count(1);
+}
+
+// ---- dense <-> split volume copies for the parity taps ----
+__global__ void k_volume_copy(Vol vol, Dims dm, float* dense, int to_dense)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t n = dm.npx() * dm.Dn;
+    if (i >= n) return;
+    const size_t p = i / dm.Dn;
+    const int d = (int)(i % dm.Dn);
+    float* c = cell_ptr(vol, dm, p, d);
+    if (to_dense) dense[i] = *c;
+    else *c = dense[i];
+}
+void volume_gather(const Launcher& L, const Dims& d, const Vol& vol, float* dense)
+{
+    const size_t n = d.npx() * d.Dn;
+    k_volume_copy<<<(unsigned)((n + 255) / 256), 256, 0, L.stream>>>(vol, d, dense, 1);
+    L.count(1);
+}
+void volume_scatter(const Launcher& L, const Dims& d, const float* dense, const Vol& vol)
+{
+    const size_t n = d.npx() * d.Dn;
+    k_volume_copy<<<(unsigned)((n + 255) / 256), 256, 0, L.stream>>>(vol, d, const_cast<float*>(dense), 0);
     L.count(1);
 }
 
@@ -560,8 +586,9 @@ __constant__ int c_adjH[8] = {-1, 1, -1, 1, -1, 1, 0, 0};
 __constant__ int c_adjW[8] = {-1, 1, 0, 0, 1, -1, -1, 1};
 
 __global__ void k_discont_adjust(const int32_t* __restrict__ disp, int32_t* __restrict__ out, const uint8_t* __restrict__ E,
-                                 const float* __restrict__ vol, int H, int W, int Dp)
+                                 Vol vol, Dims dm)
 {
+    const int H = dm.H, W = dm.W;
     const int w = blockIdx.x * blockDim.x + threadIdx.x, h = blockIdx.y * blockDim.y + threadIdx.y;
     if (w >= W || h >= H) return;
     const size_t p = (size_t)h * W + w;
@@ -580,12 +607,12 @@ __global__ void k_discont_adjust(const int32_t* __restrict__ disp, int32_t* __re
         }
         if (dir != -1 && d >= 0) {
             dir = (dir + 4) % 8;
-            float cost = vol[p * Dp + d];
+            float cost = *cell_ptr(vol, dm, p, d);
             const size_t p1 = (size_t)(h + c_adjH[dir]) * W + (w + c_adjW[dir]);
             const size_t p2 = (size_t)(h + c_adjH[dir + 1]) * W + (w + c_adjW[dir + 1]);
             const int d1 = disp[p1], d2 = disp[p2];
-            const float c1 = d1 >= 0 ? vol[p1 * Dp + d1] : -1.f;
-            const float c2 = d2 >= 0 ? vol[p2 * Dp + d2] : -1.f;
+            const float c1 = d1 >= 0 ? *cell_ptr(vol, dm, p1, d1) : -1.f;
+            const float c2 = d2 >= 0 ? *cell_ptr(vol, dm, p2, d2) : -1.f;
             if (c1 != -1.f && c1 < cost) { d = d1; cost = c1; }
             if (c2 != -1.f && c2 < cost) { d = d2; }
         }
@@ -594,7 +621,7 @@ __global__ void k_discont_adjust(const int32_t* __restrict__ disp, int32_t* __re
 }
 
 cudaError_t discontinuity_adjustment(const Launcher& L, const Dims& d, const int32_t* disp_in, int32_t* disp_out,
-                                     const float* vol_left, const EdgeScratch& s)
+                                     const Vol& vol_left, const EdgeScratch& s)
 {
     const size_t npx = d.npx();
     dim3 b(32, 8), g((d.W + 31) / 32, (d.H + 7) / 8);
@@ -625,7 +652,7 @@ cudaError_t discontinuity_adjustment(const Launcher& L, const Dims& d, const int
         L.count(1);
     }
     k_edges_finalize<<<(unsigned)((npx + 255) / 256), 256, 0, L.stream>>>(s.map, s.edges, npx);
-    k_discont_adjust<<<g, b, 0, L.stream>>>(disp_in, disp_out, s.edges, vol_left, d.H, d.W, d.Dp);
+    k_discont_adjust<<<g, b, 0, L.stream>>>(disp_in, disp_out, s.edges, vol_left, d);
     L.count(2);
     return cudaSuccess;
 }
@@ -633,15 +660,16 @@ cudaError_t discontinuity_adjustment(const Launcher& L, const Dims& d, const int
 // ========================================================================== a14
 // subpixelEnhancement (ADCensus.cpp:1344-1374): quadratic fit on the LEFT volume, then
 // cv::medianBlur 3x3 (BORDER_REPLICATE) over the float map including negative markers.
-__global__ void k_subpixel(const int32_t* __restrict__ disp, const float* __restrict__ vol, float* __restrict__ out, size_t npx, int Dn, int Dp)
+__global__ void k_subpixel(const int32_t* __restrict__ disp, Vol vol, Dims dm, float* __restrict__ out)
 {
+    const size_t npx = dm.npx();
+    const int Dn = dm.Dn;
     const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= npx) return;
     const int d = disp[p];
     float f = (float)d;
     if (d > 0 && d < Dn - 1) {
-        const float* c = vol + p * Dp;
-        const float cost = c[d], cp = c[d + 1], cm = c[d - 1];
+        const float cost = *cell_ptr(vol, dm, p, d), cp = *cell_ptr(vol, dm, p, d + 1), cm = *cell_ptr(vol, dm, p, d - 1);
         const float num = __fsub_rn(cp, cm);
         const float den = __fmul_rn(2.f, __fsub_rn(__fadd_rn(cp, cm), __fmul_rn(2.f, cost)));
         const float diff = __fdiv_rn(num, den);
@@ -679,10 +707,10 @@ __global__ void k_median3(const float* __restrict__ src, float* __restrict__ dst
     dst[(size_t)y * W + x] = p[4];
 }
 
-void subpixel(const Launcher& L, const Dims& d, const int32_t* disp, const float* vol_left, float* tmp, float* out)
+void subpixel(const Launcher& L, const Dims& d, const int32_t* disp, const Vol& vol_left, float* tmp, float* out)
 {
     const size_t npx = d.npx();
-    k_subpixel<<<(unsigned)((npx + 255) / 256), 256, 0, L.stream>>>(disp, vol_left, tmp, npx, d.Dn, d.Dp);
+    k_subpixel<<<(unsigned)((npx + 255) / 256), 256, 0, L.stream>>>(disp, vol_left, d, tmp);
     dim3 b(32, 8), g((d.W + 31) / 32, (d.H + 7) / 8);
     k_median3<<<g, b, 0, L.stream>>>(tmp, out, d.H, d.W);
     L.count(2);

@@ -40,19 +40,20 @@ struct ScanParams {
 };
 
 struct StepIn {
-    const float* src;      // cost vector of the pixel
+    const float* src;      // main part of the pixel's cost vector (128-byte aligned)
+    const float* tsrc;     // tail part (disparities >= Dm); read by the last register only
     const uint16_t* tf;    // other-view flag word of lane 0 for this pixel (lane l reads tf[sgn*l])
     const uint8_t* own;    // own-view flag byte
 };
 
 template <int K>
 __device__ __forceinline__ void load_step(float (&cur)[K], unsigned& tf, unsigned& own, const StepIn& in, int lane, int sgn,
-                                          int ownbit, bool lastvalid)
+                                          int ownbit, bool has_tail, bool lastvalid)
 {
 #pragma unroll
     for (int k = 0; k < K; ++k) {
-        if (k < K - 1 || lastvalid) cur[k] = in.src[lane + 32 * k];
-        else cur[k] = CUDART_INF_F;
+        if (k < K - 1 || !has_tail) cur[k] = in.src[lane + 32 * k];
+        else cur[k] = lastvalid ? in.tsrc[lane] : CUDART_INF_F;
     }
     tf = in.tf[sgn * lane];
     own = (*in.own >> ownbit) & 1u;
@@ -99,11 +100,13 @@ __device__ __forceinline__ bool scan_step(float (&prev)[K], const float (&cur)[K
 }
 
 template <int K>
-__device__ __forceinline__ void store_vec(float* dst, const float (&v)[K], int lane, bool lastvalid)
+__device__ __forceinline__ void store_vec(float* dst, float* tdst, const float (&v)[K], int lane, bool has_tail, bool lastvalid)
 {
 #pragma unroll
-    for (int k = 0; k < K; ++k)
-        if (k < K - 1 || lastvalid) dst[lane + 32 * k] = v[k];
+    for (int k = 0; k < K; ++k) {
+        if (k < K - 1 || !has_tail) dst[lane + 32 * k] = v[k];
+        else if (lastvalid) tdst[lane] = v[k];
+    }
 }
 
 // cost2disparity: first strict minimum over d (ADCensus.cpp:1398-1409).
@@ -126,25 +129,28 @@ __device__ __forceinline__ int warp_argmin(const float (&v)[K], int lane)
 //   VERT : pixel stride = W*Dp floats; flag row = row of max(pos, pred), flag bit 0
 //   HORZ : pixel stride = Dp floats;   flag col = max(pos, pred),        flag bit 1
 template <int K, bool VERT, bool WTA>
-__device__ __forceinline__ void scan_dir(float (&prev)[K], float* __restrict__ vol, const uint8_t* __restrict__ fown,
+__device__ __forceinline__ void scan_dir(float (&prev)[K], const Vol& vol, const uint8_t* __restrict__ fown,
                                          const uint16_t* __restrict__ tfo, const Dims& dm, int line, int first, int dir,
-                                         int count, int sgn, int lane, bool lastvalid, bool do_store, int32_t* wta_out,
-                                         const ScanParams& sp)
+                                         int count, int sgn, int lane, bool has_tail, bool lastvalid, bool do_store,
+                                         int32_t* wta_out, const ScanParams& sp)
 {
-    const int W = dm.W, Dp = dm.Dp, Wp = dm.W + 2 * kTfPad;
+    const int W = dm.W, Wp = dm.W + 2 * kTfPad;
     const int ownbit = VERT ? 0 : 1;
     // element strides per step
-    const ptrdiff_t vstep = (ptrdiff_t)dir * (VERT ? (ptrdiff_t)W * Dp : (ptrdiff_t)Dp);
+    const ptrdiff_t vstep = (ptrdiff_t)dir * (VERT ? (ptrdiff_t)W * dm.Dm : (ptrdiff_t)dm.Dm);
+    const ptrdiff_t wstep = (ptrdiff_t)dir * (VERT ? (ptrdiff_t)W * dm.Rp : (ptrdiff_t)dm.Rp);
     const ptrdiff_t fstep = (ptrdiff_t)dir * (VERT ? (ptrdiff_t)W : 1);
     const ptrdiff_t tstep = (ptrdiff_t)dir * (VERT ? (ptrdiff_t)Wp : 1);
     // position of the first pixel and of its flag pixel (= max(pos, pred))
     const int y0 = VERT ? first : line, x0 = VERT ? line : first;
     const int fy0 = VERT ? (dir > 0 ? first : first + 1) : line, fx0 = VERT ? line : (dir > 0 ? first : first + 1);
     StepIn nxt;  // operands of step i + SCAN_PF
-    nxt.src = vol + ((size_t)y0 * W + x0) * Dp;
+    nxt.src = vol.main + ((size_t)y0 * W + x0) * dm.Dm;
+    nxt.tsrc = vol.tail + ((size_t)y0 * W + x0) * dm.Rp;
     nxt.own = fown + (size_t)fy0 * W + fx0;
     nxt.tf = tfo + (size_t)(VERT ? 0 : 1) * dm.H * Wp + (size_t)fy0 * Wp + kTfPad + fx0;
-    float* dst = vol + ((size_t)y0 * W + x0) * Dp;
+    float* dst = vol.main + ((size_t)y0 * W + x0) * dm.Dm;
+    float* tdst = vol.tail + ((size_t)y0 * W + x0) * dm.Rp;
     int32_t* wdst = WTA ? wta_out + (size_t)y0 * W + x0 : nullptr;
 
     // Register rings of 2*SCAN_PF entries: step i consumes entry i mod 2PF and refills entry
@@ -160,8 +166,9 @@ __device__ __forceinline__ void scan_dir(float (&prev)[K], float* __restrict__ v
     }
 #pragma unroll
     for (int u = 0; u < SCAN_PF; ++u) {
-        if (u < count) load_step<K>(cur[u], tf[u], own[u], nxt, lane, sgn, ownbit, lastvalid);
+        if (u < count) load_step<K>(cur[u], tf[u], own[u], nxt, lane, sgn, ownbit, has_tail, lastvalid);
         nxt.src += vstep;
+        nxt.tsrc += wstep;
         nxt.own += fstep;
         nxt.tf += tstep;
     }
@@ -171,13 +178,15 @@ __device__ __forceinline__ void scan_dir(float (&prev)[K], float* __restrict__ v
             const int i = i0 + u;
             if (i < count) {
                 const int w = (u + SCAN_PF) % SCAN_U;
-                if (i + SCAN_PF < count) load_step<K>(cur[w], tf[w], own[w], nxt, lane, sgn, ownbit, lastvalid);
+                if (i + SCAN_PF < count) load_step<K>(cur[w], tf[w], own[w], nxt, lane, sgn, ownbit, has_tail, lastvalid);
                 nxt.src += vstep;
+                nxt.tsrc += wstep;
                 nxt.own += fstep;
                 nxt.tf += tstep;
                 const bool changed = scan_step<K>(prev, cur[u], tf[u], own[u], lane, sp);
-                if (changed && do_store) store_vec<K>(dst, prev, lane, lastvalid);
+                if (changed && do_store) store_vec<K>(dst, tdst, prev, lane, has_tail, lastvalid);
                 dst += vstep;
+                tdst += wstep;
                 if (WTA) {
                     const int best = warp_argmin<K>(prev, lane);
                     if (lane == 0) *wdst = best;
@@ -200,26 +209,33 @@ k_scanline(Dims dm, ViewPtrs v0, ViewPtrs v1, ScanParams sp, int32_t* wta0, int3
     const int nlines = VERT ? dm.W : dm.H, len = VERT ? dm.H : dm.W;
     if (line >= nlines) return;
     const int sgn = view == 0 ? 1 : -1;
-    const bool lastvalid = lane + 32 * (K - 1) < dm.Dn;
+    // K = ceil(Dn / 32) registers per lane; when Dn is not a multiple of 32 the last one holds the tail part
+    const bool has_tail = dm.Rp != 0;
+    const bool lastvalid = !has_tail || lane < dm.tail();
     float prev[K];
     {
-        const float* src = v.vol + (VERT ? (size_t)line : (size_t)line * dm.W) * dm.Dp;
+        const size_t p0 = VERT ? (size_t)line : (size_t)line * dm.W;
+        const float* src = v.vol.main + p0 * dm.Dm;
+        const float* tsrc = v.vol.tail + p0 * dm.Rp;
 #pragma unroll
-        for (int k = 0; k < K; ++k) prev[k] = (k < K - 1 || lastvalid) ? src[lane + 32 * k] : CUDART_INF_F;
+        for (int k = 0; k < K; ++k) {
+            if (k < K - 1 || !has_tail) prev[k] = src[lane + 32 * k];
+            else prev[k] = lastvalid ? tsrc[lane] : CUDART_INF_F;
+        }
     }
     // forward: pos = 1 .. len-1 (pred pos-1); backward: pos = len-2 .. 0 (pred pos+1).
-    scan_dir<K, VERT, false>(prev, v.vol, v.flags, o.tflags, dm, line, 1, 1, len - 1, sgn, lane, lastvalid, true, nullptr, sp);
+    scan_dir<K, VERT, false>(prev, v.vol, v.flags, o.tflags, dm, line, 1, 1, len - 1, sgn, lane, has_tail, lastvalid, true, nullptr, sp);
     if (VERT) {
-        scan_dir<K, VERT, false>(prev, v.vol, v.flags, o.tflags, dm, line, len - 2, -1, len - 1, sgn, lane, lastvalid, true,
-                                 nullptr, sp);
+        scan_dir<K, VERT, false>(prev, v.vol, v.flags, o.tflags, dm, line, len - 2, -1, len - 1, sgn, lane, has_tail, lastvalid,
+                                 true, nullptr, sp);
     } else {
         // last pass: fuse the WTA; pixel len-1 is final after the forward pass.
         int32_t* wta_out = view ? wta1 : wta0;
         const int best = warp_argmin<K>(prev, lane);
         if (lane == 0) wta_out[(size_t)line * dm.W + len - 1] = best;
         const bool do_store = view == 0 || sp.store_right_final != 0;
-        scan_dir<K, VERT, true>(prev, v.vol, v.flags, o.tflags, dm, line, len - 2, -1, len - 1, sgn, lane, lastvalid, do_store,
-                                wta_out, sp);
+        scan_dir<K, VERT, true>(prev, v.vol, v.flags, o.tflags, dm, line, len - 2, -1, len - 1, sgn, lane, has_tail, lastvalid,
+                                do_store, wta_out, sp);
     }
 }
 

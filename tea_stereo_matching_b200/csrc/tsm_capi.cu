@@ -34,12 +34,13 @@ struct tsm_ctx {
     long long launches = 0;
 
     // geometry of the arena
-    Dims dm{0, 0, 0, 0};
+    Dims dm{0, 0, 0, 0, 0};
     tsm_adcensus_config cfg{};
     bool have_pair = false;
 
     // device buffers
-    Buf img[2], img4[2], census[2], arms[2], wsize[2], flags[2], tflags[2], vol[2], wta_[2];
+    Buf img[2], img4[2], census[2], arms[2], wsize[2], flags[2], tflags[2], vol[2], vtail[2], wta_[2];
+    Buf dense;  // [H][W][Dn] staging for volume taps / pokes
     bool stage_mode = false;  // tsm_stage_run: keep every tap-able buffer complete
     Buf disp[2], fin, ftmp;
     Buf v_vote, v_lowcnt, v_off, v_mark, v_start, v_sums, v_flat;
@@ -178,10 +179,7 @@ int ensure_arena(tsm_ctx* c, const tsm_adcensus_config* cfg, int H, int W)
     CK(c, cudaSetDevice(c->device));
     if ((rc = ensure_tables(c))) return rc;
     Dims d;
-    d.H = H;
-    d.W = W;
-    d.Dn = cfg->max_disparity - cfg->min_disparity + 1;
-    d.Dp = (d.Dn + 3) & ~3;
+    d.set(H, W, cfg->max_disparity - cfg->min_disparity + 1);
     c->dm = d;
     c->cfg = *cfg;
     const size_t npx = d.npx();
@@ -193,7 +191,8 @@ int ensure_arena(tsm_ctx* c, const tsm_adcensus_config* cfg, int H, int W)
         if ((rc = ensure(c, c->wsize[k], npx * 2 * 8))) return rc;
         if ((rc = ensure(c, c->flags[k], npx))) return rc;
         if ((rc = ensure(c, c->tflags[k], (size_t)2 * H * (W + 2 * kTfPad) * 2))) return rc;
-        if ((rc = ensure(c, c->vol[k], (d.ncell() + aggregate_overread_floats(d)) * 4, true))) return rc;
+        if ((rc = ensure(c, c->vol[k], (npx * d.Dm + aggregate_overread_floats(d)) * 4 + 256, true))) return rc;
+        if ((rc = ensure(c, c->vtail[k], (npx * d.Rp + aggregate_overread_floats(d)) * 4 + 256, true))) return rc;
         if ((rc = ensure(c, c->wta_[k], npx * 4))) return rc;
         if ((rc = ensure(c, c->disp[k], npx * 4))) return rc;
     }
@@ -229,7 +228,8 @@ ViewPtrs view_ptrs(tsm_ctx* c, int k)
     v.inv_wsize = (const double*)c->wsize[k].p;
     v.flags = (const uint8_t*)c->flags[k].p;
     v.tflags = (const uint16_t*)c->tflags[k].p;
-    v.vol = (float*)c->vol[k].p;
+    v.vol.main = (float*)c->vol[k].p;
+    v.vol.tail = (float*)c->vtail[k].p;
     return v;
 }
 
@@ -432,7 +432,7 @@ void tsm_destroy(tsm_ctx* c)
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     Buf* all[] = {&c->img[0], &c->img[1], &c->img4[0], &c->img4[1], &c->census[0], &c->census[1], &c->arms[0], &c->arms[1],
-                  &c->wsize[0], &c->wsize[1], &c->flags[0], &c->flags[1], &c->tflags[0], &c->tflags[1], &c->vol[0], &c->vol[1], &c->wta_[0], &c->wta_[1],
+                  &c->wsize[0], &c->wsize[1], &c->flags[0], &c->flags[1], &c->tflags[0], &c->tflags[1], &c->vtail[0], &c->vtail[1], &c->dense, &c->vol[0], &c->vol[1], &c->wta_[0], &c->wta_[1],
                   &c->disp[0], &c->disp[1], &c->fin, &c->ftmp, &c->v_vote, &c->v_lowcnt, &c->v_off, &c->v_mark, &c->v_start,
                   &c->v_sums, &c->v_flat, &c->e_gray, &c->e_blur, &c->e_mag, &c->e_gx, &c->e_gy, &c->e_map, &c->e_edges,
                   &c->e_hist, &c->e_lut, &c->e_changed, &c->tab_ad, &c->tab_c, &c->r_src, &c->r_map1[0], &c->r_map1[1],
@@ -672,14 +672,14 @@ int tsm_stage_run(tsm_ctx* c, int mask, int arg)
     return TSM_OK;
 }
 
-int tsm_volume_pitch(const tsm_ctx* c) { return c ? c->dm.Dp : 0; }
+int tsm_volume_pitch(const tsm_ctx* c) { return c ? c->dm.Dn : 0; }
 
 static Buf* tap_buffer(tsm_ctx* c, int id, size_t* bytes)
 {
     const size_t npx = c->dm.npx();
     switch (id) {
-        case TSM_BUF_VOL_LEFT: *bytes = c->dm.ncell() * 4; return &c->vol[0];
-        case TSM_BUF_VOL_RIGHT: *bytes = c->dm.ncell() * 4; return &c->vol[1];
+        case TSM_BUF_VOL_LEFT: *bytes = npx * c->dm.Dn * 4; return &c->vol[0];
+        case TSM_BUF_VOL_RIGHT: *bytes = npx * c->dm.Dn * 4; return &c->vol[1];
         case TSM_BUF_ARMS_LEFT: *bytes = npx * 4; return &c->arms[0];
         case TSM_BUF_ARMS_RIGHT: *bytes = npx * 4; return &c->arms[1];
         case TSM_BUF_WTA_LEFT: *bytes = npx * 4; return &c->wta_[0];
@@ -711,7 +711,15 @@ int tsm_tap(tsm_ctx* c, int buffer, void* dst, size_t bytes)
     if (!b || !b->p) return fail(c, TSM_E_ARG, "tsm_tap: unknown buffer %d", buffer);
     if (bytes != need) return fail(c, TSM_E_ARG, "tsm_tap: buffer %d holds %zu bytes, caller passed %zu", buffer, need, bytes);
     CK(c, cudaSetDevice(c->device));
-    CK(c, cudaMemcpyAsync(dst, b->p, need, cudaMemcpyDeviceToHost, c->stream));
+    const void* srcp = b->p;
+    if (buffer == TSM_BUF_VOL_LEFT || buffer == TSM_BUF_VOL_RIGHT) {  // split layout -> dense [H][W][Dn]
+        int rc = ensure(c, c->dense, need);
+        if (rc) return rc;
+        Launcher L{c->stream, &c->launches};
+        volume_gather(L, c->dm, view_ptrs(c, buffer - TSM_BUF_VOL_LEFT).vol, (float*)c->dense.p);
+        srcp = c->dense.p;
+    }
+    CK(c, cudaMemcpyAsync(dst, srcp, need, cudaMemcpyDeviceToHost, c->stream));
     CK(c, cudaStreamSynchronize(c->stream));
     return TSM_OK;
 }
@@ -725,6 +733,15 @@ int tsm_poke(tsm_ctx* c, int buffer, const void* src, size_t bytes)
     if (!b || !b->p) return fail(c, TSM_E_ARG, "tsm_poke: unknown buffer %d", buffer);
     if (bytes != need) return fail(c, TSM_E_ARG, "tsm_poke: buffer %d holds %zu bytes, caller passed %zu", buffer, need, bytes);
     CK(c, cudaSetDevice(c->device));
+    if (buffer == TSM_BUF_VOL_LEFT || buffer == TSM_BUF_VOL_RIGHT) {  // dense [H][W][Dn] -> split layout
+        int rc = ensure(c, c->dense, need);
+        if (rc) return rc;
+        CK(c, cudaMemcpyAsync(c->dense.p, src, need, cudaMemcpyHostToDevice, c->stream));
+        Launcher L{c->stream, &c->launches};
+        volume_scatter(L, c->dm, (const float*)c->dense.p, view_ptrs(c, buffer - TSM_BUF_VOL_LEFT).vol);
+        CK(c, cudaStreamSynchronize(c->stream));
+        return TSM_OK;
+    }
     CK(c, cudaMemcpyAsync(b->p, src, need, cudaMemcpyHostToDevice, c->stream));
     CK(c, cudaStreamSynchronize(c->stream));
     return TSM_OK;
