@@ -220,7 +220,9 @@ def main():
         return float(t.item())
 
     # frames of this rank: global frame i -> rank i % N ; seeds 1000+i
-    my_frames = [i for i in range(args.batch) if i % world == rank]
+    from tea_stereo_matching_b200.sharding import frames_for_rank
+
+    my_frames = frames_for_rank(args.batch, world, rank)
     n_distinct = max(1, min(DISTINCT, len(my_frames)))
     t0 = time.time()
     frames = [synth_v1(H, W, MAXD, seed=1000 + my_frames[j]) for j in range(n_distinct)]

@@ -1,0 +1,277 @@
+// stereo.cpp -- implementation of the facade in stereo.h on top of the tsm_* C-ABI.
+// Error behaviour follows the reference: setters and the image check throw std::string
+// (source/ADCensus.cpp:310,326,333), internal failures std::runtime_error (:383-387);
+// EpipolarRectify logs and returns on bad input (source/EpipolarRectify.cpp:48-57,70-79,89-98)
+// but loadEpipolarRectifyMap throws std::runtime_error on empty maps (:35-40).
+#include "stereo.h"
+#include "../../include/tsm.h"
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <stdexcept>
+
+namespace {
+
+bool log_enabled() { static const bool on = std::getenv("TSM_LOG") != nullptr; return on; }
+void log_info(const std::string& m) { if (log_enabled()) std::fprintf(stderr, "[INFO] %s\n", m.c_str()); }
+void log_error(const std::string& m) { std::fprintf(stderr, "[ERROR] %s\n", m.c_str()); }
+
+int default_device()
+{
+	const char* e = std::getenv("TSM_DEVICE");
+	return e ? std::atoi(e) : 0;
+}
+
+struct Ctx {
+	tsm_ctx* h = nullptr;
+	int device = -1;
+	void ensure(int dev)
+	{
+		if (h && device == dev) return;
+		reset();
+		if (tsm_create(dev, &h) != TSM_OK) throw std::runtime_error(tsm_last_error(nullptr));
+		device = dev;
+	}
+	void reset() { if (h) tsm_destroy(h); h = nullptr; device = -1; }
+	~Ctx() { reset(); }
+};
+
+int map_kind_of(const cv::Mat& m1, const cv::Mat& m2)
+{
+	if (m1.type() == CV_16SC2 && m2.type() == CV_16UC1) return TSM_MAP_FIXED_16SC2_16UC1;
+	if (m1.type() == CV_32FC1 && m2.type() == CV_32FC1) return TSM_MAP_FLOAT_32FC1_X2;
+	return -1;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------- ADCensusParams
+void stereo::ADCensusParams::setADCensusParams(const ColorModel& colorModel)
+{
+	lambdaAD = 10.f; censusWin = CensusWin::CENSUSWIN_9x7; lambdaCensus = 30.f;
+	lambdaHue = 1.f; lambdaSaturation = 2.5f; lambdaIntensity = 2.5f;
+	iterations = 4; pi1 = 1.f; pi2 = 3.f; dispTolerance = 0; votingThresh = 20; votingRatioThresh = 0.4f;
+	maxSearchDepth = 20; blurKernelSize = 3; cannyThresh1 = 30; cannyThresh2 = 90; cannyKernelSize = 3;
+	const bool rgb = colorModel == ColorModel::RGB;
+	colorThresh1 = rgb ? 20 : 5; colorThresh2 = rgb ? 6 : 1;
+	maxLength1 = rgb ? 34 : 17; maxLength2 = rgb ? 17 : 8; colorDiff = rgb ? 15 : 3;
+	saturationThresh1 = rgb ? 0 : 10; saturationThresh2 = rgb ? 0 : 2;
+	intensityThresh1 = rgb ? 0 : 12; intensityThresh2 = rgb ? 0 : 3;
+}
+
+// ------------------------------------------------------------ EpipolarRectifyMap
+stereo::EpipolarRectifyMap::EpipolarRectifyMap(const cv::Mat& R1_, const cv::Mat& R2_, const cv::Mat& P1_, const cv::Mat& P2_,
+	const cv::Mat& m00, const cv::Mat& m01, const cv::Mat& m10, const cv::Mat& m11)
+	: R1(R1_), R2(R2_), P1(P1_), P2(P2_), map00(m00), map01(m01), map10(m10), map11(m11) {}
+
+bool stereo::EpipolarRectifyMap::empty() const
+{
+	return map00.empty() || map01.empty() || map10.empty() || map11.empty();
+}
+
+// --------------------------------------------------------------- EpipolarRectify
+class stereo::EpipolarRectify::EpipolarRectifyImpl
+{
+public:
+	EpipolarRectifyMap m_rectifyMap;
+	cv::Size m_imgsz;
+	cv::Mat c00, c01, c10, c11;  // continuous copies handed to the C-ABI
+	int kind = -1;
+	Ctx ctx;
+};
+
+stereo::EpipolarRectify::EpipolarRectify() { impl = std::make_unique<EpipolarRectifyImpl>(); }
+stereo::EpipolarRectify::EpipolarRectify(const EpipolarRectifyMap& rectifyMap, const cv::Size& imgsz)
+{
+	impl = std::make_unique<EpipolarRectifyImpl>();
+	loadEpipolarRectifyMap(rectifyMap, imgsz);
+}
+stereo::EpipolarRectify::~EpipolarRectify() {}
+
+void stereo::EpipolarRectify::loadEpipolarRectifyMap(const EpipolarRectifyMap& rectifyMap, const cv::Size& imgsz)
+{
+	log_info("Loading stereo epipolar rectify params...");
+	if (rectifyMap.empty()) {
+		std::string msg = "stereo params is empty, please load it first";
+		log_error(msg);
+		throw std::runtime_error(msg);
+	}
+	impl->m_rectifyMap = rectifyMap;
+	impl->m_imgsz = imgsz;
+	impl->c00 = rectifyMap.map00.clone(); impl->c01 = rectifyMap.map01.clone();
+	impl->c10 = rectifyMap.map10.clone(); impl->c11 = rectifyMap.map11.clone();
+	impl->kind = map_kind_of(impl->c00, impl->c01);
+	if (impl->kind < 0 || map_kind_of(impl->c10, impl->c11) != impl->kind)
+		throw std::runtime_error("[EpipolarRectify] unsupported map types (need CV_16SC2+CV_16UC1 or CV_32FC1 x2)");
+	if (impl->ctx.h) tsm_invalidate_maps(impl->ctx.h);
+	log_info("Loaded stereo epipolar rectify params!");
+}
+
+void stereo::EpipolarRectify::rectify(const cv::Mat& stereoImage, cv::Mat& rectifiedStereoImage)
+{
+	if (impl->m_rectifyMap.empty()) { log_error("Stereo epipolar rectify params is empty, please load it first."); return; }
+	if (stereoImage.empty()) { log_error("Stereo image is empty."); return; }
+	cv::Mat l, r;
+	rectify(stereoImage, l, r);
+	cv::hconcat(l, r, rectifiedStereoImage);
+}
+
+void stereo::EpipolarRectify::rectify(const cv::Mat& stereoImage, cv::Mat& rectifyLeftImage, cv::Mat& rectifiedRightImage)
+{
+	if (impl->m_rectifyMap.empty()) { log_error("Stereo epipolar rectify params is empty, please load it first."); return; }
+	if (stereoImage.empty()) { log_error("Left or Right image is empty."); return; }
+	const int W = impl->m_imgsz.width, H = impl->m_imgsz.height;
+	if (impl->c00.rows == H && impl->c00.cols == W && stereoImage.cols >= 2 * W && stereoImage.rows >= H && stereoImage.type() == CV_8UC3) {
+		impl->ctx.ensure(default_device());
+		cv::Mat l(H, W, CV_8UC3), r(H, W, CV_8UC3);
+		int rc = tsm_rectify_stereo(impl->ctx.h, stereoImage.data, stereoImage.step, H, W, impl->c00.data, impl->c01.data,
+			impl->c10.data, impl->c11.data, impl->kind, l.data, l.step, r.data, r.step);
+		if (rc != TSM_OK) throw std::runtime_error(tsm_last_error(impl->ctx.h));
+		rectifyLeftImage = l; rectifiedRightImage = r;
+		return;
+	}
+	cv::Mat left = stereoImage(cv::Rect(0, 0, W, H)).clone();
+	cv::Mat right = stereoImage(cv::Rect(W, 0, W, H)).clone();
+	rectify(left, right, rectifyLeftImage, rectifiedRightImage);
+}
+
+void stereo::EpipolarRectify::rectify(const cv::Mat& leftImage, const cv::Mat& rightImage, cv::Mat& rectifyLeftImage, cv::Mat& rectifiedRightImage)
+{
+	if (impl->m_rectifyMap.empty()) { log_error("Stereo epipolar rectify params is empty, please load it first."); return; }
+	if (leftImage.empty() || rightImage.empty()) { log_error("Left or Right image is empty."); return; }
+	impl->ctx.ensure(default_device());
+	const cv::Mat* src[2] = {&leftImage, &rightImage};
+	const cv::Mat* m1[2] = {&impl->c00, &impl->c10};
+	const cv::Mat* m2[2] = {&impl->c01, &impl->c11};
+	cv::Mat out[2];
+	for (int k = 0; k < 2; ++k) {
+		out[k].create(m1[k]->rows, m1[k]->cols, CV_8UC3);
+		int rc = tsm_remap(impl->ctx.h, src[k]->data, src[k]->step, src[k]->rows, src[k]->cols, m1[k]->data, m2[k]->data,
+			impl->kind, m1[k]->rows, m1[k]->cols, out[k].data, out[k].step);
+		if (rc != TSM_OK) throw std::runtime_error(tsm_last_error(impl->ctx.h));
+	}
+	rectifyLeftImage = out[0]; rectifiedRightImage = out[1];
+}
+
+// ---------------------------------------------------------------- StereoMatching
+stereo::StereoMatching::~StereoMatching() {}
+
+// ---------------------------------------------------------------------- ADCensus
+class stereo::ADCensus::ADCensusImpl
+{
+public:
+	// defaults of ADCensusImpl::ADCensusImpl, source/ADCensus.cpp:409-420
+	int m_minDisparity = 0, m_maxDisparity = 64;
+	ADCensusParams m_paMatching{ColorModel::HSI};
+	ColorModel m_colorModel = ColorModel::HSI;
+	bool m_roiMatching = false, m_maskMatching = false;
+	int m_offset = 0;
+	int device = default_device();
+	Ctx ctx[2];
+	tsm_adcensus_config config() const
+	{
+		tsm_adcensus_config c;
+		c.min_disparity = m_minDisparity; c.max_disparity = m_maxDisparity;
+		c.color_model = m_colorModel == ColorModel::RGB ? TSM_COLOR_RGB : TSM_COLOR_HSI;
+		c.roi_matching = m_roiMatching; c.mask_matching = m_maskMatching; c.offset = m_offset;
+		return c;
+	}
+};
+
+stereo::ADCensus::ADCensus() { impl = std::make_unique<ADCensusImpl>(); }
+stereo::ADCensus::~ADCensus() {}
+
+void stereo::ADCensus::setMinMaxDisparity(const int& minDisparity, const int& maxDisparity)
+{
+	if (minDisparity * maxDisparity < 0 or minDisparity >= maxDisparity)
+		throw(std::string("[ADCensus] Set MinMaxDisparity error."));
+	impl->m_minDisparity = minDisparity;
+	impl->m_maxDisparity = maxDisparity;
+}
+
+void stereo::ADCensus::setMatchingStrategy(const ColorModel& colorModel, const bool& roiMatching, const bool& maskMatching)
+{
+	impl->m_colorModel = colorModel;
+	impl->m_paMatching = ADCensusParams(colorModel);
+	impl->m_roiMatching = roiMatching;
+	impl->m_maskMatching = maskMatching;
+}
+
+void stereo::ADCensus::setOffset(const int& offset)
+{
+	if (offset < 0) throw(std::string("[ADCensus] Offset must be positive."));
+	impl->m_offset = offset;
+}
+
+void stereo::ADCensus::setDevice(const int& device) { impl->device = device; }
+
+static void check_pair(const cv::Mat& l, const cv::Mat& r)
+{
+	if (l.empty() or r.empty() or l.size() != r.size()) throw(std::string("[ADCensus] Image error."));
+	// stricter than the reference (which reads any Mat through at<Vec3b>, UB for other types)
+	if (l.type() != CV_8UC3 or r.type() != CV_8UC3) throw(std::string("[ADCensus] Image error."));
+}
+
+void stereo::ADCensus::compute(const cv::Mat& leftImage, const cv::Mat& rightImage, cv::Mat& disparity)
+{
+	check_pair(leftImage, rightImage);
+	log_info("Computing disparity...");
+	auto start = std::chrono::steady_clock::now();
+	impl->ctx[0].ensure(impl->device);
+	cv::Mat out(leftImage.rows, leftImage.cols, CV_32FC1);
+	const tsm_adcensus_config cfg = impl->config();
+	int rc = tsm_adcensus_compute(impl->ctx[0].h, &cfg, leftImage.data, leftImage.step, rightImage.data, rightImage.step,
+		leftImage.rows, leftImage.cols, (float*)out.data, out.step);
+	if (rc == TSM_E_ARG) throw(std::string(tsm_last_error(impl->ctx[0].h)));
+	if (rc != TSM_OK) throw std::runtime_error(tsm_last_error(impl->ctx[0].h));
+	disparity = out;
+	auto tt = std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - start);
+	log_info("Disparity map computed. Timing: " + std::to_string(tt.count() / 1000.0) + " ms.");
+}
+
+void stereo::ADCensus::compute(const std::vector<cv::Mat>& leftImages, const std::vector<cv::Mat>& rightImages, std::vector<cv::Mat>& disparities)
+{
+	if (leftImages.size() != rightImages.size()) throw(std::string("[ADCensus] Image error."));
+	const size_t n = leftImages.size();
+	for (size_t i = 0; i < n; ++i) check_pair(leftImages[i], rightImages[i]);
+	disparities.assign(n, cv::Mat());
+	const tsm_adcensus_config cfg = impl->config();
+	for (int k = 0; k < 2; ++k) impl->ctx[k].ensure(impl->device);
+	auto fail = [&](tsm_ctx* c, int rc) {
+		if (rc == TSM_E_ARG) throw(std::string(tsm_last_error(c)));
+		throw std::runtime_error(tsm_last_error(c));
+	};
+	for (size_t i = 0; i <= n; ++i) {
+		if (i < n) {
+			tsm_ctx* c = impl->ctx[i & 1].h;
+			int rc = tsm_adcensus_enqueue(c, &cfg, leftImages[i].data, leftImages[i].step, rightImages[i].data, rightImages[i].step,
+				leftImages[i].rows, leftImages[i].cols);
+			if (rc != TSM_OK) fail(c, rc);
+		}
+		if (i >= 1) {
+			tsm_ctx* c = impl->ctx[(i - 1) & 1].h;
+			cv::Mat out(leftImages[i - 1].rows, leftImages[i - 1].cols, CV_32FC1);
+			int rc = tsm_adcensus_wait(c, (float*)out.data, out.step);
+			if (rc != TSM_OK) fail(c, rc);
+			disparities[i - 1] = out;
+		}
+	}
+}
+
+void stereo::ADCensus::compute(EpipolarRectify& rectify, const cv::Mat& stereoImage, cv::Mat& disparity)
+{
+	auto& r = *rectify.impl;
+	if (r.m_rectifyMap.empty()) throw std::runtime_error("stereo params is empty, please load it first");
+	if (stereoImage.empty() or stereoImage.type() != CV_8UC3) throw(std::string("[ADCensus] Image error."));
+	const int W = r.m_imgsz.width, H = r.m_imgsz.height;
+	if (stereoImage.cols < 2 * W or stereoImage.rows < H or r.c00.rows != H or r.c00.cols != W)
+		throw(std::string("[ADCensus] Image error."));
+	impl->ctx[0].ensure(impl->device);
+	cv::Mat out(H, W, CV_32FC1);
+	const tsm_adcensus_config cfg = impl->config();
+	int rc = tsm_rectify_adcensus(impl->ctx[0].h, &cfg, stereoImage.data, stereoImage.step, H, W, r.c00.data, r.c01.data, r.c10.data,
+		r.c11.data, r.kind, (float*)out.data, out.step);
+	if (rc == TSM_E_ARG) throw(std::string(tsm_last_error(impl->ctx[0].h)));
+	if (rc != TSM_OK) throw std::runtime_error(tsm_last_error(impl->ctx[0].h));
+	disparity = out;
+}

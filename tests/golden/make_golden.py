@@ -2,7 +2,8 @@
 """Generates the committed golden vectors under tests/golden/.
 
 Run in the dev container (needs /root/reference and python cv2 4.13.0):
-    python tests/golden/make_golden.py
+    python tests/golden/make_golden.py          # small fixtures (seconds)
+    python tests/golden/make_golden.py full     # full-size C1 / C2 reference outputs (minutes)
 
 * pair_0600_320x180.npz  -- the reference's demo pair demo-imgs/0600-{Left,Right}.bmp,
   area-downscaled x4 with cv2 (inputs only; BGR uint8).
@@ -106,5 +107,25 @@ def main():
         print(p.name, p.stat().st_size)
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and len(sys.argv) == 1:
     main()
+
+
+def full_size():
+    """Full-size reference outputs (slow: ~3 min for C1, ~6 min for C2 on 8 cores)."""
+    ref = oracle.Ref()
+    for name, (lf, rf), maxd in (("c1_0600_720p", ("0600-Left.bmp", "0600-Right.bmp"), 192),
+                                 ("c2_motorcycle", ("Motorcycle_Left.png", "Motorcycle_Right.png"), 256)):
+        L = cv2.imread(str(REF_IMGS / lf))
+        R = cv2.imread(str(REF_IMGS / rf))
+        np.savez_compressed(OUT / f"pair_{name}.npz", left=L, right=R)
+        st = ref.run(L, R, maxd, serial_scanline=True, volumes=False)
+        np.savez_compressed(OUT / f"ref_{name}_d{maxd}.npz", max_disparity=maxd, wta0=st.wta[0].astype(np.int16),
+                            wta1=st.wta[1].astype(np.int16), lrc=st.lrc.astype(np.int16), vote4=st.vote[4].astype(np.int16),
+                            interp=st.interp.astype(np.int16), discont=st.discont.astype(np.int16), final=st.final,
+                            seconds=np.array([st.seconds[k] for k in ("init", "agg", "scan", "multi")]))
+        print(name, st.seconds)
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "full":
+    full_size()

@@ -1,0 +1,57 @@
+"""The C++20 facade (tea_stereo_matching_b200/cpp): same class names / signatures / exception
+types as the reference's stereo::ADCensus and stereo::EpipolarRectify."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+CPP = ROOT / "tea_stereo_matching_b200" / "cpp"
+DEMO = ROOT / "tests" / "cpp" / "facade_demo"
+
+
+@pytest.fixture(scope="module")
+def demo(native_lib):
+    env = {k: v for k, v in os.environ.items() if k not in ("CXX", "CC")}
+    subprocess.run(["make", "-s", "-C", str(CPP)], check=True, env=env)
+    subprocess.run(["g++", "-std=c++20", "-O1", "-o", str(DEMO), str(ROOT / "tests" / "cpp" / "facade_demo.cpp"),
+                    f"-L{ROOT / 'tea_stereo_matching_b200'}", "-ltea_stereo", "-ltsm_b200",
+                    f"-Wl,-rpath,{ROOT / 'tea_stereo_matching_b200'}"], check=True, env=env)
+    return DEMO
+
+
+def test_facade_api_error_behaviour(demo):
+    r = subprocess.run([str(demo), "api"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "API CHECKS PASSED" in r.stdout
+    assert "Set MinMaxDisparity error" in r.stdout and "Image error" in r.stdout
+
+
+@pytest.mark.gpu
+def test_facade_compute_matches_python_mirror_and_oracle(demo, pair_0600, port, tmp_path):
+    import tea_stereo_matching_b200 as t
+
+    left, right = pair_0600
+    H, W, _ = left.shape
+    D = 48
+    inp, out = tmp_path / "in.bin", tmp_path / "out.bin"
+    with open(inp, "wb") as f:
+        f.write(np.array([H, W, D], np.int32).tobytes())
+        f.write(left.tobytes())
+        f.write(right.tobytes())
+    r = subprocess.run([str(demo), "run", str(inp), str(out)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    got = np.fromfile(out, np.float32).reshape(H, W)
+    m = t.ADCensus()
+    m.setMatchingStrategy(t.ColorModel.RGB)
+    m.setMinMaxDisparity(0, D)
+    assert np.array_equal(got, m.compute(left, right))  # same kernels behind both host mirrors
+    want = port.compute(left, right, D)
+    diff = np.abs(got.astype(np.float64) - want)
+    assert (diff > 1).mean() <= 1e-3 and (diff > 0.05).mean() <= 1e-3
+    r = subprocess.run([str(demo), "batch", str(inp), str(out), "3"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    b = np.fromfile(out, np.float32).reshape(3, H, W)
+    assert all(np.array_equal(b[i], got) for i in range(3))

@@ -11,6 +11,8 @@ Bars (BASELINE.json north_star):
 import numpy as np
 import pytest
 
+from tea_stereo_matching_b200.synth import synth_v1
+
 pytestmark = pytest.mark.gpu
 
 AGG_RTOL = 2e-6
@@ -29,6 +31,14 @@ def _cases(pair_0600, golden_synth):
         ("0600_320x180_d48", left, right, 48),
         ("synth_96x128_d24", golden_synth["left"], golden_synth["right"], int(golden_synth["max_disparity"])),
         ("0600_crop_ragged_d70", left[11:150, 7:300].copy(), right[11:150, 7:300].copy(), 70),
+        # BASELINE disparity ranges on small images: Dn = 129 / 193 / 257 / 385 (K = 5 / 7 / 9 / 13 registers, tail = 1)
+        ("synth_60x400_d128",) + synth_v1(60, 400, 128, seed=31) + (128,),
+        ("synth_72x420_d192",) + synth_v1(72, 420, 192, seed=32) + (192,),
+        ("synth_56x520_d256",) + synth_v1(56, 520, 256, seed=33) + (256,),
+        ("synth_gray_52x700_d384",) + synth_v1(52, 700, 384, seed=34, gray=True) + (384,),
+        # Dn a multiple of 32 (no tail part) and Dn < 32 (tail only)
+        ("synth_64x200_d63",) + synth_v1(64, 200, 63, seed=35) + (63,),
+        ("synth_50x90_d15",) + synth_v1(50, 90, 15, seed=36) + (15,),
     ]
 
 
