@@ -13,7 +13,7 @@ __device__ inline float2 bump(float2 v) { v.x += 1.f; v.y += 1.f; return v; }
 __device__ inline float4 bump(float4 v) { v.x += 1.f; v.y += 1.f; v.z += 1.f; v.w += 1.f; return v; }
 
 template <int VEC, int PF, bool VERT>
-__global__ void walk(float* vol, int H, int W, int Dp, int chunks_per_line)
+__global__ void walk(float* vol, int H, int W, int Dp, int chunks_per_line, int lag, const unsigned* small)
 {
     extern __shared__ unsigned char dummy[];
     typedef typename V<VEC>::T T;
@@ -27,12 +27,22 @@ __global__ void walk(float* vol, int H, int W, int Dp, int chunks_per_line)
     float* base = vol + (VERT ? (size_t)line * Dp : (size_t)line * W * Dp) + d;
     const float* in = base;
     float* out = base;
+    const unsigned* sm = small ? small + (VERT ? (size_t)line : (size_t)line * W) : nullptr;
+    const size_t sstride = VERT ? W : 1;
+    unsigned acc = 0;
+    // extra lag: read `lag` positions ahead before the first write
+    for (int t = 0; t < lag; ++t) { acc += __float_as_uint(*(in + t * stride)); }
+    in += (size_t)lag * stride;
     T buf[2][PF];
 #pragma unroll
     for (int u = 0; u < PF; ++u) buf[0][u] = *reinterpret_cast<const T*>(in + u * stride);
     in += PF * stride;
     int t = 0;
-    for (; t + 2 * PF <= len; t += 2 * PF) {
+    for (; t + 2 * PF + lag <= len; t += 2 * PF) {
+        if (sm) {
+#pragma unroll
+            for (int u = 0; u < 2 * PF; ++u) acc += sm[(size_t)(t + u) * sstride];
+        }
 #pragma unroll
         for (int u = 0; u < PF; ++u) buf[1][u] = *reinterpret_cast<const T*>(in + u * stride);
         in += PF * stride;
@@ -44,11 +54,11 @@ __global__ void walk(float* vol, int H, int W, int Dp, int chunks_per_line)
 #pragma unroll
         for (int u = 0; u < PF; ++u) { *reinterpret_cast<T*>(out) = bump(buf[1][u]); out += stride; }
     }
-    if (dummy[0] == 123 && lane == 77) out[0] = 0;
+    if ((dummy[0] == 123 && lane == 77) || acc == 0x12345u) out[0] = 0;
 }
 
 template <int VEC, int PF, bool VERT>
-void run(float* vol, int H, int W, int Dp, int warps_per_sm, const char* tag, int bt = 64)
+void run(float* vol, int H, int W, int Dp, int warps_per_sm, const char* tag, int bt = 64, int lag = 0, const unsigned* small = nullptr)
 {
     const int chunks = (Dp + 32 * VEC - 1) / (32 * VEC);
     const int nwarps = (VERT ? W : H) * chunks;
@@ -59,15 +69,15 @@ void run(float* vol, int H, int W, int Dp, int warps_per_sm, const char* tag, in
     const int grid = (nwarps * 32 + bt - 1) / bt;
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0); cudaEventCreate(&e1);
-    walk<VEC, PF, VERT><<<grid, bt, smem>>>(vol, H, W, Dp, chunks);
+    walk<VEC, PF, VERT><<<grid, bt, smem>>>(vol, H, W, Dp, chunks, lag, small);
     CK(cudaDeviceSynchronize());
     cudaEventRecord(e0);
-    for (int i = 0; i < 3; ++i) walk<VEC, PF, VERT><<<grid, bt, smem>>>(vol, H, W, Dp, chunks);
+    for (int i = 0; i < 3; ++i) walk<VEC, PF, VERT><<<grid, bt, smem>>>(vol, H, W, Dp, chunks, lag, small);
     cudaEventRecord(e1);
     CK(cudaDeviceSynchronize());
     float ms; cudaEventElapsedTime(&ms, e0, e1); ms /= 3;
     const double bytes = 2.0 * H * W * (double)Dp * 4;
-    printf("%-6s Dp=%d bt=%3d VEC=%d PF=%2d warps/SM=%2d %s: %.3f ms  %.0f GB/s\n", tag, Dp, bt, VEC, PF, warps_per_sm, VERT ? "V" : "H", ms, bytes / ms / 1e6);
+    printf("%-6s lag=%2d small=%d Dp=%d bt=%3d VEC=%d PF=%2d warps/SM=%2d %s: %.3f ms  %.0f GB/s\n", tag, lag, small != nullptr, Dp, bt, VEC, PF, warps_per_sm, VERT ? "V" : "H", ms, bytes / ms / 1e6);
 }
 
 int main()
@@ -77,15 +87,19 @@ int main()
     const size_t n = (size_t)H * W * Dp + (size_t)64 * W * Dp;
     CK(cudaMalloc(&vol, n * 4));
     CK(cudaMemset(vol, 0, n * 4));
-    for (int dp : {196, 192, 224}) {
-        run<2, 8, false>(vol, H, W, dp, 6, "walk");
-        run<2, 8, false>(vol, H, W, dp, 12, "walk");
-        run<4, 8, false>(vol, H, W, dp, 6, "walk");
-        run<4, 8, false>(vol, H, W, dp, 12, "walk");
-        run<2, 8, true>(vol, H, W, dp, 6, "walk");
-        run<4, 8, true>(vol, H, W, dp, 12, "walk");
-        run<2, 8, false>(vol, H, W, dp, 12, "walk", 128);
-        run<4, 8, false>(vol, H, W, dp, 8, "walk", 64);
-    }
+    unsigned* small;
+    CK(cudaMalloc(&small, (size_t)H * W * 4));
+    CK(cudaMemset(small, 1, (size_t)H * W * 4));
+    const int dp = 192;
+    run<2, 8, false>(vol, H, W, dp, 6, "walk", 64, 33, nullptr);
+    run<2, 8, false>(vol, H, W + 1, dp, 6, "walk", 64, 33, nullptr);    // line pitch + 1 pixel: partition camping?
+    run<2, 8, false>(vol, H, W + 5, dp, 6, "walk", 64, 33, nullptr);
+    run<2, 8, true>(vol, H, W + 1, dp, 6, "walk", 64, 33, nullptr);
+    // copy-like reference in the same harness: "pixel vector" = 64 floats -> every warp streams contiguously
+    run<2, 8, false>(vol, 1080 * 3, W, 64, 6, "copy", 64, 33, nullptr);
+    run<2, 8, false>(vol, 1080 * 3, W, 64, 24, "copy", 64, 33, nullptr);
+    run<4, 8, false>(vol, 1080 * 3 / 2, W, 128, 24, "copy", 64, 33, nullptr);
+    run<2, 8, false>(vol, H, W, dp, 24, "walk", 64, 33, nullptr);
+    run<2, 8, false>(vol, H, W, dp, 48, "walk", 64, 33, nullptr);
     return 0;
 }

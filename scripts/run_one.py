@@ -17,8 +17,13 @@ ap.add_argument("--W", type=int, default=1920)
 ap.add_argument("--D", type=int, default=192)
 ap.add_argument("--reps", type=int, default=2)
 ap.add_argument("--gray", action="store_true")
+ap.add_argument("--pair", default=None, help="npz with left/right (e.g. tests/golden/pair_c1_0600_720p.npz)")
 a = ap.parse_args()
-l, r = synth_v1(a.H, a.W, a.D, seed=1000, gray=a.gray)
+if a.pair:
+    z = np.load(a.pair)
+    l, r = z["left"], z["right"]
+else:
+    l, r = synth_v1(a.H, a.W, a.D, seed=1000, gray=a.gray)
 m = t.ADCensus()
 m.setMatchingStrategy(t.ColorModel.RGB)
 m.setMinMaxDisparity(0, a.D)

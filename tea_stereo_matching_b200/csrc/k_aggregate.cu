@@ -21,10 +21,11 @@
 // AGG_PF steps.
 //
 // Division: the reference divides the fp32 sum by (float)N with an IEEE fp32 divide
-// (ADCensus.cpp:747).  q = fl32( (double)fl32(sum) * fl64(1/N) ) is the same number:
-// the sum has 24 significant bits and N < 2^13, so sum/N is either exactly representable
-// or at least 2^-38 (relative) away from any fp32 rounding boundary, far more than the
-// 2^-52 error of the fp64 product.
+// (ADCensus.cpp:747); so does __fdiv_rn(fl32(sum), (float)N) here.
+//
+// Per-position side data (the two arm lengths of the pass and N) come as ONE 32-bit step
+// descriptor (k_prep.cu), four consecutive positions per 16-byte load: small broadcast loads
+// cost real bandwidth on this access pattern (measured: -15 % with two scalar loads per step).
 #include "tsm_common.cuh"
 
 namespace tsm {
@@ -36,10 +37,14 @@ constexpr int AGG_NC = TSM_AGG_NC;        // adjacent disparities (chains) per t
 constexpr int AGG_BLOCK = 128 / AGG_NC;   // threads per CTA
 constexpr int AGG_LAG = kMaxArm;          // 33
 #ifndef TSM_AGG_PF
-#define TSM_AGG_PF 12
+#define TSM_AGG_PF 8
 #endif
 constexpr int AGG_PF = TSM_AGG_PF;        // prefetch distance
-constexpr int AGG_U = 2 * AGG_PF;         // steps per main-loop iteration (two batches)
+#ifndef TSM_AGG_NBUF
+#define TSM_AGG_NBUF 4
+#endif
+constexpr int AGG_NBUF = TSM_AGG_NBUF;    // register buffers: NBUF-1 batches in flight
+constexpr int AGG_U = AGG_NBUF * AGG_PF;  // steps per main-loop iteration
 constexpr int AGG_RING = 72;              // >= 68 prefixes, multiple of AGG_PF
 constexpr int AGG_SLOT = AGG_BLOCK * 8 * AGG_NC;  // bytes between consecutive ring slots
 constexpr int AGG_RING_BYTES = AGG_RING * AGG_SLOT;
@@ -75,13 +80,7 @@ __device__ __forceinline__ void st_stream(float* p, float a, float b)
     else asm volatile("st.global.L1::no_allocate.f32 [%0], %1;" ::"l"(p), "f"(a) : "memory");
 }
 
-// (neg, pos) arm pair of this pass from a packed uchar4 (up, down, left, right).
-template <bool VERT>
-__device__ __forceinline__ void arm_pair(uint32_t packed, int& a, int& b)
-{
-    if (VERT) { a = packed & 0xff; b = (packed >> 8) & 0xff; }
-    else { a = (packed >> 16) & 0xff; b = packed >> 24; }
-}
+static_assert(AGG_PF % 4 == 0, "descriptors are fetched four at a time");
 
 // Requires len >= AGG_LAG + 1 (host-checked) and AGG_PF positions of over-read slack
 // behind every line end (the volumes are allocated with it).
@@ -108,23 +107,19 @@ k_agg_walk(Dims dm, ViewPtrs v0, ViewPtrs v1, int wsel, int nb_main)
     const int line = (int)(chain / npair), d = AGG_NC * (int)(chain % npair);
 
     const size_t cstride = VERT ? (size_t)W * pitch : (size_t)pitch;  // floats between consecutive positions
-    const size_t astride = VERT ? (size_t)W : 1;
     const size_t line_px = VERT ? (size_t)line : (size_t)line * W;
     const float* in_ptr = part + line_px * pitch + d;
     float* out_ptr = part + line_px * pitch + d;
-    const uint32_t* arm_line = reinterpret_cast<const uint32_t*>(v.arms) + line_px;
-    const double* inv_line = v.inv_wsize + (size_t)wsel * H * W + line_px;
-    const uint32_t* arm_ptr = arm_line;
-    const double* inv_ptr = inv_line;
+    const uint32_t* desc_line = VERT ? v.desc_v + (size_t)line * dm.Hd() : v.desc_h + (size_t)line * dm.Wd();
+    const uint32_t* desc_ptr = desc_line;
 
     const uint32_t ring0 = (uint32_t)__cvta_generic_to_shared(ring_raw) + threadIdx.x * (8 * AGG_NC);
     double P0 = 0.0, P1 = 0.0;
     st_ring(ring0 + AGG_P0 * AGG_SLOT, 0.0, 0.0);  // P[0]
 
     // output o, given the (possibly virtual) slot byte offset `top` of P[o + 34]
-    auto output = [&](uint32_t top, uint32_t armw, double inv) {
-        int a, b;
-        arm_pair<VERT>(armw, a, b);
+    auto output = [&](uint32_t top, uint32_t desc) {
+        const int a = desc & 0xff, b = (desc >> 8) & 0xff;
         int s1 = (int)top - (AGG_LAG - b) * AGG_SLOT;      // P[o + b + 1]
         int s0 = (int)top - (AGG_LAG + 1 + a) * AGG_SLOT;  // P[o - a]
         s1 += (s1 < 0) ? AGG_RING_BYTES : 0;
@@ -134,8 +129,9 @@ k_agg_walk(Dims dm, ViewPtrs v0, ViewPtrs v1, int wsel, int nb_main)
         ld_ring(ring0 + s0, l0, l1);
         float r0 = __double2float_rn(h0 - l0), r1 = __double2float_rn(h1 - l1);
         if (NORM) {
-            r0 = __double2float_rn((double)r0 * inv);
-            r1 = __double2float_rn((double)r1 * inv);
+            const float n = (float)(desc >> 16);
+            r0 = __fdiv_rn(r0, n);
+            r1 = __fdiv_rn(r1, n);
         }
         st_stream(out_ptr, r0, r1);
         out_ptr += cstride;
@@ -169,19 +165,18 @@ k_agg_walk(Dims dm, ViewPtrs v0, ViewPtrs v1, int wsel, int nb_main)
     // processed.  Batching matters: a warp has only six scoreboard slots and a slot completes
     // when ALL loads charged to it have landed, so independent loads must be grouped by the
     // time they are needed, not interleaved one per step.
-    float2 vin[2][AGG_PF];
-    uint32_t av[2][AGG_PF];
-    double iv[2][AGG_PF];
+    float2 vin[AGG_NBUF][AGG_PF];
+    uint32_t av[AGG_NBUF][AGG_PF];
     auto load_batch = [&](int buf) {
 #pragma unroll
-        for (int u = 0; u < AGG_PF; ++u) {
-            vin[buf][u] = ld_stream(in_ptr + (size_t)u * cstride);
-            av[buf][u] = arm_ptr[(size_t)u * astride];
-            iv[buf][u] = NORM ? inv_ptr[(size_t)u * astride] : 0.0;
+        for (int u = 0; u < AGG_PF; ++u) vin[buf][u] = ld_stream(in_ptr + (size_t)u * cstride);
+#pragma unroll
+        for (int j = 0; j < AGG_PF / 4; ++j) {
+            const uint4 q = *reinterpret_cast<const uint4*>(desc_ptr + 4 * j);
+            av[buf][4 * j + 0] = q.x; av[buf][4 * j + 1] = q.y; av[buf][4 * j + 2] = q.z; av[buf][4 * j + 3] = q.w;
         }
         in_ptr += (size_t)AGG_PF * cstride;
-        arm_ptr += (size_t)AGG_PF * astride;
-        inv_ptr += (size_t)AGG_PF * astride;
+        desc_ptr += AGG_PF;
     };
     auto run_batch = [&](int buf, int nsteps) {  // nsteps == AGG_PF in the steady state
 #pragma unroll
@@ -191,37 +186,40 @@ k_agg_walk(Dims dm, ViewPtrs v0, ViewPtrs v1, int wsel, int nb_main)
                 P1 += (double)vin[buf][u].y;
                 const uint32_t slot = nx + u * AGG_SLOT;
                 st_ring(ring0 + slot, P0, P1);
-                output(slot, av[buf][u], iv[buf][u]);
+                output(slot, av[buf][u]);
             }
         }
     };
     const int nB = len - AGG_LAG;
     uint32_t newest = hs;  // slot of the newest prefix
     int done = 0;
-    load_batch(0);
-    for (; done + 2 * AGG_PF <= nB; done += 2 * AGG_PF) {
-        load_batch(1);
-        run_batch(0, AGG_PF);
-        nx += AGG_PF * AGG_SLOT;
-        if (nx == AGG_RING_BYTES) nx = 0;
-        load_batch(0);
-        run_batch(1, AGG_PF);
-        nx += AGG_PF * AGG_SLOT;
-        if (nx == AGG_RING_BYTES) nx = 0;
-    }
-    // tail: fewer than 2*AGG_PF steps left; buffer 0 is loaded (possibly over-reading the slack)
-    {
-        int rem = nB - done;
-        if (rem > AGG_PF) load_batch(1);
-        const int n0 = rem < AGG_PF ? rem : AGG_PF;
-        run_batch(0, n0);
-        if (n0 > 0) newest = nx + (uint32_t)(n0 - 1) * AGG_SLOT;
-        else newest = (nx == 0 ? AGG_RING_BYTES : nx) - AGG_SLOT;
-        if (rem > AGG_PF) {
+    // AGG_NBUF register buffers: NBUF-1 batches are in flight while one is being processed.
+#pragma unroll
+    for (int b = 0; b < AGG_NBUF - 1; ++b) load_batch(b);
+    for (; done + AGG_NBUF * AGG_PF <= nB; done += AGG_NBUF * AGG_PF) {
+#pragma unroll
+        for (int b = 0; b < AGG_NBUF; ++b) {
+            load_batch((b + AGG_NBUF - 1) % AGG_NBUF);
+            run_batch(b, AGG_PF);
             nx += AGG_PF * AGG_SLOT;
             if (nx == AGG_RING_BYTES) nx = 0;
-            run_batch(1, rem - AGG_PF);
-            newest = nx + (uint32_t)(rem - AGG_PF - 1) * AGG_SLOT;
+        }
+    }
+    // tail: fewer than NBUF*PF steps left; buffers 0 .. NBUF-2 already hold the next batches
+    {
+        int rem = nB - done;
+        newest = (nx == 0 ? AGG_RING_BYTES : nx) - AGG_SLOT;
+#pragma unroll
+        for (int b = 0; b < AGG_NBUF; ++b) {
+            if (rem > 0) {
+                if (b == AGG_NBUF - 1) load_batch(b);  // the one buffer that was not prefetched
+                const int n = rem < AGG_PF ? rem : AGG_PF;
+                run_batch(b, n);
+                newest = nx + (uint32_t)(n - 1) * AGG_SLOT;
+                nx += AGG_PF * AGG_SLOT;
+                if (nx == AGG_RING_BYTES) nx = 0;
+                rem -= n;
+            }
         }
     }
     // ---- drain: o = len-LAG .. len-1.  Newest prefix stays P[len]; the virtual slot of P[o+34]
@@ -230,7 +228,7 @@ k_agg_walk(Dims dm, ViewPtrs v0, ViewPtrs v1, int wsel, int nb_main)
         const int o = len - AGG_LAG + j;
         uint32_t top = newest + (uint32_t)(j + 1) * AGG_SLOT;
         top -= (top >= AGG_RING_BYTES) ? AGG_RING_BYTES : 0;
-        output(top, arm_line[(size_t)o * astride], NORM ? inv_line[(size_t)o * astride] : 0.0);
+        output(top, desc_line[o]);
     }
 }
 
@@ -259,9 +257,8 @@ k_agg_small(Dims dm, ViewPtrs v0, ViewPtrs v1, int wsel, int nb_main)
     const int line = (int)(chain / nd), d = (int)(chain % nd);
     const size_t line_px = VERT ? (size_t)line : (size_t)line * W;
     float* cell = part + line_px * pitch + d;
-    const size_t cstride = VERT ? (size_t)W * pitch : (size_t)pitch, astride = VERT ? (size_t)W : 1;
-    const uint32_t* arm = reinterpret_cast<const uint32_t*>(v.arms) + line_px;
-    const double* inv = v.inv_wsize + (size_t)wsel * H * W + line_px;
+    const size_t cstride = VERT ? (size_t)W * pitch : (size_t)pitch;
+    const uint32_t* desc = VERT ? v.desc_v + (size_t)line * dm.Hd() : v.desc_h + (size_t)line * dm.Wd();
     double* my = sring + threadIdx.x;
     my[0] = 0.0;
     double P = 0.0;
@@ -274,14 +271,14 @@ k_agg_small(Dims dm, ViewPtrs v0, ViewPtrs v1, int wsel, int nb_main)
             my[head * AGS_BLOCK] = P;
         }
         if (o >= 0 && o < len) {
-            int a, b;
-            arm_pair<VERT>(arm[(size_t)o * astride], a, b);
+            const uint32_t w = desc[o];
+            const int a = w & 0xff, b = (w >> 8) & 0xff;
             const int newest = (t < len) ? t + 1 : len;
             int s1 = head - (newest - (o + b + 1)), s0 = head - (newest - (o - a));
             s1 += (s1 < 0) ? AGS_RING : 0;
             s0 += (s0 < 0) ? AGS_RING : 0;
             float r = __double2float_rn(my[s1 * AGS_BLOCK] - my[s0 * AGS_BLOCK]);
-            if (NORM) r = __double2float_rn((double)r * inv[(size_t)o * astride]);
+            if (NORM) r = __fdiv_rn(r, (float)(w >> 16));
             cell[(size_t)o * cstride] = r;
         }
     }
@@ -320,9 +317,9 @@ static void launch_walk(const Launcher& L, const Dims& d, const ViewPtrs& left, 
 
 size_t aggregate_overread_floats(const Dims& d)
 {
-    // k_agg_walk prefetches up to 2*AGG_PF positions past the end of a line; the vertical pass
+    // k_agg_walk prefetches up to AGG_NBUF*AGG_PF positions past the end of a line; the vertical pass
     // therefore touches that many rows behind each part of the volume (pitch <= max(Dm, Rp)).
-    return (size_t)(2 * AGG_PF + 1) * d.W * (size_t)(d.Dm > d.Rp ? d.Dm : d.Rp);
+    return (size_t)(AGG_U + 1) * d.W * (size_t)(d.Dm > d.Rp ? d.Dm : d.Rp);
 }
 
 void aggregate(const Launcher& L, const Dims& d, const ViewPtrs& left, const ViewPtrs& right)

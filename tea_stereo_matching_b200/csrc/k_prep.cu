@@ -107,15 +107,18 @@ __global__ void k_arms(const uint32_t* __restrict__ img4, uchar4* __restrict__ a
     arms[(size_t)y * W + x] = a;
 }
 
-// ---- cross-window sizes -----------------------------------------------------
-// aggregation1D propagates the window size like a cost (ADCensus.cpp:716) starting
-// from all ones (:733): horizontal-first -> N = sum over the vertical arm of the row
-// lengths; vertical-first -> sum over the horizontal arm of the column lengths.
-__global__ void k_wsize(const uchar4* __restrict__ arms, double* __restrict__ inv_wsize, int H, int W)
+// ---- aggregation step descriptors -----------------------------------------------
+// aggregation1D propagates the window size like a cost (ADCensus.cpp:716) starting from all
+// ones (:733): horizontal-first iteration -> N_hf = sum over the vertical arm of the row
+// lengths; vertical-first -> N_vf = sum over the horizontal arm of the column lengths.
+// The pass that ENDS an iteration divides by N (:743-749): a vertical pass ends a
+// horizontal-first iteration (N_hf), a horizontal pass a vertical-first one (N_vf).
+__global__ void k_agg_desc(const uchar4* __restrict__ arms, uint32_t* __restrict__ desc_h, uint32_t* __restrict__ desc_v,
+                           int H, int W, int Wd, int Hd)
 {
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
     if (x >= W || y >= H) return;
-    const size_t npx = (size_t)H * W, p = (size_t)y * W + x;
+    const size_t p = (size_t)y * W + x;
     const uchar4 a = arms[p];
     int nh = 0, nv = 0;
     for (int j = -(int)a.x; j <= (int)a.y; ++j) {
@@ -126,8 +129,8 @@ __global__ void k_wsize(const uchar4* __restrict__ arms, double* __restrict__ in
         const uchar4 q = arms[p + j];
         nv += q.x + q.y + 1;
     }
-    inv_wsize[p] = __drcp_rn((double)nh);
-    inv_wsize[npx + p] = __drcp_rn((double)nv);
+    desc_h[(size_t)y * Wd + x] = (uint32_t)a.z | ((uint32_t)a.w << 8) | ((uint32_t)nv << 16);
+    desc_v[(size_t)x * Hd + y] = (uint32_t)a.x | ((uint32_t)a.y << 8) | ((uint32_t)nh << 16);
 }
 
 // ---- similarity flags ---------------------------------------------------------
@@ -167,7 +170,7 @@ __global__ void k_tflags(const uint8_t* __restrict__ flags, uint16_t* __restrict
 }
 
 void prep_view(const Launcher& L, const Dims& d, int view, const uint8_t* img, uint32_t* img4, uint64_t* census,
-               uchar4* arms, double* inv_wsize, uint8_t* flags, uint16_t* tflags)
+               uchar4* arms, uint32_t* desc_h, uint32_t* desc_v, uint8_t* flags, uint16_t* tflags)
 {
     const size_t npx = d.npx();
     k_pack_bgrx<<<(unsigned)((npx + 255) / 256), 256, 0, L.stream>>>(img, img4, npx);
@@ -175,7 +178,7 @@ void prep_view(const Launcher& L, const Dims& d, int view, const uint8_t* img, u
     k_census<<<cg, cb, 0, L.stream>>>(img4, census, d.H, d.W);
     dim3 b(32, 8), g((d.W + 31) / 32, (d.H + 7) / 8);
     k_arms<<<g, b, 0, L.stream>>>(img4, arms, d.H, d.W);
-    k_wsize<<<g, b, 0, L.stream>>>(arms, inv_wsize, d.H, d.W);
+    k_agg_desc<<<g, b, 0, L.stream>>>(arms, desc_h, desc_v, d.H, d.W, d.Wd(), d.Hd());
     k_flags<<<g, b, 0, L.stream>>>(img4, flags, d.H, d.W);
     // the LEFT image's table is read by the right volume at x - d (s = -1), the right one's at x + d
     dim3 tg((d.W + 2 * kTfPad + 127) / 128, d.H);

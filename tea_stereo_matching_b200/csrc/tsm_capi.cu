@@ -39,7 +39,7 @@ struct tsm_ctx {
     bool have_pair = false;
 
     // device buffers
-    Buf img[2], img4[2], census[2], arms[2], wsize[2], flags[2], tflags[2], vol[2], vtail[2], wta_[2];
+    Buf img[2], img4[2], census[2], arms[2], desc_h[2], desc_v[2], flags[2], tflags[2], vol[2], vtail[2], wta_[2];
     Buf dense;  // [H][W][Dn] staging for volume taps / pokes
     bool stage_mode = false;  // tsm_stage_run: keep every tap-able buffer complete
     Buf disp[2], fin, ftmp;
@@ -188,7 +188,8 @@ int ensure_arena(tsm_ctx* c, const tsm_adcensus_config* cfg, int H, int W)
         if ((rc = ensure(c, c->img4[k], npx * 4))) return rc;
         if ((rc = ensure(c, c->census[k], npx * 6 * 8))) return rc;
         if ((rc = ensure(c, c->arms[k], npx * 4))) return rc;
-        if ((rc = ensure(c, c->wsize[k], npx * 2 * 8))) return rc;
+        if ((rc = ensure(c, c->desc_h[k], ((size_t)H * d.Wd() + 256) * 4, true))) return rc;
+        if ((rc = ensure(c, c->desc_v[k], ((size_t)W * d.Hd() + 256) * 4, true))) return rc;
         if ((rc = ensure(c, c->flags[k], npx))) return rc;
         if ((rc = ensure(c, c->tflags[k], (size_t)2 * H * (W + 2 * kTfPad) * 2))) return rc;
         if ((rc = ensure(c, c->vol[k], (npx * d.Dm + aggregate_overread_floats(d)) * 4 + 256, true))) return rc;
@@ -225,7 +226,8 @@ ViewPtrs view_ptrs(tsm_ctx* c, int k)
     v.img4 = (const uint32_t*)c->img4[k].p;
     v.census = (const uint64_t*)c->census[k].p;
     v.arms = (const uchar4*)c->arms[k].p;
-    v.inv_wsize = (const double*)c->wsize[k].p;
+    v.desc_h = (const uint32_t*)c->desc_h[k].p;
+    v.desc_v = (const uint32_t*)c->desc_v[k].p;
     v.flags = (const uint8_t*)c->flags[k].p;
     v.tflags = (const uint16_t*)c->tflags[k].p;
     v.vol.main = (float*)c->vol[k].p;
@@ -267,7 +269,8 @@ int run_stages(tsm_ctx* c, int mask, int arg)
         ScopedStage s(c, "prep");
         for (int k = 0; k < 2; ++k)
             prep_view(L, d, k, (const uint8_t*)c->img[k].p, (uint32_t*)c->img4[k].p, (uint64_t*)c->census[k].p,
-                      (uchar4*)c->arms[k].p, (double*)c->wsize[k].p, (uint8_t*)c->flags[k].p, (uint16_t*)c->tflags[k].p);
+                      (uchar4*)c->arms[k].p, (uint32_t*)c->desc_h[k].p, (uint32_t*)c->desc_v[k].p, (uint8_t*)c->flags[k].p,
+                      (uint16_t*)c->tflags[k].p);
     }
     if (mask & TSM_STAGE_INIT) {
         ScopedStage s(c, "cost_init");
@@ -432,7 +435,7 @@ void tsm_destroy(tsm_ctx* c)
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     Buf* all[] = {&c->img[0], &c->img[1], &c->img4[0], &c->img4[1], &c->census[0], &c->census[1], &c->arms[0], &c->arms[1],
-                  &c->wsize[0], &c->wsize[1], &c->flags[0], &c->flags[1], &c->tflags[0], &c->tflags[1], &c->vtail[0], &c->vtail[1], &c->dense, &c->vol[0], &c->vol[1], &c->wta_[0], &c->wta_[1],
+                  &c->desc_h[0], &c->desc_h[1], &c->desc_v[0], &c->desc_v[1], &c->flags[0], &c->flags[1], &c->tflags[0], &c->tflags[1], &c->vtail[0], &c->vtail[1], &c->dense, &c->vol[0], &c->vol[1], &c->wta_[0], &c->wta_[1],
                   &c->disp[0], &c->disp[1], &c->fin, &c->ftmp, &c->v_vote, &c->v_lowcnt, &c->v_off, &c->v_mark, &c->v_start,
                   &c->v_sums, &c->v_flat, &c->e_gray, &c->e_blur, &c->e_mag, &c->e_gx, &c->e_gy, &c->e_map, &c->e_edges,
                   &c->e_hist, &c->e_lut, &c->e_changed, &c->tab_ad, &c->tab_c, &c->r_src, &c->r_map1[0], &c->r_map1[1],
