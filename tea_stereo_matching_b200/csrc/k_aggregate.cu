@@ -80,7 +80,7 @@ __device__ __forceinline__ void st_stream(float* p, float a, float b)
     else asm volatile("st.global.L1::no_allocate.f32 [%0], %1;" ::"l"(p), "f"(a) : "memory");
 }
 
-static_assert(AGG_PF % 4 == 0, "descriptors are fetched four at a time");
+static_assert(AGG_PF % 4 == 0, "descriptors are fetched four at a time; batches run in sub-blocks of 4");
 
 // Requires len >= AGG_LAG + 1 (host-checked) and AGG_PF positions of over-read slack
 // behind every line end (the volumes are allocated with it).
@@ -178,15 +178,51 @@ k_agg_walk(Dims dm, ViewPtrs v0, ViewPtrs v1, int wsel, int nb_main)
         in_ptr += (size_t)AGG_PF * cstride;
         desc_ptr += AGG_PF;
     };
+    // One batch = AGG_PF steps, processed in sub-blocks of 4: (A) the four prefix pushes and their ring
+    // stores, (B) all eight ring loads, (C) the four outputs.  A warp issues in order, so finishing
+    // step u right after its own ring loads would expose the LDS -> DADD -> F2F -> STG latency on every
+    // step; grouped like this it is paid once per four steps.
     auto run_batch = [&](int buf, int nsteps) {  // nsteps == AGG_PF in the steady state
 #pragma unroll
-        for (int u = 0; u < AGG_PF; ++u) {
-            if (u < nsteps) {
-                P0 += (double)vin[buf][u].x;
-                P1 += (double)vin[buf][u].y;
-                const uint32_t slot = nx + u * AGG_SLOT;
-                st_ring(ring0 + slot, P0, P1);
-                output(slot, av[buf][u]);
+        for (int u0 = 0; u0 < AGG_PF; u0 += 4) {
+            double h0[4], h1[4], l0[4], l1[4];
+#pragma unroll
+            for (int w = 0; w < 4; ++w) {
+                const int u = u0 + w;
+                if (u < nsteps) {
+                    P0 += (double)vin[buf][u].x;
+                    P1 += (double)vin[buf][u].y;
+                    st_ring(ring0 + nx + u * AGG_SLOT, P0, P1);
+                }
+            }
+#pragma unroll
+            for (int w = 0; w < 4; ++w) {
+                const int u = u0 + w;
+                if (u < nsteps) {
+                    const uint32_t desc = av[buf][u];
+                    const int a = desc & 0xff, b = (desc >> 8) & 0xff;
+                    const uint32_t top = nx + u * AGG_SLOT;
+                    int s1 = (int)top - (AGG_LAG - b) * AGG_SLOT;      // P[o + b + 1]
+                    int s0 = (int)top - (AGG_LAG + 1 + a) * AGG_SLOT;  // P[o - a]
+                    s1 += (s1 < 0) ? AGG_RING_BYTES : 0;
+                    s0 += (s0 < 0) ? AGG_RING_BYTES : 0;
+                    ld_ring(ring0 + s1, h0[w], h1[w]);
+                    ld_ring(ring0 + s0, l0[w], l1[w]);
+                }
+            }
+#pragma unroll
+            for (int w = 0; w < 4; ++w) {
+                const int u = u0 + w;
+                if (u < nsteps) {
+                    float r0 = __double2float_rn(h0[w] - l0[w]), r1 = __double2float_rn(h1[w] - l1[w]);
+                    if (NORM) {
+                        const float n = (float)(av[buf][u] >> 16);
+                        r0 = __fdiv_rn(r0, n);
+                        r1 = __fdiv_rn(r1, n);
+                    }
+                    st_stream(out_ptr, r0, r1);
+                    out_ptr += cstride;
+                }
             }
         }
     };
