@@ -146,13 +146,15 @@ __global__ void k_flags(const uint32_t* __restrict__ img4, uint8_t* __restrict__
     flags[p] = f;
 }
 
-// ---- strided flag tables for the scanline kernels ---------------------------------
-// tflags[plane][y][kTfPad + c] bit k = flag bit `plane` of pixel (y, c + s*32k), 0 outside
-// the image, for c in [-kTfPad, W + kTfPad).  A lane of the scanline warp that handles
-// d = lane + 32k (k = 0..K-1) then gets all its K similarity bits with one 16-bit load.
-__global__ void k_tflags(const uint8_t* __restrict__ flags, uint16_t* __restrict__ tflags, int H, int W, int s, int K)
+// ---- scan tables for the scanline kernels -------------------------------------------
+// stab[plane][y][kTfPad + c], c in [-kTfPad, pitch - kTfPad):
+//   bits 0..15: flag bit `plane` of the OTHER image at (y, c + s*32k), k = 0..K-1, 0 outside the image --
+//               a lane of the scanline warp that handles d = lane + 32k gets all its K similarity
+//               bits from the one word at column x + s*lane;
+//   bit 31    : flag bit `plane` of the OWN image at (y, c).
+__global__ void k_scan_table(const uint8_t* __restrict__ fown, const uint8_t* __restrict__ foth, uint32_t* __restrict__ stab,
+                             int H, int W, int Wp, int s, int K)
 {
-    const int Wp = W + 2 * kTfPad;
     const int cx = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
     if (cx >= Wp) return;
     const int c = cx - kTfPad;
@@ -160,17 +162,33 @@ __global__ void k_tflags(const uint8_t* __restrict__ flags, uint16_t* __restrict
     for (int k = 0; k < K; ++k) {
         const int x = c + s * 32 * k;
         if (x >= 0 && x < W) {
-            const unsigned f = flags[(size_t)y * W + x];
+            const unsigned f = foth[(size_t)y * W + x];
             tv |= (f & 1u) << k;
             th |= ((f >> 1) & 1u) << k;
         }
     }
-    tflags[(size_t)y * Wp + cx] = (uint16_t)tv;
-    tflags[(size_t)H * Wp + (size_t)y * Wp + cx] = (uint16_t)th;
+    if (c >= 0 && c < W) {
+        const unsigned f = fown[(size_t)y * W + c];
+        tv |= (f & 1u) << 31;
+        th |= ((f >> 1) & 1u) << 31;
+    }
+    stab[(size_t)y * Wp + cx] = tv;
+    stab[(size_t)H * Wp + (size_t)y * Wp + cx] = th;
+}
+
+void prep_scan_tables(const Launcher& L, const Dims& d, const uint8_t* flags_left, const uint8_t* flags_right,
+                      uint32_t* stab_left, uint32_t* stab_right)
+{
+    const int Wp = d.stab_pitch(), K = (d.Dn + 31) / 32;
+    dim3 tg((Wp + 127) / 128, d.H);
+    // the left volume looks at the right image at x + d, the right volume at the left image at x - d
+    k_scan_table<<<tg, 128, 0, L.stream>>>(flags_left, flags_right, stab_left, d.H, d.W, Wp, 1, K);
+    k_scan_table<<<tg, 128, 0, L.stream>>>(flags_right, flags_left, stab_right, d.H, d.W, Wp, -1, K);
+    L.count(2);
 }
 
 void prep_view(const Launcher& L, const Dims& d, int view, const uint8_t* img, uint32_t* img4, uint64_t* census,
-               uchar4* arms, uint32_t* desc_h, uint32_t* desc_v, uint8_t* flags, uint16_t* tflags)
+               uchar4* arms, uint32_t* desc_h, uint32_t* desc_v, uint8_t* flags)
 {
     const size_t npx = d.npx();
     k_pack_bgrx<<<(unsigned)((npx + 255) / 256), 256, 0, L.stream>>>(img, img4, npx);
@@ -180,10 +198,7 @@ void prep_view(const Launcher& L, const Dims& d, int view, const uint8_t* img, u
     k_arms<<<g, b, 0, L.stream>>>(img4, arms, d.H, d.W);
     k_agg_desc<<<g, b, 0, L.stream>>>(arms, desc_h, desc_v, d.H, d.W, d.Wd(), d.Hd());
     k_flags<<<g, b, 0, L.stream>>>(img4, flags, d.H, d.W);
-    // the LEFT image's table is read by the right volume at x - d (s = -1), the right one's at x + d
-    dim3 tg((d.W + 2 * kTfPad + 127) / 128, d.H);
-    k_tflags<<<tg, 128, 0, L.stream>>>(flags, tflags, d.H, d.W, view == 0 ? -1 : 1, (d.Dn + 31) / 32);
-    L.count(6);
+    L.count(5);
 }
 
 }  // namespace tsm

@@ -20,9 +20,17 @@
 // horizontal ones) and walks it forward then backward; the predecessor's updated cost
 // vector stays in registers (lanes over d, d = lane + 32k); the d-1 / d+1 neighbours
 // come from two rotate-shuffles per register.  The other view's similarity bits for all
-// K registers of a lane arrive as ONE 16-bit word (tflags, see k_prep.cu).  Inputs of the
-// next pixels do not depend on the recurrence: they are loaded SCAN_PF steps ahead into a
-// register ring.  The pass pair (down+up, right+left) is one launch; both views share it.
+// K registers of a lane, plus the own-view bit, arrive as ONE 32-bit word (scan table, see
+// k_prep.cu).  The pass pair (down+up, right+left) is one launch; both views share it.
+//
+// Inputs of the next pixels do not depend on the recurrence, so they are streamed by TMA:
+// lane 0 of every warp issues cp.async.bulk copies (the 128-byte aligned main part of the
+// pixel's cost vector, its tail chunk and a 144-byte window of the scan table) SC_NST steps
+// ahead into a per-warp shared-memory ring; each stage completes on its own mbarrier
+// (expect_tx bytes).  Completion is tracked by the mbarrier, not by register scoreboards,
+// so the loads really stay in flight across the shuffle / REDUX waits of the recurrence
+// (a register prefetch ring measured 4.2 + 3.5 ms per pair: every short-scoreboard wait also
+// waited for the DRAM loads sharing its slot).
 #include "tsm_common.cuh"
 #include <limits.h>
 #include <math_constants.h>
@@ -30,37 +38,58 @@
 namespace tsm {
 
 constexpr int SCAN_WARPS = 4;
-constexpr int SCAN_PF = 4;           // prefetch distance
-constexpr int SCAN_U = 2 * SCAN_PF;  // unroll factor = length of the register rings
+constexpr int SC_NST = 8;    // TMA stages (steps in flight) per warp
+constexpr int SC_WIN = 36;   // scan-table words fetched per step (32 lanes + 16-byte alignment slack)
 
 struct ScanParams {
     float p1[3];
     float p2[3];
     int store_right_final;  // 0: the last pass of the right volume only feeds its WTA
+    int stage_bytes;        // Dm*4 + tail chunk + table window, multiple of 16
+    int tail_bytes;         // bytes of the tail chunk copied per step (0 when Dn % 32 == 0)
 };
 
-struct StepIn {
-    const float* src;      // main part of the pixel's cost vector (128-byte aligned)
-    const float* tsrc;     // tail part (disparities >= Dm); read by the last register only
-    const uint16_t* tf;    // other-view flag word of lane 0 for this pixel (lane l reads tf[sgn*l])
-    const uint8_t* own;    // own-view flag byte
-};
-
-template <int K>
-__device__ __forceinline__ void load_step(float (&cur)[K], unsigned& tf, unsigned& own, const StepIn& in, int lane, int sgn,
-                                          int ownbit, bool has_tail, bool lastvalid)
+// ---- mbarrier / TMA bulk-copy primitives (sm_90+ PTX) ----
+__device__ __forceinline__ void mbar_init(uint32_t bar, unsigned count)
 {
-#pragma unroll
-    for (int k = 0; k < K; ++k) {
-        if (k < K - 1 || !has_tail) cur[k] = in.src[lane + 32 * k];
-        else cur[k] = lastvalid ? in.tsrc[lane] : CUDART_INF_F;
-    }
-    tf = in.tf[sgn * lane];
-    own = (*in.own >> ownbit) & 1u;
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, unsigned parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "DONE:\n"
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(uint32_t dst, const void* src, unsigned bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ float lds_f32(uint32_t a)
+{
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
 }
 
-// Updates prev (the predecessor's vector) to the new vector of this pixel; returns through
-// `store` whether the pixel changed (m != 0).
+// Updates prev (the predecessor's vector) to the new vector of this pixel; returns whether
+// the pixel changed (m != 0).
 template <int K>
 __device__ __forceinline__ bool scan_step(float (&prev)[K], const float (&cur)[K], unsigned tf, unsigned own, int lane,
                                           const ScanParams& sp)
@@ -124,75 +153,101 @@ __device__ __forceinline__ int warp_argmin(const float (&v)[K], int lane)
     return (int)__reduce_min_sync(0xffffffffu, bb == gmin ? (unsigned)bd : 0x7fffffffu);
 }
 
+// Per-warp pipeline state: stage ring + mbarriers live in shared memory.
+struct ScanPipe {
+    uint32_t stage0;  // shared address of stage 0
+    uint32_t bar0;    // shared address of mbarrier 0
+    unsigned it;      // steps consumed so far (stage = it % SC_NST, parity = (it / SC_NST) & 1)
+};
+
 // One direction of one line: `count` pixels starting at `first`, stepping by `dir` (+1/-1);
 // the predecessor of a pixel is the previous one on the path.
-//   VERT : pixel stride = W*Dp floats; flag row = row of max(pos, pred), flag bit 0
-//   HORZ : pixel stride = Dp floats;   flag col = max(pos, pred),        flag bit 1
+//   VERT : pixel stride = one image row; flag pixel = (max(pos, pred), line), table plane 0
+//   HORZ : pixel stride = one pixel;     flag pixel = (line, max(pos, pred)), table plane 1
 template <int K, bool VERT, bool WTA>
-__device__ __forceinline__ void scan_dir(float (&prev)[K], const Vol& vol, const uint8_t* __restrict__ fown,
-                                         const uint16_t* __restrict__ tfo, const Dims& dm, int line, int first, int dir,
-                                         int count, int sgn, int lane, bool has_tail, bool lastvalid, bool do_store,
-                                         int32_t* wta_out, const ScanParams& sp)
+__device__ __forceinline__ void scan_dir(float (&prev)[K], const Vol& vol, const uint32_t* __restrict__ stab, const Dims& dm,
+                                         ScanPipe& pipe, int line, int first, int dir, int count, int sgn, int lane,
+                                         bool has_tail, bool lastvalid, bool do_store, int32_t* wta_out, const ScanParams& sp)
 {
-    const int W = dm.W, Wp = dm.W + 2 * kTfPad;
-    const int ownbit = VERT ? 0 : 1;
-    // element strides per step
+    const int W = dm.W, Wp = dm.stab_pitch();
+    const uint32_t* tab = stab + (size_t)(VERT ? 0 : 1) * dm.H * Wp;
+    const unsigned main_bytes = (unsigned)dm.Dm * 4u, tail_bytes = (unsigned)sp.tail_bytes;
+    const unsigned total_bytes = main_bytes + tail_bytes + SC_WIN * 4u;
+    const int lo_off = sgn > 0 ? 0 : -31;  // lowest table column a lane reads, relative to the flag column
+
+    // geometry of step i
+    auto pixel = [&](int i, int& y, int& x, int& fy, int& fx) {
+        const int pos = first + i * dir;
+        y = VERT ? pos : line;
+        x = VERT ? line : pos;
+        fy = VERT ? (dir > 0 ? pos : pos + 1) : line;
+        fx = VERT ? line : (dir > 0 ? pos : pos + 1);
+    };
+    // lane 0: arm the stage's mbarrier and launch the three bulk copies of step i
+    auto issue = [&](int i, unsigned slot) {
+        int y, x, fy, fx;
+        pixel(i, y, x, fy, fx);
+        const size_t p = (size_t)y * W + x;
+        const uint32_t st = pipe.stage0 + slot * (unsigned)sp.stage_bytes, bar = pipe.bar0 + slot * 8u;
+        mbar_expect_tx(bar, total_bytes);
+        if (main_bytes) tma_load_1d(st, vol.main + p * dm.Dm, main_bytes, bar);
+        if (tail_bytes) {
+            const size_t te = dm.Rp >= 4 ? p * dm.Rp : (p & ~(size_t)1) * 2;
+            tma_load_1d(st + main_bytes, vol.tail + te, tail_bytes, bar);
+        }
+        const int a = (kTfPad + fx + lo_off) & ~3;
+        tma_load_1d(st + main_bytes + tail_bytes, tab + (size_t)fy * Wp + a, SC_WIN * 4u, bar);
+    };
+
+    if (lane == 0) {
+        for (int i = 0; i < SC_NST && i < count; ++i) issue(i, (pipe.it + i) % SC_NST);
+    }
+    float* dst = nullptr;
+    float* tdst = nullptr;
+    int32_t* wdst = nullptr;
+    {
+        int y, x, fy, fx;
+        pixel(0, y, x, fy, fx);
+        const size_t p = (size_t)y * W + x;
+        dst = vol.main + p * dm.Dm;
+        tdst = vol.tail + p * dm.Rp;
+        if (WTA) wdst = wta_out + p;
+    }
     const ptrdiff_t vstep = (ptrdiff_t)dir * (VERT ? (ptrdiff_t)W * dm.Dm : (ptrdiff_t)dm.Dm);
     const ptrdiff_t wstep = (ptrdiff_t)dir * (VERT ? (ptrdiff_t)W * dm.Rp : (ptrdiff_t)dm.Rp);
-    const ptrdiff_t fstep = (ptrdiff_t)dir * (VERT ? (ptrdiff_t)W : 1);
-    const ptrdiff_t tstep = (ptrdiff_t)dir * (VERT ? (ptrdiff_t)Wp : 1);
-    // position of the first pixel and of its flag pixel (= max(pos, pred))
-    const int y0 = VERT ? first : line, x0 = VERT ? line : first;
-    const int fy0 = VERT ? (dir > 0 ? first : first + 1) : line, fx0 = VERT ? line : (dir > 0 ? first : first + 1);
-    StepIn nxt;  // operands of step i + SCAN_PF
-    nxt.src = vol.main + ((size_t)y0 * W + x0) * dm.Dm;
-    nxt.tsrc = vol.tail + ((size_t)y0 * W + x0) * dm.Rp;
-    nxt.own = fown + (size_t)fy0 * W + fx0;
-    nxt.tf = tfo + (size_t)(VERT ? 0 : 1) * dm.H * Wp + (size_t)fy0 * Wp + kTfPad + fx0;
-    float* dst = vol.main + ((size_t)y0 * W + x0) * dm.Dm;
-    float* tdst = vol.tail + ((size_t)y0 * W + x0) * dm.Rp;
-    int32_t* wdst = WTA ? wta_out + (size_t)y0 * W + x0 : nullptr;
+    const ptrdiff_t pstep = (ptrdiff_t)dir * (VERT ? (ptrdiff_t)W : 1);
 
-    // Register rings of 2*SCAN_PF entries: step i consumes entry i mod 2PF and refills entry
-    // (i + PF) mod 2PF (consumed PF steps earlier), so a load never targets a live register.
-    float cur[SCAN_U][K];
-    unsigned tf[SCAN_U], own[SCAN_U];
+    for (int i = 0; i < count; ++i) {
+        const unsigned slot = pipe.it % SC_NST, parity = (pipe.it / SC_NST) & 1u;
+        const uint32_t st = pipe.stage0 + slot * (unsigned)sp.stage_bytes;
+        int y, x, fy, fx;
+        pixel(i, y, x, fy, fx);
+        mbar_wait(pipe.bar0 + slot * 8u, parity);
+        float cur[K];
 #pragma unroll
-    for (int u = 0; u < SCAN_U; ++u) {
-        tf[u] = 0u;
-        own[u] = 0u;
-#pragma unroll
-        for (int k = 0; k < K; ++k) cur[u][k] = 0.f;
-    }
-#pragma unroll
-    for (int u = 0; u < SCAN_PF; ++u) {
-        if (u < count) load_step<K>(cur[u], tf[u], own[u], nxt, lane, sgn, ownbit, has_tail, lastvalid);
-        nxt.src += vstep;
-        nxt.tsrc += wstep;
-        nxt.own += fstep;
-        nxt.tf += tstep;
-    }
-    for (int i0 = 0; i0 < count; i0 += SCAN_U) {
-#pragma unroll
-        for (int u = 0; u < SCAN_U; ++u) {
-            const int i = i0 + u;
-            if (i < count) {
-                const int w = (u + SCAN_PF) % SCAN_U;
-                if (i + SCAN_PF < count) load_step<K>(cur[w], tf[w], own[w], nxt, lane, sgn, ownbit, has_tail, lastvalid);
-                nxt.src += vstep;
-                nxt.tsrc += wstep;
-                nxt.own += fstep;
-                nxt.tf += tstep;
-                const bool changed = scan_step<K>(prev, cur[u], tf[u], own[u], lane, sp);
-                if (changed && do_store) store_vec<K>(dst, tdst, prev, lane, has_tail, lastvalid);
-                dst += vstep;
-                tdst += wstep;
-                if (WTA) {
-                    const int best = warp_argmin<K>(prev, lane);
-                    if (lane == 0) *wdst = best;
-                    wdst += fstep;
-                }
+        for (int k = 0; k < K; ++k) {
+            if (k < K - 1 || !has_tail) cur[k] = lds_f32(st + (lane + 32 * k) * 4);
+            else {
+                const int toff = dm.Rp >= 4 ? 0 : (int)((((size_t)y * W + x) & 1) * 2);
+                cur[k] = lastvalid ? lds_f32(st + main_bytes + (toff + lane) * 4) : CUDART_INF_F;
             }
+        }
+        const int a = (kTfPad + fx + lo_off) & ~3;
+        const int w0 = kTfPad + fx - a;  // window index of the flag pixel itself
+        const uint32_t tw = lds_u32(st + main_bytes + tail_bytes + (w0 + sgn * lane) * 4);
+        const uint32_t ow = lds_u32(st + main_bytes + tail_bytes + w0 * 4);
+        __syncwarp();  // every lane has read the stage; it may be refilled
+        if (lane == 0 && i + SC_NST < count) issue(i + SC_NST, slot);
+        pipe.it++;
+
+        const bool changed = scan_step<K>(prev, cur, tw & 0xffffu, ow >> 31, lane, sp);
+        if (changed && do_store) store_vec<K>(dst, tdst, prev, lane, has_tail, lastvalid);
+        dst += vstep;
+        tdst += wstep;
+        if (WTA) {
+            const int best = warp_argmin<K>(prev, lane);
+            if (lane == 0) *wdst = best;
+            wdst += pstep;
         }
     }
 }
@@ -201,17 +256,29 @@ template <int K, bool VERT>
 __global__ void __launch_bounds__(SCAN_WARPS * 32)
 k_scanline(Dims dm, ViewPtrs v0, ViewPtrs v1, ScanParams sp, int32_t* wta0, int32_t* wta1)
 {
+    extern __shared__ __align__(128) unsigned char scan_smem[];
     const int view = blockIdx.y;
     const ViewPtrs& v = view ? v1 : v0;
-    const ViewPtrs& o = view ? v0 : v1;
-    const int lane = threadIdx.x & 31;
-    const int line = blockIdx.x * SCAN_WARPS + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int line = blockIdx.x * SCAN_WARPS + warp;
     const int nlines = VERT ? dm.W : dm.H, len = VERT ? dm.H : dm.W;
     if (line >= nlines) return;
     const int sgn = view == 0 ? 1 : -1;
     // K = ceil(Dn / 32) registers per lane; when Dn is not a multiple of 32 the last one holds the tail part
     const bool has_tail = dm.Rp != 0;
     const bool lastvalid = !has_tail || lane < dm.tail();
+
+    ScanPipe pipe;
+    const uint32_t warp_bytes = SC_NST * (unsigned)sp.stage_bytes + SC_NST * 8u;
+    pipe.stage0 = (uint32_t)__cvta_generic_to_shared(scan_smem) + warp * ((warp_bytes + 127u) & ~127u);
+    pipe.bar0 = pipe.stage0 + SC_NST * (unsigned)sp.stage_bytes;
+    pipe.it = 0;
+    if (lane == 0) {
+        for (int s = 0; s < SC_NST; ++s) mbar_init(pipe.bar0 + s * 8u, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+
     float prev[K];
     {
         const size_t p0 = VERT ? (size_t)line : (size_t)line * dm.W;
@@ -224,18 +291,21 @@ k_scanline(Dims dm, ViewPtrs v0, ViewPtrs v1, ScanParams sp, int32_t* wta0, int3
         }
     }
     // forward: pos = 1 .. len-1 (pred pos-1); backward: pos = len-2 .. 0 (pred pos+1).
-    scan_dir<K, VERT, false>(prev, v.vol, v.flags, o.tflags, dm, line, 1, 1, len - 1, sgn, lane, has_tail, lastvalid, true, nullptr, sp);
+    scan_dir<K, VERT, false>(prev, v.vol, v.stab, dm, pipe, line, 1, 1, len - 1, sgn, lane, has_tail, lastvalid, true, nullptr, sp);
+    // the backward pass re-reads (through the async proxy) what this warp has just written
+    asm volatile("fence.proxy.async;" ::: "memory");
+    __syncwarp();
     if (VERT) {
-        scan_dir<K, VERT, false>(prev, v.vol, v.flags, o.tflags, dm, line, len - 2, -1, len - 1, sgn, lane, has_tail, lastvalid,
-                                 true, nullptr, sp);
+        scan_dir<K, VERT, false>(prev, v.vol, v.stab, dm, pipe, line, len - 2, -1, len - 1, sgn, lane, has_tail, lastvalid, true,
+                                 nullptr, sp);
     } else {
         // last pass: fuse the WTA; pixel len-1 is final after the forward pass.
         int32_t* wta_out = view ? wta1 : wta0;
         const int best = warp_argmin<K>(prev, lane);
         if (lane == 0) wta_out[(size_t)line * dm.W + len - 1] = best;
         const bool do_store = view == 0 || sp.store_right_final != 0;
-        scan_dir<K, VERT, true>(prev, v.vol, v.flags, o.tflags, dm, line, len - 2, -1, len - 1, sgn, lane, has_tail, lastvalid,
-                                do_store, wta_out, sp);
+        scan_dir<K, VERT, true>(prev, v.vol, v.stab, dm, pipe, line, len - 2, -1, len - 1, sgn, lane, has_tail, lastvalid, do_store,
+                                wta_out, sp);
     }
 }
 
@@ -243,9 +313,20 @@ template <int K>
 static void launch_scan(const Launcher& L, const Dims& d, const ViewPtrs& left, const ViewPtrs& right, const ScanParams& sp,
                         int32_t* wta0, int32_t* wta1)
 {
+    const unsigned warp_bytes = ((unsigned)(SC_NST * sp.stage_bytes + SC_NST * 8) + 127u) & ~127u;
+    const size_t smem = (size_t)SCAN_WARPS * warp_bytes;
+    static size_t smem_set[2] = {0, 0};
+    if (smem > smem_set[0]) {
+        cudaFuncSetAttribute(k_scanline<K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        smem_set[0] = smem;
+    }
+    if (smem > smem_set[1]) {
+        cudaFuncSetAttribute(k_scanline<K, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        smem_set[1] = smem;
+    }
     dim3 gv((d.W + SCAN_WARPS - 1) / SCAN_WARPS, 2), gh((d.H + SCAN_WARPS - 1) / SCAN_WARPS, 2);
-    k_scanline<K, true><<<gv, SCAN_WARPS * 32, 0, L.stream>>>(d, left, right, sp, wta0, wta1);
-    k_scanline<K, false><<<gh, SCAN_WARPS * 32, 0, L.stream>>>(d, left, right, sp, wta0, wta1);
+    k_scanline<K, true><<<gv, SCAN_WARPS * 32, smem, L.stream>>>(d, left, right, sp, wta0, wta1);
+    k_scanline<K, false><<<gh, SCAN_WARPS * 32, smem, L.stream>>>(d, left, right, sp, wta0, wta1);
     L.count(2);
 }
 
@@ -256,6 +337,8 @@ void scanline(const Launcher& L, const Dims& d, const ViewPtrs& left, const View
     sp.p1[0] = p1_lo; sp.p1[1] = 0.25f; sp.p1[2] = 1.f;
     sp.p2[0] = p2_lo; sp.p2[1] = 0.75f; sp.p2[2] = 3.f;
     sp.store_right_final = store_right_final ? 1 : 0;
+    sp.tail_bytes = d.Rp == 0 ? 0 : (d.Rp >= 4 ? d.Rp * 4 : 16);
+    sp.stage_bytes = d.Dm * 4 + sp.tail_bytes + SC_WIN * 4;
     const int K = (d.Dn + 31) / 32;
 #define TSM_SCAN_CASE(k) case k: launch_scan<k>(L, d, left, right, sp, wta_left, wta_right); break;
     switch (K) {

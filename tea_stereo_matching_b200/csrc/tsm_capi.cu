@@ -191,7 +191,7 @@ int ensure_arena(tsm_ctx* c, const tsm_adcensus_config* cfg, int H, int W)
         if ((rc = ensure(c, c->desc_h[k], ((size_t)H * d.Wd() + 256) * 4, true))) return rc;
         if ((rc = ensure(c, c->desc_v[k], ((size_t)W * d.Hd() + 256) * 4, true))) return rc;
         if ((rc = ensure(c, c->flags[k], npx))) return rc;
-        if ((rc = ensure(c, c->tflags[k], (size_t)2 * H * (W + 2 * kTfPad) * 2))) return rc;
+        if ((rc = ensure(c, c->tflags[k], ((size_t)2 * H * d.stab_pitch() + 64) * 4, true))) return rc;
         if ((rc = ensure(c, c->vol[k], (npx * d.Dm + aggregate_overread_floats(d)) * 4 + 256, true))) return rc;
         if ((rc = ensure(c, c->vtail[k], (npx * d.Rp + aggregate_overread_floats(d)) * 4 + 256, true))) return rc;
         if ((rc = ensure(c, c->wta_[k], npx * 4))) return rc;
@@ -229,7 +229,7 @@ ViewPtrs view_ptrs(tsm_ctx* c, int k)
     v.desc_h = (const uint32_t*)c->desc_h[k].p;
     v.desc_v = (const uint32_t*)c->desc_v[k].p;
     v.flags = (const uint8_t*)c->flags[k].p;
-    v.tflags = (const uint16_t*)c->tflags[k].p;
+    v.stab = (const uint32_t*)c->tflags[k].p;
     v.vol.main = (float*)c->vol[k].p;
     v.vol.tail = (float*)c->vtail[k].p;
     return v;
@@ -269,8 +269,9 @@ int run_stages(tsm_ctx* c, int mask, int arg)
         ScopedStage s(c, "prep");
         for (int k = 0; k < 2; ++k)
             prep_view(L, d, k, (const uint8_t*)c->img[k].p, (uint32_t*)c->img4[k].p, (uint64_t*)c->census[k].p,
-                      (uchar4*)c->arms[k].p, (uint32_t*)c->desc_h[k].p, (uint32_t*)c->desc_v[k].p, (uint8_t*)c->flags[k].p,
-                      (uint16_t*)c->tflags[k].p);
+                      (uchar4*)c->arms[k].p, (uint32_t*)c->desc_h[k].p, (uint32_t*)c->desc_v[k].p, (uint8_t*)c->flags[k].p);
+        prep_scan_tables(L, d, (const uint8_t*)c->flags[0].p, (const uint8_t*)c->flags[1].p, (uint32_t*)c->tflags[0].p,
+                         (uint32_t*)c->tflags[1].p);
     }
     if (mask & TSM_STAGE_INIT) {
         ScopedStage s(c, "cost_init");
