@@ -149,23 +149,45 @@ __device__ __forceinline__ void for_each_region(const int32_t* __restrict__ disp
     }
 }
 
+// A CTA owns a tile of 256 consecutive pixels: every thread classifies its own pixel, the
+// pixels that need region work are compacted into a shared list and the 8 warps then take
+// them one at a time (most pixels need none, so a warp per pixel would mostly launch to exit).
+constexpr int VOTE_TILE = 256, VOTE_WARPS = 8;
+__device__ __forceinline__ int tile_compact(bool want, int local, int* list, int* count)
+{
+    // order inside the list is irrelevant; returns the number of entries after the barrier
+    const unsigned b = __ballot_sync(0xffffffffu, want);
+    const int lane = threadIdx.x & 31;
+    int base = 0;
+    if (lane == 0 && b) base = atomicAdd(count, __popc(b));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (want) list[base + __popc(b & ((1u << lane) - 1u))] = local;
+    __syncthreads();
+    return *count;
+}
+
 template <bool HF>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(VOTE_TILE)
 k_vote_count(const int32_t* __restrict__ disp, const uchar4* __restrict__ arms, int32_t* __restrict__ vote,
              int32_t* __restrict__ lowcnt, size_t npx, int W)
 {
-    const size_t p = (size_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    __shared__ int list[VOTE_TILE];
+    __shared__ int count;
+    if (threadIdx.x == 0) count = 0;
+    __syncthreads();
+    const size_t p0 = (size_t)blockIdx.x * VOTE_TILE, pt = p0 + threadIdx.x;
+    const bool outlier = pt < npx && disp[pt] < 0;
+    if (pt < npx && !outlier) { vote[pt] = 0; lowcnt[pt] = 0; }
+    const int n = tile_compact(outlier, threadIdx.x, list, &count);
     const int lane = threadIdx.x & 31;
-    if (p >= npx) return;
-    if (disp[p] >= 0) {
-        if (lane == 0) { vote[p] = 0; lowcnt[p] = 0; }
-        return;
-    }
-    int cnt = 0;
-    for_each_region<HF>(disp, arms, W, p, lane, [&](bool valid, int) { cnt += __popc(__ballot_sync(0xffffffffu, valid)); });
-    if (lane == 0) {
-        vote[p] = cnt;
-        lowcnt[p] = cnt <= kVotingThresh ? cnt : 0;
+    for (int i = threadIdx.x >> 5; i < n; i += VOTE_WARPS) {
+        const size_t p = p0 + list[i];
+        int cnt = 0;
+        for_each_region<HF>(disp, arms, W, p, lane, [&](bool valid, int) { cnt += __popc(__ballot_sync(0xffffffffu, valid)); });
+        if (lane == 0) {
+            vote[p] = cnt;
+            lowcnt[p] = cnt <= kVotingThresh ? cnt : 0;
+        }
     }
 }
 
@@ -178,64 +200,81 @@ __global__ void k_vote_mark(const int32_t* __restrict__ disp, const int32_t* __r
 }
 
 template <bool HF>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(VOTE_TILE)
 k_vote_fill(const int32_t* __restrict__ disp, const uchar4* __restrict__ arms, const int32_t* __restrict__ vote,
             const int32_t* __restrict__ off, uint16_t* __restrict__ flat, size_t npx, int W)
 {
-    const size_t p = (size_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    __shared__ int list[VOTE_TILE];
+    __shared__ int count;
+    if (threadIdx.x == 0) count = 0;
+    __syncthreads();
+    const size_t p0 = (size_t)blockIdx.x * VOTE_TILE, pt = p0 + threadIdx.x;
+    bool low = false;
+    if (pt < npx && disp[pt] < 0) {
+        const int nv = vote[pt];
+        low = nv > 0 && nv <= kVotingThresh;
+    }
+    const int n = tile_compact(low, threadIdx.x, list, &count);
     const int lane = threadIdx.x & 31;
-    if (p >= npx) return;
-    if (disp[p] >= 0) return;
-    const int n = vote[p];
-    if (n == 0 || n > kVotingThresh) return;
-    uint16_t* dst = flat + off[p];
-    int base = 0;
-    for_each_region<HF>(disp, arms, W, p, lane, [&](bool valid, int v) {
-        const unsigned b = __ballot_sync(0xffffffffu, valid);
-        if (valid) dst[base + __popc(b & ((1u << lane) - 1u))] = (uint16_t)v;
-        base += __popc(b);
-    });
+    for (int i = threadIdx.x >> 5; i < n; i += VOTE_WARPS) {
+        const size_t p = p0 + list[i];
+        uint16_t* dst = flat + off[p];
+        int base = 0;
+        for_each_region<HF>(disp, arms, W, p, lane, [&](bool valid, int v) {
+            const unsigned b = __ballot_sync(0xffffffffu, valid);
+            if (valid) dst[base + __popc(b & ((1u << lane) - 1u))] = (uint16_t)v;
+            base += __popc(b);
+        });
+    }
 }
 
-constexpr int VOTE_WARPS = 8;
 template <bool HF>
-__global__ void __launch_bounds__(VOTE_WARPS * 32)
+__global__ void __launch_bounds__(VOTE_TILE)
 k_vote_high(const int32_t* __restrict__ disp, const uchar4* __restrict__ arms, const int32_t* __restrict__ vote,
             const int32_t* __restrict__ off, const int32_t* __restrict__ start, const uint16_t* __restrict__ flat,
             int32_t* __restrict__ out, size_t npx, int W, int Dn)
 {
     extern __shared__ int hist_all[];  // [VOTE_WARPS][Dn]
+    __shared__ int list[VOTE_TILE];
+    __shared__ int count;
+    if (threadIdx.x == 0) count = 0;
+    __syncthreads();
+    const size_t p0 = (size_t)blockIdx.x * VOTE_TILE, pt = p0 + threadIdx.x;
+    bool high = false;
+    if (pt < npx) {
+        const int dp = disp[pt];
+        high = dp < 0 && vote[pt] > kVotingThresh;
+        if (!high) out[pt] = dp;  // valid pixel or low-vote outlier: unchanged (:1077-1080, :1132-1135)
+    }
+    const int n = tile_compact(high, threadIdx.x, list, &count);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const size_t p = (size_t)blockIdx.x * VOTE_WARPS + warp;
-    if (p >= npx) return;
-    const int dp = disp[p];
-    const int n = vote[p];
-    if (dp >= 0 || n <= kVotingThresh) {  // valid pixel or low-vote outlier: unchanged (:1077-1080, :1132-1135)
-        if (lane == 0) out[p] = dp;
-        return;
-    }
     int* hist = hist_all + warp * Dn;
-    for (int d = lane; d < Dn; d += 32) hist[d] = 0;
-    __syncwarp();
-    for_each_region<HF>(disp, arms, W, p, lane, [&](bool valid, int v) {
-        if (valid) atomicAdd(&hist[v], 1);
-    });
-    for (int i = start[p] + lane; i < off[p]; i += 32) atomicAdd(&hist[flat[i]], 1);  // the leak
-    __syncwarp();
-    int best = 0, bd = INT_MAX;
-    for (int d = lane; d < Dn; d += 32) {
-        const int h = hist[d];
-        if (h > best) { best = h; bd = d; }
-    }
+    for (int i = warp; i < n; i += VOTE_WARPS) {
+        const size_t p = p0 + list[i];
+        const int dp = disp[p], nv = vote[p];
+        for (int d = lane; d < Dn; d += 32) hist[d] = 0;
+        __syncwarp();
+        for_each_region<HF>(disp, arms, W, p, lane, [&](bool valid, int v) {
+            if (valid) atomicAdd(&hist[v], 1);
+        });
+        for (int j = start[p] + lane; j < off[p]; j += 32) atomicAdd(&hist[flat[j]], 1);  // the leak
+        __syncwarp();
+        int best = 0, bd = INT_MAX;
+        for (int d = lane; d < Dn; d += 32) {
+            const int h = hist[d];
+            if (h > best) { best = h; bd = d; }
+        }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const int oh = __shfl_xor_sync(0xffffffffu, best, o);
-        const int od = __shfl_xor_sync(0xffffffffu, bd, o);
-        if (oh > best || (oh == best && od < bd)) { best = oh; bd = od; }
-    }
-    if (lane == 0) {
-        const float ratio = __fdiv_rn((float)best, (float)n);  // hist[d] / (float)vote, :1144
-        out[p] = (best > 0 && ratio > kVotingRatio) ? bd : dp;
+        for (int o = 16; o > 0; o >>= 1) {
+            const int oh = __shfl_xor_sync(0xffffffffu, best, o);
+            const int od = __shfl_xor_sync(0xffffffffu, bd, o);
+            if (oh > best || (oh == best && od < bd)) { best = oh; bd = od; }
+        }
+        if (lane == 0) {
+            const float ratio = __fdiv_rn((float)best, (float)nv);  // hist[d] / (float)vote, :1144
+            out[p] = (best > 0 && ratio > kVotingRatio) ? bd : dp;
+        }
+        __syncwarp();
     }
 }
 
@@ -344,16 +383,16 @@ static void region_voting_t(const Launcher& L, const Dims& d, const int32_t* dis
                             const VoteScratch& s)
 {
     const size_t npx = d.npx();
-    const unsigned wblocks = (unsigned)((npx + 7) / 8);
-    k_vote_count<HF><<<wblocks, 256, 0, L.stream>>>(disp_in, arms, s.vote, s.lowcnt, npx, d.W);
+    const unsigned wblocks = (unsigned)((npx + VOTE_TILE - 1) / VOTE_TILE);
+    k_vote_count<HF><<<wblocks, VOTE_TILE, 0, L.stream>>>(disp_in, arms, s.vote, s.lowcnt, npx, d.W);
     L.count(1);
     exclusive_scan<OpSum>(L, s.lowcnt, s.off, s.blocksums, npx);
     k_vote_mark<<<(unsigned)((npx + 255) / 256), 256, 0, L.stream>>>(disp_in, s.vote, s.off, s.mark, npx);
     L.count(1);
     exclusive_scan<OpMax>(L, s.mark, s.start, s.blocksums, npx);
-    k_vote_fill<HF><<<wblocks, 256, 0, L.stream>>>(disp_in, arms, s.vote, s.off, s.flat, npx, d.W);
+    k_vote_fill<HF><<<wblocks, VOTE_TILE, 0, L.stream>>>(disp_in, arms, s.vote, s.off, s.flat, npx, d.W);
     const size_t smem = (size_t)VOTE_WARPS * d.Dn * sizeof(int);
-    k_vote_high<HF><<<(unsigned)((npx + VOTE_WARPS - 1) / VOTE_WARPS), VOTE_WARPS * 32, smem, L.stream>>>(
+    k_vote_high<HF><<<wblocks, VOTE_TILE, smem, L.stream>>>(
         disp_in, arms, s.vote, s.off, s.start, s.flat, disp_out, npx, d.W, d.Dn);
     L.count(2);
 }

@@ -37,8 +37,14 @@
 
 namespace tsm {
 
-constexpr int SCAN_WARPS = 4;
-constexpr int SC_NST = 8;    // TMA stages (steps in flight) per warp
+#ifndef TSM_SCAN_WARPS
+#define TSM_SCAN_WARPS 4
+#endif
+#ifndef TSM_SC_NST
+#define TSM_SC_NST 8
+#endif
+constexpr int SCAN_WARPS = TSM_SCAN_WARPS;
+constexpr int SC_NST = TSM_SC_NST;    // TMA stages (steps in flight) per warp
 constexpr int SC_WIN = 36;   // scan-table words fetched per step (32 lanes + 16-byte alignment slack)
 
 struct ScanParams {
