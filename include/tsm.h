@@ -165,6 +165,12 @@ size_t tsm_buffer_bytes(const tsm_ctx* ctx, int buffer);
 int tsm_tap(tsm_ctx* ctx, int buffer, void* dst, size_t bytes);
 int tsm_poke(tsm_ctx* ctx, int buffer, const void* src, size_t bytes);
 
+/* Device self-tests of arithmetic shortcuts the kernels rely on.  *mismatches receives the number of
+ * failing cases (0 = pass).  TSM_SELFTEST_DIV: the branch-free fp32 divide used by the aggregation
+ * normalisation equals the IEEE divide (source/ADCensus.cpp:747) for every divisor 1..4489. */
+enum tsm_selftest_id { TSM_SELFTEST_DIV = 0 };
+int tsm_selftest(tsm_ctx* ctx, int which, unsigned long long* mismatches);
+
 /* Per-stage device time of the last compute on this ctx, in milliseconds, measured
  * with CUDA events on the ctx stream when profiling was enabled.  names/ms arrays of
  * length *n; returns the number of stages actually filled in *n. */

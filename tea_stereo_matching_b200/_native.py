@@ -32,7 +32,7 @@ EXPORTS = [
     "tsm_device_count", "tsm_synchronize", "tsm_adcensus_compute", "tsm_adcensus_compute_device",
     "tsm_adcensus_enqueue", "tsm_adcensus_wait", "tsm_remap", "tsm_rectify_stereo", "tsm_rectify_adcensus",
     "tsm_invalidate_maps", "tsm_stage_begin", "tsm_stage_run", "tsm_volume_pitch", "tsm_buffer_bytes", "tsm_tap",
-    "tsm_poke", "tsm_set_profiling", "tsm_get_stage_times", "tsm_launch_count",
+    "tsm_poke", "tsm_set_profiling", "tsm_get_stage_times", "tsm_launch_count", "tsm_selftest",
 ]
 
 
@@ -110,5 +110,6 @@ def lib() -> C.CDLL:
     L.tsm_get_stage_times.argtypes = [vp, C.POINTER(i32), C.POINTER(C.c_char_p), C.POINTER(C.c_float)]
     L.tsm_launch_count.argtypes = [vp]
     L.tsm_launch_count.restype = C.c_longlong
+    L.tsm_selftest.argtypes = [vp, i32, C.POINTER(C.c_ulonglong)]
     _lib = L
     return L

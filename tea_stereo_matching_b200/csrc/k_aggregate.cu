@@ -21,7 +21,8 @@
 // AGG_PF steps.
 //
 // Division: the reference divides the fp32 sum by (float)N with an IEEE fp32 divide
-// (ADCensus.cpp:747); so does __fdiv_rn(fl32(sum), (float)N) here.
+// (ADCensus.cpp:747); div_exact(fl32(sum), N) (tsm_common.cuh) is that divide, correctly rounded,
+// without the slow-path branch of __fdiv_rn.
 //
 // Per-position side data (the two arm lengths of the pass and N) come as ONE 32-bit step
 // descriptor (k_prep.cu), four consecutive positions per 16-byte load: small broadcast loads
@@ -129,9 +130,9 @@ k_agg_walk(Dims dm, ViewPtrs v0, ViewPtrs v1, int wsel, int nb_main)
         ld_ring(ring0 + s0, l0, l1);
         float r0 = __double2float_rn(h0 - l0), r1 = __double2float_rn(h1 - l1);
         if (NORM) {
-            const float n = (float)(desc >> 16);
-            r0 = __fdiv_rn(r0, n);
-            r1 = __fdiv_rn(r1, n);
+            const RcpN rn = rcp_prepare((float)(desc >> 16));
+            r0 = div_exact(r0, rn);
+            r1 = div_exact(r1, rn);
         }
         st_stream(out_ptr, r0, r1);
         out_ptr += cstride;
@@ -186,9 +187,11 @@ k_agg_walk(Dims dm, ViewPtrs v0, ViewPtrs v1, int wsel, int nb_main)
 #pragma unroll
         for (int u0 = 0; u0 < AGG_PF; u0 += 4) {
             double h0[4], h1[4], l0[4], l1[4];
+            RcpN rn[4];
 #pragma unroll
             for (int w = 0; w < 4; ++w) {
                 const int u = u0 + w;
+                if (NORM && u < nsteps) rn[w] = rcp_prepare((float)(av[buf][u] >> 16));  // off the critical path
                 if (u < nsteps) {
                     P0 += (double)vin[buf][u].x;
                     P1 += (double)vin[buf][u].y;
@@ -216,9 +219,8 @@ k_agg_walk(Dims dm, ViewPtrs v0, ViewPtrs v1, int wsel, int nb_main)
                 if (u < nsteps) {
                     float r0 = __double2float_rn(h0[w] - l0[w]), r1 = __double2float_rn(h1[w] - l1[w]);
                     if (NORM) {
-                        const float n = (float)(av[buf][u] >> 16);
-                        r0 = __fdiv_rn(r0, n);
-                        r1 = __fdiv_rn(r1, n);
+                        r0 = div_exact(r0, rn[w]);
+                        r1 = div_exact(r1, rn[w]);
                     }
                     st_stream(out_ptr, r0, r1);
                     out_ptr += cstride;
@@ -314,7 +316,7 @@ k_agg_small(Dims dm, ViewPtrs v0, ViewPtrs v1, int wsel, int nb_main)
             s1 += (s1 < 0) ? AGS_RING : 0;
             s0 += (s0 < 0) ? AGS_RING : 0;
             float r = __double2float_rn(my[s1 * AGS_BLOCK] - my[s0 * AGS_BLOCK]);
-            if (NORM) r = __fdiv_rn(r, (float)(w >> 16));
+            if (NORM) r = div_exact(r, rcp_prepare((float)(w >> 16)));
             cell[(size_t)o * cstride] = r;
         }
     }
@@ -371,6 +373,30 @@ void aggregate(const Launcher& L, const Dims& d, const ViewPtrs& left, const Vie
         }
         hf = !hf;
     }
+}
+
+// ---- self-test: div_exact == __fdiv_rn for every divisor the aggregation can see ----
+__global__ void k_selftest_div(unsigned long long* mismatches)
+{
+    // blockIdx.x + 1 = divisor b in [1, 4489]; 2^21 dividends per divisor: a dense sweep of mantissas at the
+    // magnitudes aggregation produces (sums in [0, 8978]) plus exact multiples of b
+    const float b = (float)(blockIdx.x + 1);
+    const RcpN rn = rcp_prepare(b);
+    unsigned long long bad = 0;
+    for (unsigned i = threadIdx.x; i < (1u << 21); i += blockDim.x) {
+        float a;
+        if (i & 1) a = __uint_as_float(0x3a000000u + i * 1021u);  // ~[4.9e-4, 1.3e4], stride-1021 mantissa walk
+        else a = b * (float)(i >> 1) * 0.001953125f;                // multiples of b / 512
+        if (!(a >= 0.f && a < 16384.f)) continue;
+        if (__float_as_uint(div_exact(a, rn)) != __float_as_uint(__fdiv_rn(a, b))) ++bad;
+    }
+    if (bad) atomicAdd(mismatches, bad);
+}
+
+void selftest_div(const Launcher& L, unsigned long long* d_mismatches)
+{
+    k_selftest_div<<<4489, 256, 0, L.stream>>>(d_mismatches);
+    L.count(1);
 }
 
 }  // namespace tsm

@@ -777,4 +777,21 @@ int tsm_get_stage_times(tsm_ctx* c, int* n, const char** names, float* ms)
 
 long long tsm_launch_count(const tsm_ctx* c) { return c ? c->launches : 0; }
 
+int tsm_selftest(tsm_ctx* c, int which, unsigned long long* mismatches)
+{
+    if (!c || !mismatches) return TSM_E_ARG;
+    if (which != TSM_SELFTEST_DIV) return fail(c, TSM_E_ARG, "tsm_selftest: unknown test %d", which);
+    CK(c, cudaSetDevice(c->device));
+    unsigned long long* d = nullptr;
+    CK(c, cudaMalloc(&d, sizeof *d));
+    cudaMemsetAsync(d, 0, sizeof *d, c->stream);
+    Launcher L{c->stream, &c->launches};
+    selftest_div(L, d);
+    cudaError_t e = cudaMemcpyAsync(mismatches, d, sizeof *d, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail(c, TSM_E_CUDA, "tsm_selftest: %s", cudaGetErrorString(e));
+    return TSM_OK;
+}
+
 }  // extern "C"

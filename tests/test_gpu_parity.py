@@ -256,3 +256,16 @@ def test_rectify_matches_cv_restatement(port, native_lib):
     m.setMinMaxDisparity(0, 24)
     fused = rect.rectify_adcensus(stereo, m)
     assert np.array_equal(fused, m.compute(want[0], want[1]))
+
+
+def test_division_shortcut_is_ieee_exact(native_lib):
+    """div_exact (branch-free fast path) == __fdiv_rn for every divisor the normalisation can see."""
+    import ctypes as C
+
+    import tea_stereo_matching_b200 as t
+
+    ctx = t.Context(0)
+    bad = C.c_ulonglong(123)
+    ctx.check(native_lib.tsm_selftest(ctx.handle, 0, C.byref(bad)))
+    assert bad.value == 0
+    ctx.close()
