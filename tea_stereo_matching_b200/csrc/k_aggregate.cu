@@ -38,14 +38,19 @@ constexpr int AGG_NC = TSM_AGG_NC;        // adjacent disparities (chains) per t
 constexpr int AGG_BLOCK = 128 / AGG_NC;   // threads per CTA
 constexpr int AGG_LAG = kMaxArm;          // 33
 #ifndef TSM_AGG_PF
-#define TSM_AGG_PF 8
+#define TSM_AGG_PF 4
 #endif
 constexpr int AGG_PF = TSM_AGG_PF;        // prefetch distance
 #ifndef TSM_AGG_NBUF
-#define TSM_AGG_NBUF 4
+#define TSM_AGG_NBUF 8
 #endif
 constexpr int AGG_NBUF = TSM_AGG_NBUF;    // register buffers: NBUF-1 batches in flight
 constexpr int AGG_U = AGG_NBUF * AGG_PF;  // steps per main-loop iteration
+#ifndef TSM_AGG_SUB
+#define TSM_AGG_SUB 4
+#endif
+constexpr int AGG_SUB = TSM_AGG_SUB;      // steps per software-pipelined sub-block of a batch
+static_assert(AGG_PF % AGG_SUB == 0, "sub-blocks tile a batch");
 constexpr int AGG_RING = 72;              // >= 68 prefixes, multiple of AGG_PF
 constexpr int AGG_SLOT = AGG_BLOCK * 8 * AGG_NC;  // bytes between consecutive ring slots
 constexpr int AGG_RING_BYTES = AGG_RING * AGG_SLOT;
@@ -185,11 +190,11 @@ k_agg_walk(Dims dm, ViewPtrs v0, ViewPtrs v1, int wsel, int nb_main)
     // step; grouped like this it is paid once per four steps.
     auto run_batch = [&](int buf, int nsteps) {  // nsteps == AGG_PF in the steady state
 #pragma unroll
-        for (int u0 = 0; u0 < AGG_PF; u0 += 4) {
-            double h0[4], h1[4], l0[4], l1[4];
-            RcpN rn[4];
+        for (int u0 = 0; u0 < AGG_PF; u0 += AGG_SUB) {
+            double h0[AGG_SUB], h1[AGG_SUB], l0[AGG_SUB], l1[AGG_SUB];
+            RcpN rn[AGG_SUB];
 #pragma unroll
-            for (int w = 0; w < 4; ++w) {
+            for (int w = 0; w < AGG_SUB; ++w) {
                 const int u = u0 + w;
                 if (NORM && u < nsteps) rn[w] = rcp_prepare((float)(av[buf][u] >> 16));  // off the critical path
                 if (u < nsteps) {
@@ -199,7 +204,7 @@ k_agg_walk(Dims dm, ViewPtrs v0, ViewPtrs v1, int wsel, int nb_main)
                 }
             }
 #pragma unroll
-            for (int w = 0; w < 4; ++w) {
+            for (int w = 0; w < AGG_SUB; ++w) {
                 const int u = u0 + w;
                 if (u < nsteps) {
                     const uint32_t desc = av[buf][u];
@@ -214,7 +219,7 @@ k_agg_walk(Dims dm, ViewPtrs v0, ViewPtrs v1, int wsel, int nb_main)
                 }
             }
 #pragma unroll
-            for (int w = 0; w < 4; ++w) {
+            for (int w = 0; w < AGG_SUB; ++w) {
                 const int u = u0 + w;
                 if (u < nsteps) {
                     float r0 = __double2float_rn(h0[w] - l0[w]), r1 = __double2float_rn(h1[w] - l1[w]);
