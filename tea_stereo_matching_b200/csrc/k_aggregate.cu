@@ -28,6 +28,8 @@
 // descriptor (k_prep.cu), four consecutive positions per 16-byte load: small broadcast loads
 // cost real bandwidth on this access pattern (measured: -15 % with two scalar loads per step).
 #include "tsm_common.cuh"
+#include <cstdio>
+#include <cstdlib>
 
 namespace tsm {
 
@@ -52,35 +54,86 @@ constexpr int AGG_U = AGG_NBUF * AGG_PF;  // steps per main-loop iteration
 constexpr int AGG_SUB = TSM_AGG_SUB;      // steps per software-pipelined sub-block of a batch
 static_assert(AGG_PF % AGG_SUB == 0, "sub-blocks tile a batch");
 constexpr int AGG_RING = 72;              // >= 68 prefixes, multiple of AGG_PF
-constexpr int AGG_SLOT = AGG_BLOCK * 8 * AGG_NC;  // bytes between consecutive ring slots
-constexpr int AGG_RING_BYTES = AGG_RING * AGG_SLOT;
 // P[i] lives in slot (i + AGG_P0) mod AGG_RING, chosen so that P[AGG_LAG + 1] (the first
 // prefix written in the main loop) sits on a multiple of AGG_PF.
 constexpr int AGG_P0 = (AGG_PF - (AGG_LAG + 1) % AGG_PF) % AGG_PF;
 static_assert(AGG_RING % AGG_PF == 0 && AGG_RING >= 2 * kMaxArm + 2, "ring geometry");
 static_assert(AGG_PF <= AGG_LAG, "arm prefetch must stay inside the line");
 
-__device__ __forceinline__ void st_ring(uint32_t addr, double a, double b)
-{
-    if (AGG_NC == 2) asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(addr), "d"(a), "d"(b) : "memory");
-    else asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(a) : "memory");
-}
-__device__ __forceinline__ void ld_ring(uint32_t addr, double& a, double& b)
-{
-    if (AGG_NC == 2) asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(a), "=d"(b) : "r"(addr) : "memory");
-    else { asm volatile("ld.shared.f64 %0, [%1];" : "=d"(a) : "r"(addr) : "memory"); b = 0.0; }
-}
+// ---- prefix rings ----------------------------------------------------------------------------
+// A ring holds the last AGG_RING prefixes of the thread's AGG_NC chains.  Two homes:
+//   SmemRing<T>: shared memory, [AGG_RING][T threads] x 16 bytes (slot stride T*16 bytes);
+//   TmemRing   : tensor memory.  A warp with warp%4 == q owns TMEM lanes 32q..32q+31, thread = lane,
+//                slot s = 4 consecutive 32-bit columns 4s..4s+3 of that lane (tcgen05.st/ld 32x32b.x4).
+//                Slot offsets must be warp-uniform there: every lane of the warp walks the SAME line.
+// Offsets handed to st/ld are in ring units (SLOT per slot, SPAN per ring).
+template <int THREADS>
+struct SmemRing {
+    static constexpr int SLOT = THREADS * 8 * AGG_NC;
+    static constexpr int SPAN = AGG_RING * SLOT;
+    struct Raw { double a, b; };
+    uint32_t base;
+    __device__ __forceinline__ void st(uint32_t off, double a, double b) const
+    {
+        if (AGG_NC == 2) asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(base + off), "d"(a), "d"(b) : "memory");
+        else asm volatile("st.shared.f64 [%0], %1;" ::"r"(base + off), "d"(a) : "memory");
+    }
+    __device__ __forceinline__ void ld(uint32_t off, Raw& r) const
+    {
+        if (AGG_NC == 2) asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(r.a), "=d"(r.b) : "r"(base + off) : "memory");
+        else { asm volatile("ld.shared.f64 %0, [%1];" : "=d"(r.a) : "r"(base + off) : "memory"); r.b = 0.0; }
+    }
+    __device__ __forceinline__ void st_fence() const {}
+    __device__ __forceinline__ void ld_fence() const {}
+    __device__ __forceinline__ void unpack(Raw& r, double& a, double& b) const { a = r.a; b = r.b; }
+};
+
+struct TmemRing {
+    static_assert(AGG_NC == 2, "a TMEM slot is one fp64 pair");
+    static constexpr int SLOT = 4;  // columns
+    static constexpr int SPAN = AGG_RING * SLOT;
+    struct Raw { uint32_t w[4]; };
+    uint32_t base;  // (lane quarter << 16) | first column
+    __device__ __forceinline__ void st(uint32_t off, double a, double b) const
+    {
+        uint32_t a0, a1, b0, b1;
+        asm("mov.b64 {%0, %1}, %2;" : "=r"(a0), "=r"(a1) : "d"(a));
+        asm("mov.b64 {%0, %1}, %2;" : "=r"(b0), "=r"(b1) : "d"(b));
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(base + off), "r"(a0), "r"(a1),
+                     "r"(b0), "r"(b1)
+                     : "memory");
+    }
+    __device__ __forceinline__ void ld(uint32_t off, Raw& r) const
+    {
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(r.w[0]), "=r"(r.w[1]), "=r"(r.w[2]), "=r"(r.w[3])
+                     : "r"(base + off)
+                     : "memory");
+    }
+    // tcgen05.st / .ld are asynchronous: a store must be waited for before the slot is read back, and
+    // the destination registers of a load must not be touched before wait::ld.
+    __device__ __forceinline__ void st_fence() const { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+    __device__ __forceinline__ void ld_fence() const { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+    __device__ __forceinline__ void unpack(Raw& r, double& a, double& b) const
+    {
+        // volatile pins keep every use of the loaded words behind the (volatile) wait::ld
+#pragma unroll
+        for (int i = 0; i < 4; ++i) asm volatile("" : "+r"(r.w[i]));
+        asm("mov.b64 %0, {%1, %2};" : "=d"(a) : "r"(r.w[0]), "r"(r.w[1]));
+        asm("mov.b64 %0, {%1, %2};" : "=d"(b) : "r"(r.w[2]), "r"(r.w[3]));
+    }
+};
 
 // Streaming accesses of the cost volume: every cell is touched exactly once per pass, so the
 // lines must not occupy the (small, shared-memory-carved) L1.
-__device__ __forceinline__ float2 ld_stream(const float* p)
+__device__ __forceinline__ float2 ld_stream(const char* p)
 {
     float2 v;
     if (AGG_NC == 2) asm volatile("ld.global.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
     else { asm volatile("ld.global.L1::no_allocate.f32 %0, [%1];" : "=f"(v.x) : "l"(p)); v.y = 0.f; }
     return v;
 }
-__device__ __forceinline__ void st_stream(float* p, float a, float b)
+__device__ __forceinline__ void st_stream(char* p, float a, float b)
 {
     if (AGG_NC == 2) asm volatile("st.global.L1::no_allocate.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(a), "f"(b) : "memory");
     else asm volatile("st.global.L1::no_allocate.f32 [%0], %1;" ::"l"(p), "f"(a) : "memory");
@@ -88,110 +141,78 @@ __device__ __forceinline__ void st_stream(float* p, float a, float b)
 
 static_assert(AGG_PF % 4 == 0, "descriptors are fetched four at a time; batches run in sub-blocks of 4");
 
-// Requires len >= AGG_LAG + 1 (host-checked) and AGG_PF positions of over-read slack
+// One thread walks its AGG_NC chains along one line.  `cell` = first cell of the chains, `cstride` =
+// BYTES between consecutive positions (32-bit: keeps the pointer stepping to one add-with-carry), `desc_line` = the line's step descriptors.
+// Requires len >= AGG_LAG + 1 + AGG_U (host-checked) and AGG_U positions of over-read slack
 // behind every line end (the volumes are allocated with it).
-template <bool VERT, bool NORM>
-__global__ void __launch_bounds__(AGG_BLOCK)
-k_agg_walk(Dims dm, ViewPtrs v0, ViewPtrs v1, int wsel, int nb_main)
+template <bool NORM, class Ring>
+__device__ __forceinline__ void walk_line(const Ring ring, float* cell, const uint32_t cstride, const uint32_t* desc_line,
+                                          const int len)
 {
-    extern __shared__ __align__(16) unsigned char ring_raw[];  // [AGG_RING][AGG_BLOCK] x double2
-    const ViewPtrs& v = blockIdx.y ? v1 : v0;
-    const int H = dm.H, W = dm.W;
-    const int nlines = VERT ? W : H, len = VERT ? H : W;
-    // chains of the 128-byte aligned main part first, then (blocks >= nb_main) those of the tail part
-    float* part;
-    int pitch, npair;
-    long long chain;
-    if ((int)blockIdx.x < nb_main) {
-        part = v.vol.main; pitch = dm.Dm; npair = dm.Dm / AGG_NC;
-        chain = (long long)blockIdx.x * AGG_BLOCK + threadIdx.x;
-    } else {
-        part = v.vol.tail; pitch = dm.Rp; npair = (dm.tail() + AGG_NC - 1) / AGG_NC;
-        chain = (long long)((int)blockIdx.x - nb_main) * AGG_BLOCK + threadIdx.x;
-    }
-    if (chain >= (long long)nlines * npair) return;
-    const int line = (int)(chain / npair), d = AGG_NC * (int)(chain % npair);
-
-    const size_t cstride = VERT ? (size_t)W * pitch : (size_t)pitch;  // floats between consecutive positions
-    const size_t line_px = VERT ? (size_t)line : (size_t)line * W;
-    const float* in_ptr = part + line_px * pitch + d;
-    float* out_ptr = part + line_px * pitch + d;
-    const uint32_t* desc_line = VERT ? v.desc_v + (size_t)line * dm.Hd() : v.desc_h + (size_t)line * dm.Wd();
+    constexpr int SLOT = Ring::SLOT, SPAN = Ring::SPAN;
+    typedef typename Ring::Raw Raw;
+    const char* in_ptr = reinterpret_cast<const char*>(cell);
+    char* out_ptr = reinterpret_cast<char*>(cell);
     const uint32_t* desc_ptr = desc_line;
 
-    const uint32_t ring0 = (uint32_t)__cvta_generic_to_shared(ring_raw) + threadIdx.x * (8 * AGG_NC);
     double P0 = 0.0, P1 = 0.0;
-    st_ring(ring0 + AGG_P0 * AGG_SLOT, 0.0, 0.0);  // P[0]
-
-    // output o, given the (possibly virtual) slot byte offset `top` of P[o + 34]
-    auto output = [&](uint32_t top, uint32_t desc) {
-        const int a = desc & 0xff, b = (desc >> 8) & 0xff;
-        int s1 = (int)top - (AGG_LAG - b) * AGG_SLOT;      // P[o + b + 1]
-        int s0 = (int)top - (AGG_LAG + 1 + a) * AGG_SLOT;  // P[o - a]
-        s1 += (s1 < 0) ? AGG_RING_BYTES : 0;
-        s0 += (s0 < 0) ? AGG_RING_BYTES : 0;
-        double h0, h1, l0, l1;
-        ld_ring(ring0 + s1, h0, h1);
-        ld_ring(ring0 + s0, l0, l1);
-        float r0 = __double2float_rn(h0 - l0), r1 = __double2float_rn(h1 - l1);
-        if (NORM) {
-            const RcpN rn = rcp_prepare((float)(desc >> 16));
-            r0 = div_exact(r0, rn);
-            r1 = div_exact(r1, rn);
-        }
-        st_stream(out_ptr, r0, r1);
-        out_ptr += cstride;
-    };
+    ring.st(AGG_P0 * SLOT, 0.0, 0.0);  // P[0]
 
     // ---- fill: pushes t = 0 .. AGG_LAG-1 (P[1..33] -> slots AGG_P0+1 .. AGG_P0+33, no wrap),
     // values fetched in 3 batches of 11 ----
-    uint32_t hs = AGG_P0 * AGG_SLOT;  // slot of the newest prefix
+    uint32_t hs = AGG_P0 * SLOT;  // slot of the newest prefix
     static_assert(AGG_LAG == 33, "fill batches");
 #pragma unroll 1
     for (int g = 0; g < 3; ++g) {
         float2 tmp[11];
 #pragma unroll
-        for (int u = 0; u < 11; ++u) tmp[u] = ld_stream(in_ptr + (size_t)u * cstride);
-        in_ptr += (size_t)11 * cstride;
+        for (int u = 0; u < 11; ++u) {
+            tmp[u] = ld_stream(in_ptr);
+            in_ptr += cstride;
+        }
 #pragma unroll
         for (int u = 0; u < 11; ++u) {
             P0 += (double)tmp[u].x;
             P1 += (double)tmp[u].y;
-            hs += AGG_SLOT;
-            st_ring(ring0 + hs, P0, P1);
+            hs += SLOT;
+            ring.st(hs, P0, P1);
         }
     }
     // newest = P[33] at slot AGG_P0 + 33; the next prefix P[34] goes to a multiple of AGG_PF.
-    uint32_t nx = hs + AGG_SLOT;  // slot of the next prefix to be written, multiple of AGG_PF slots
-    if (nx == AGG_RING_BYTES) nx = 0;
+    uint32_t nx = hs + SLOT;  // slot of the next prefix to be written, multiple of AGG_PF slots
+    if (nx == SPAN) nx = 0;
 
     // ---- main: steps t = AGG_LAG .. len-1: push in[t] -> P[t+1], emit o = t - AGG_LAG ----
-    // Software pipeline in BATCHES of AGG_PF steps with two register buffers: all loads of batch
-    // i+1 are issued back to back, then batch i (whose loads were issued one batch earlier) is
-    // processed.  Batching matters: a warp has only six scoreboard slots and a slot completes
-    // when ALL loads charged to it have landed, so independent loads must be grouped by the
-    // time they are needed, not interleaved one per step.
+    // Software pipeline in BATCHES of AGG_PF steps over AGG_NBUF register buffers: all loads of a
+    // batch are issued back to back, NBUF-1 batches ahead of their use.  Batching matters: a warp
+    // has only six scoreboard slots and a slot completes when ALL loads charged to it have landed,
+    // so independent loads must be grouped by the time they are needed, not interleaved one per step.
     float2 vin[AGG_NBUF][AGG_PF];
     uint32_t av[AGG_NBUF][AGG_PF];
     auto load_batch = [&](int buf) {
 #pragma unroll
-        for (int u = 0; u < AGG_PF; ++u) vin[buf][u] = ld_stream(in_ptr + (size_t)u * cstride);
+        for (int u = 0; u < AGG_PF; ++u) {
+            vin[buf][u] = ld_stream(in_ptr);
+            in_ptr += cstride;
+            // Opaque step: otherwise the unrolled loop is re-associated into base + k*cstride with all
+            // 32 multiples hoisted as loop invariants (77 extra live registers in the vertical pass).
+            asm volatile("" : "+l"(in_ptr));
+        }
 #pragma unroll
         for (int j = 0; j < AGG_PF / 4; ++j) {
             const uint4 q = *reinterpret_cast<const uint4*>(desc_ptr + 4 * j);
             av[buf][4 * j + 0] = q.x; av[buf][4 * j + 1] = q.y; av[buf][4 * j + 2] = q.z; av[buf][4 * j + 3] = q.w;
         }
-        in_ptr += (size_t)AGG_PF * cstride;
         desc_ptr += AGG_PF;
     };
-    // One batch = AGG_PF steps, processed in sub-blocks of 4: (A) the four prefix pushes and their ring
-    // stores, (B) all eight ring loads, (C) the four outputs.  A warp issues in order, so finishing
-    // step u right after its own ring loads would expose the LDS -> DADD -> F2F -> STG latency on every
-    // step; grouped like this it is paid once per four steps.
+    // One batch = AGG_PF steps, processed in sub-blocks of AGG_SUB: (A) the prefix pushes and their
+    // ring stores, (B) all ring loads, (C) the outputs.  A warp issues in order, so finishing step u
+    // right after its own ring loads would expose the ring-load -> DADD -> F2F -> STG latency on
+    // every step; grouped like this it is paid once per sub-block.
     auto run_batch = [&](int buf, int nsteps) {  // nsteps == AGG_PF in the steady state
 #pragma unroll
         for (int u0 = 0; u0 < AGG_PF; u0 += AGG_SUB) {
-            double h0[AGG_SUB], h1[AGG_SUB], l0[AGG_SUB], l1[AGG_SUB];
+            Raw hi[AGG_SUB], lo[AGG_SUB];
             RcpN rn[AGG_SUB];
 #pragma unroll
             for (int w = 0; w < AGG_SUB; ++w) {
@@ -200,35 +221,41 @@ k_agg_walk(Dims dm, ViewPtrs v0, ViewPtrs v1, int wsel, int nb_main)
                 if (u < nsteps) {
                     P0 += (double)vin[buf][u].x;
                     P1 += (double)vin[buf][u].y;
-                    st_ring(ring0 + nx + u * AGG_SLOT, P0, P1);
+                    ring.st(nx + u * SLOT, P0, P1);
                 }
             }
+            ring.st_fence();
 #pragma unroll
             for (int w = 0; w < AGG_SUB; ++w) {
                 const int u = u0 + w;
                 if (u < nsteps) {
                     const uint32_t desc = av[buf][u];
                     const int a = desc & 0xff, b = (desc >> 8) & 0xff;
-                    const uint32_t top = nx + u * AGG_SLOT;
-                    int s1 = (int)top - (AGG_LAG - b) * AGG_SLOT;      // P[o + b + 1]
-                    int s0 = (int)top - (AGG_LAG + 1 + a) * AGG_SLOT;  // P[o - a]
-                    s1 += (s1 < 0) ? AGG_RING_BYTES : 0;
-                    s0 += (s0 < 0) ? AGG_RING_BYTES : 0;
-                    ld_ring(ring0 + s1, h0[w], h1[w]);
-                    ld_ring(ring0 + s0, l0[w], l1[w]);
+                    const uint32_t top = nx + u * SLOT;
+                    int s1 = (int)top - (AGG_LAG - b) * SLOT;      // P[o + b + 1]
+                    int s0 = (int)top - (AGG_LAG + 1 + a) * SLOT;  // P[o - a]
+                    s1 += (s1 < 0) ? SPAN : 0;
+                    s0 += (s0 < 0) ? SPAN : 0;
+                    ring.ld(s1, hi[w]);
+                    ring.ld(s0, lo[w]);
                 }
             }
+            ring.ld_fence();
 #pragma unroll
             for (int w = 0; w < AGG_SUB; ++w) {
                 const int u = u0 + w;
                 if (u < nsteps) {
-                    float r0 = __double2float_rn(h0[w] - l0[w]), r1 = __double2float_rn(h1[w] - l1[w]);
+                    double h0, h1, l0, l1;
+                    ring.unpack(hi[w], h0, h1);
+                    ring.unpack(lo[w], l0, l1);
+                    float r0 = __double2float_rn(h0 - l0), r1 = __double2float_rn(h1 - l1);
                     if (NORM) {
                         r0 = div_exact(r0, rn[w]);
                         r1 = div_exact(r1, rn[w]);
                     }
                     st_stream(out_ptr, r0, r1);
                     out_ptr += cstride;
+                    asm volatile("" : "+l"(out_ptr));
                 }
             }
         }
@@ -244,34 +271,265 @@ k_agg_walk(Dims dm, ViewPtrs v0, ViewPtrs v1, int wsel, int nb_main)
         for (int b = 0; b < AGG_NBUF; ++b) {
             load_batch((b + AGG_NBUF - 1) % AGG_NBUF);
             run_batch(b, AGG_PF);
-            nx += AGG_PF * AGG_SLOT;
-            if (nx == AGG_RING_BYTES) nx = 0;
+            nx += AGG_PF * SLOT;
+            if (nx == SPAN) nx = 0;
         }
     }
     // tail: fewer than NBUF*PF steps left; buffers 0 .. NBUF-2 already hold the next batches
     {
         int rem = nB - done;
-        newest = (nx == 0 ? AGG_RING_BYTES : nx) - AGG_SLOT;
+        newest = (nx == 0 ? SPAN : nx) - SLOT;
 #pragma unroll
         for (int b = 0; b < AGG_NBUF; ++b) {
             if (rem > 0) {
                 if (b == AGG_NBUF - 1) load_batch(b);  // the one buffer that was not prefetched
                 const int n = rem < AGG_PF ? rem : AGG_PF;
                 run_batch(b, n);
-                newest = nx + (uint32_t)(n - 1) * AGG_SLOT;
-                nx += AGG_PF * AGG_SLOT;
-                if (nx == AGG_RING_BYTES) nx = 0;
+                newest = nx + (uint32_t)(n - 1) * SLOT;
+                nx += AGG_PF * SLOT;
+                if (nx == SPAN) nx = 0;
                 rem -= n;
             }
         }
     }
     // ---- drain: o = len-LAG .. len-1.  Newest prefix stays P[len]; the virtual slot of P[o+34]
     // is (j+1) slots past it.  Only real slots (<= o+b+1 <= len) are read.
+#pragma unroll 1
     for (int j = 0; j < AGG_LAG; ++j) {
         const int o = len - AGG_LAG + j;
-        uint32_t top = newest + (uint32_t)(j + 1) * AGG_SLOT;
-        top -= (top >= AGG_RING_BYTES) ? AGG_RING_BYTES : 0;
-        output(top, desc_line[o]);
+        uint32_t top = newest + (uint32_t)(j + 1) * SLOT;
+        top -= (top >= SPAN) ? SPAN : 0;
+        const uint32_t desc = desc_line[o];
+        const int a = desc & 0xff, b = (desc >> 8) & 0xff;
+        int s1 = (int)top - (AGG_LAG - b) * SLOT;      // P[o + b + 1]
+        int s0 = (int)top - (AGG_LAG + 1 + a) * SLOT;  // P[o - a]
+        s1 += (s1 < 0) ? SPAN : 0;
+        s0 += (s0 < 0) ? SPAN : 0;
+        Raw hi, lo;
+        ring.ld(s1, hi);
+        ring.ld(s0, lo);
+        ring.ld_fence();
+        double h0, h1, l0, l1;
+        ring.unpack(hi, h0, h1);
+        ring.unpack(lo, l0, l1);
+        float r0 = __double2float_rn(h0 - l0), r1 = __double2float_rn(h1 - l1);
+        if (NORM) {
+            const RcpN rn = rcp_prepare((float)(desc >> 16));
+            r0 = div_exact(r0, rn);
+            r1 = div_exact(r1, rn);
+        }
+        st_stream(out_ptr, r0, r1);
+        out_ptr += cstride;
+    }
+}
+
+// Which chains a thread owns: chain index -> (part, line, first disparity).
+struct ChainSel {
+    float* cell;
+    uint32_t cstride;  // bytes
+    const uint32_t* desc_line;
+};
+template <bool VERT>
+__device__ __forceinline__ ChainSel select_chain(const Dims& dm, const ViewPtrs& v, bool tail_part, long long chain, int npair)
+{
+    float* part = tail_part ? v.vol.tail : v.vol.main;
+    const int pitch = tail_part ? dm.Rp : dm.Dm;
+    const int line = (int)(chain / npair), d = AGG_NC * (int)(chain % npair);
+    const size_t line_px = VERT ? (size_t)line : (size_t)line * dm.W;
+    ChainSel c;
+    c.cell = part + line_px * pitch + d;
+    c.cstride = (VERT ? (uint32_t)dm.W * (uint32_t)pitch : (uint32_t)pitch) * 4u;
+    c.desc_line = VERT ? v.desc_v + (size_t)line * dm.Hd() : v.desc_h + (size_t)line * dm.Wd();
+    return c;
+}
+
+// ---- kernel 1: shared-memory rings only (any Dm) ----
+// 64-thread CTAs, 73.7 KB of ring each, 3 CTAs = 6 warps per SM.
+template <bool VERT, bool NORM>
+__global__ void __launch_bounds__(AGG_BLOCK)
+k_agg_walk(Dims dm, ViewPtrs v0, ViewPtrs v1, int wsel, int nb_main)
+{
+    extern __shared__ __align__(16) unsigned char ring_raw[];  // [AGG_RING][AGG_BLOCK] x double2
+    const ViewPtrs& v = blockIdx.y ? v1 : v0;
+    const int nlines = VERT ? dm.W : dm.H, len = VERT ? dm.H : dm.W;
+    // chains of the 128-byte aligned main part first, then (blocks >= nb_main) those of the tail part
+    const bool tail_part = (int)blockIdx.x >= nb_main;
+    const int npair = tail_part ? (dm.tail() + AGG_NC - 1) / AGG_NC : dm.Dm / AGG_NC;
+    const long long chain = (long long)((int)blockIdx.x - (tail_part ? nb_main : 0)) * AGG_BLOCK + threadIdx.x;
+    if (chain >= (long long)nlines * npair) return;
+    const ChainSel c = select_chain<VERT>(dm, v, tail_part, chain, npair);
+    SmemRing<AGG_BLOCK> ring;
+    ring.base = (uint32_t)__cvta_generic_to_shared(ring_raw) + threadIdx.x * (8 * AGG_NC);
+    walk_line<NORM>(ring, c.cell, c.cstride, c.desc_line, len);
+}
+
+// ---- kernel 2: persistent, shared-memory AND tensor-memory rings (Dm % 64 == 0) ----
+// The walk is latency-bound per warp and its throughput grows with the number of resident warps,
+// which the 1152-byte ring per thread caps at 6 per SM in shared memory.  The SM's 256 KB of
+// tensor memory is idle in this pipeline, so it takes up to four more rings-worth of warps: one CTA
+// per SM, warps 0..tm-1 keep their rings in TMEM (one lane quarter each, 288 of 512 columns),
+// the others in 216 KB of shared memory.  TMEM slot addresses are warp-uniform, which holds when a
+// warp's 32 threads walk the same line: a work item is (view, line, 32 adjacent chain pairs = 64
+// disparities), hence Dm % 64 == 0.
+// Work items are handed out through a global counter, one warp at a time (no CTA-wide barrier
+// in the loop): a line walk is long (hundreds of microseconds), a static split leaves 10 % of the
+// SM-time idle in the last wave and would couple the faster and slower ring homes.
+// Tail part (Dn - Dm < 32 disparities per pixel), vertical passes: items of 32 columns x one pair, lanes
+// over columns; slot addresses are then per-lane, so only shared-memory warps take them -- first, so that
+// they overlap with the main items.  Horizontal passes of the tail part: k_agg_tail_h.
+constexpr int AGH_TM_MAX = 4, AGH_SM_WARPS = 6;
+constexpr int AGH_SM_THREADS = 32 * AGH_SM_WARPS;
+constexpr int AGH_SMEM = SmemRing<AGH_SM_THREADS>::SPAN;
+constexpr int AGH_MAX_BLOCK = 32 * (AGH_TM_MAX + AGH_SM_WARPS);
+static_assert(TmemRing::SPAN <= 512, "ring fits the TMEM columns");
+
+__device__ __forceinline__ unsigned next_item(unsigned* ctr, int lane)
+{
+    unsigned v = 0;
+    if (lane == 0) v = atomicAdd(ctr, 1u);
+    return __shfl_sync(0xffffffffu, v, 0);
+}
+
+template <bool VERT, bool NORM>
+__global__ void __launch_bounds__(AGH_MAX_BLOCK, 1)
+k_agg_persist(Dims dm, ViewPtrs v0, ViewPtrs v1, int tm_warps, unsigned* ctr)
+{
+    extern __shared__ __align__(16) unsigned char ring_raw[];  // [AGG_RING][AGH_SM_THREADS] x double2
+    __shared__ uint32_t tm_base;
+    const int nlines = VERT ? dm.W : dm.H, len = VERT ? dm.H : dm.W;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (tm_warps > 0) {
+        if (warp == 0) {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(
+                             (uint32_t)__cvta_generic_to_shared(&tm_base))
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    }
+    const unsigned ngroups = dm.Dm / 64, per_view = (unsigned)nlines * ngroups, n_main = 2 * per_view;
+    const size_t line_step = VERT ? (size_t)dm.Dm : (size_t)dm.W * dm.Dm;  // floats between lines, main part
+    const uint32_t cstride_main = (VERT ? (uint32_t)dm.W * (uint32_t)dm.Dm : (uint32_t)dm.Dm) * 4u;
+    const int desc_pitch = VERT ? dm.Hd() : dm.Wd();
+    if (warp < tm_warps) {
+        TmemRing ring;
+        ring.base = tm_base + ((uint32_t)(warp * 32) << 16);
+        unsigned item = next_item(ctr, lane);
+        while (item < n_main) {
+            const unsigned nxt = next_item(ctr, lane);  // its latency hides behind the walk
+            const ViewPtrs& v = item >= per_view ? v1 : v0;
+            const unsigned r = item >= per_view ? item - per_view : item;
+            const unsigned line = r / ngroups, grp = r - line * ngroups;
+            float* cell = v.vol.main + line * line_step + 64 * grp + 2 * lane;
+            const uint32_t* desc_line = (VERT ? v.desc_v : v.desc_h) + (size_t)line * desc_pitch;
+            walk_line<NORM>(ring, cell, cstride_main, desc_line, len);
+            item = nxt;
+        }
+    } else {
+        SmemRing<AGH_SM_THREADS> ring;
+        ring.base = (uint32_t)__cvta_generic_to_shared(ring_raw) + (threadIdx.x - 32 * tm_warps) * (8 * AGG_NC);
+        // tail part first
+        const int tpairs = (dm.tail() + AGG_NC - 1) / AGG_NC;
+        const unsigned lgroups = (unsigned)(nlines + 31) / 32, tail_per_view = lgroups * tpairs;
+        const unsigned n_tail = VERT ? 2 * tail_per_view : 0;  // horizontal: k_agg_tail_h
+        if (n_tail) {
+            const size_t tline_step = VERT ? (size_t)dm.Rp : (size_t)dm.W * dm.Rp;
+            const uint32_t cstride_tail = (VERT ? (uint32_t)dm.W * (uint32_t)dm.Rp : (uint32_t)dm.Rp) * 4u;
+            unsigned item = next_item(ctr + 1, lane);
+            while (item < n_tail) {
+                const unsigned nxt = next_item(ctr + 1, lane);
+                const ViewPtrs& v = item >= tail_per_view ? v1 : v0;
+                const unsigned r = item >= tail_per_view ? item - tail_per_view : item;
+                const unsigned lg = r / tpairs, pr = r - lg * tpairs;
+                const unsigned line = 32 * lg + lane;
+                if (line < (unsigned)nlines) {
+                    float* cell = v.vol.tail + line * tline_step + AGG_NC * pr;
+                    const uint32_t* desc_line = (VERT ? v.desc_v : v.desc_h) + (size_t)line * desc_pitch;
+                    walk_line<NORM>(ring, cell, cstride_tail, desc_line, len);
+                }
+                item = nxt;
+            }
+        }
+        unsigned item = next_item(ctr, lane);
+        while (item < n_main) {
+            const unsigned nxt = next_item(ctr, lane);
+            const ViewPtrs& v = item >= per_view ? v1 : v0;
+            const unsigned r = item >= per_view ? item - per_view : item;
+            const unsigned line = r / ngroups, grp = r - line * ngroups;
+            float* cell = v.vol.main + line * line_step + 64 * grp + 2 * lane;
+            const uint32_t* desc_line = (VERT ? v.desc_v : v.desc_h) + (size_t)line * desc_pitch;
+            walk_line<NORM>(ring, cell, cstride_main, desc_line, len);
+            item = nxt;
+        }
+    }
+    if (tm_warps > 0) {
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tm_base) : "memory");
+    }
+}
+
+// ---- kernel 3: horizontal pass over the tail part ----
+// In the tail part [H][W][Rp] a horizontal chain steps Rp floats at a time and neighbouring chains of a
+// warp would be whole image rows apart (one 32-byte sector per lane and step: measured +0.6 ms per pass
+// for 1/96 of the data).  A row of the tail is small, so here one CTA takes (row, view, disparity pair),
+// stages the row in shared memory with coalesced loads, turns it into fp64 prefix sums with a block
+// scan, and every output is the same  P[x+b+1] - P[x-a]  as in the walk.
+constexpr int AGT_BLOCK = 256;
+template <bool NORM>
+__global__ void __launch_bounds__(AGT_BLOCK)
+k_agg_tail_h(Dims dm, ViewPtrs v0, ViewPtrs v1)
+{
+    extern __shared__ __align__(16) unsigned char tail_raw[];
+    double2* P = reinterpret_cast<double2*>(tail_raw);  // [W + 1]
+    __shared__ double2 warp_tot[AGT_BLOCK / 32];
+    const ViewPtrs& v = blockIdx.y ? v1 : v0;
+    const int y = blockIdx.x, W = dm.W, Rp = dm.Rp, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    float* row = v.vol.tail + (size_t)y * W * Rp + 2 * blockIdx.z;
+    for (int x = tid; x < W; x += AGT_BLOCK) {
+        const float2 c = *reinterpret_cast<const float2*>(row + (size_t)x * Rp);
+        P[x + 1] = make_double2((double)c.x, (double)c.y);
+    }
+    if (tid == 0) P[0] = make_double2(0.0, 0.0);
+    __syncthreads();
+    // inclusive scan: sequential inside a thread's segment, shuffles across the warp, shared memory across warps
+    const int per = (W + AGT_BLOCK - 1) / AGT_BLOCK, x0 = min(W, tid * per), x1 = min(W, x0 + per);
+    double s0 = 0.0, s1 = 0.0;
+    for (int x = x0; x < x1; ++x) {
+        s0 += P[x + 1].x;
+        s1 += P[x + 1].y;
+        P[x + 1] = make_double2(s0, s1);
+    }
+    double i0 = s0, i1 = s1;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const double t0 = __shfl_up_sync(0xffffffffu, i0, o), t1 = __shfl_up_sync(0xffffffffu, i1, o);
+        if (lane >= o) { i0 += t0; i1 += t1; }
+    }
+    if (lane == 31) warp_tot[warp] = make_double2(i0, i1);
+    __syncthreads();
+    double o0 = i0 - s0, o1 = i1 - s1;  // exclusive offset inside the warp
+    for (int w = 0; w < warp; ++w) { o0 += warp_tot[w].x; o1 += warp_tot[w].y; }
+    for (int x = x0; x < x1; ++x) {
+        double2 p = P[x + 1];
+        p.x += o0; p.y += o1;
+        P[x + 1] = p;
+    }
+    __syncthreads();
+    const uint32_t* desc = v.desc_h + (size_t)y * dm.Wd();
+    for (int x = tid; x < W; x += AGT_BLOCK) {
+        const uint32_t w = desc[x];
+        const int a = w & 0xff, b = (w >> 8) & 0xff;
+        const double2 hi = P[x + b + 1], lo = P[x - a];
+        float r0 = __double2float_rn(hi.x - lo.x), r1 = __double2float_rn(hi.y - lo.y);
+        if (NORM) {
+            const RcpN rn = rcp_prepare((float)(w >> 16));
+            r0 = div_exact(r0, rn);
+            r1 = div_exact(r1, rn);
+        }
+        *reinterpret_cast<float2*>(row + (size_t)x * Rp) = make_float2(r0, r1);
     }
 }
 
@@ -327,21 +585,70 @@ k_agg_small(Dims dm, ViewPtrs v0, ViewPtrs v1, int wsel, int nb_main)
     }
 }
 
+// Ring-home mix of the persistent kernel: tm TMEM warps + sm shared-memory warps per SM.
+// TSM_AGG_MIX="tmH,smH,tmV,smV" overrides it (kernel experiments), "0" selects the shared-memory-only kernel.
+struct AggMix {
+    int tm[2], sm[2];  // [0] horizontal, [1] vertical pass
+    bool persist;
+};
+static const AggMix& agg_mix()
+{
+    static const AggMix m = [] {
+        AggMix r = {{4, 4}, {6, 6}, true};  // measured best at 1080p D=192 (profiles/README.md)
+        if (const char* e = getenv("TSM_AGG_MIX")) {
+            int a, b, c, d;
+            if (sscanf(e, "%d,%d,%d,%d", &a, &b, &c, &d) == 4 && a >= 0 && a <= AGH_TM_MAX && c >= 0 && c <= AGH_TM_MAX &&
+                b >= 1 && b <= AGH_SM_WARPS && d >= 1 && d <= AGH_SM_WARPS) {
+                r.tm[0] = a; r.sm[0] = b; r.tm[1] = c; r.sm[1] = d;
+            } else {
+                r.persist = false;
+            }
+        }
+        return r;
+    }();
+    return m;
+}
+
 template <bool VERT, bool NORM>
-static void launch_walk(const Launcher& L, const Dims& d, const ViewPtrs& left, const ViewPtrs& right, int wsel)
+static void launch_walk(const Launcher& L, const Dims& d, const ViewPtrs& left, const ViewPtrs& right, unsigned* ctr)
 {
     const int len = VERT ? d.H : d.W;
-    if (len >= AGG_LAG + 1 + AGG_U) {
+    const long long nl = VERT ? d.W : d.H;
+    const AggMix& mix = agg_mix();
+    if (!VERT && d.tail() > 0 && len >= AGG_LAG + 1 + AGG_U) {
+        const size_t smem = (size_t)(d.W + 1) * sizeof(double2);
+        static size_t smem_set = 48 * 1024;
+        if (smem > smem_set) {
+            cudaFuncSetAttribute(k_agg_tail_h<NORM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            smem_set = smem;
+        }
+        dim3 grid((unsigned)d.H, 2, (unsigned)((d.tail() + 1) / 2));
+        k_agg_tail_h<NORM><<<grid, AGT_BLOCK, smem, L.stream>>>(d, left, right);
+        L.count(1);
+    }
+    if (len >= AGG_LAG + 1 + AGG_U && AGG_NC == 2 && d.Dm >= 64 && d.Dm % 64 == 0 && mix.persist) {
         static bool attr_set = false;
+        static int n_sm = 0;
         if (!attr_set) {
-            cudaFuncSetAttribute(k_agg_walk<VERT, NORM>, cudaFuncAttributeMaxDynamicSharedMemorySize, AGG_RING_BYTES);
+            cudaFuncSetAttribute(k_agg_persist<VERT, NORM>, cudaFuncAttributeMaxDynamicSharedMemorySize, AGH_SMEM);
+            int dev = 0;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
             attr_set = true;
         }
-        const long long nl = VERT ? d.W : d.H;
+        const int tm = mix.tm[VERT], sm = mix.sm[VERT];
+        k_agg_persist<VERT, NORM><<<n_sm, 32 * (tm + sm), AGH_SMEM, L.stream>>>(d, left, right, tm, ctr);
+    } else if (len >= AGG_LAG + 1 + AGG_U) {
+        static bool attr_set = false;
+        if (!attr_set) {
+            cudaFuncSetAttribute(k_agg_walk<VERT, NORM>, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemRing<AGG_BLOCK>::SPAN);
+            attr_set = true;
+        }
         const int nb_main = (int)((nl * (d.Dm / AGG_NC) + AGG_BLOCK - 1) / AGG_BLOCK);
-        const int nb_tail = (int)((nl * ((d.tail() + AGG_NC - 1) / AGG_NC) + AGG_BLOCK - 1) / AGG_BLOCK);
+        const int nb_tail = VERT ? (int)((nl * ((d.tail() + AGG_NC - 1) / AGG_NC) + AGG_BLOCK - 1) / AGG_BLOCK) : 0;
         dim3 grid((unsigned)(nb_main + nb_tail), 2);
-        k_agg_walk<VERT, NORM><<<grid, AGG_BLOCK, AGG_RING_BYTES, L.stream>>>(d, left, right, wsel, nb_main);
+        if (grid.x == 0) return;  // Dn < 32, horizontal pass: the tail kernel did all of it
+        k_agg_walk<VERT, NORM><<<grid, AGG_BLOCK, SmemRing<AGG_BLOCK>::SPAN, L.stream>>>(d, left, right, 0, nb_main);
     } else {
         static bool attr_set = false;
         const size_t smem = (size_t)AGS_RING * AGS_BLOCK * sizeof(double);
@@ -349,11 +656,10 @@ static void launch_walk(const Launcher& L, const Dims& d, const ViewPtrs& left, 
             cudaFuncSetAttribute(k_agg_small<VERT, NORM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             attr_set = true;
         }
-        const long long nl = VERT ? d.W : d.H;
         const int nb_main = (int)((nl * d.Dm + AGS_BLOCK - 1) / AGS_BLOCK);
         const int nb_tail = (int)((nl * d.tail() + AGS_BLOCK - 1) / AGS_BLOCK);
         dim3 grid((unsigned)(nb_main + nb_tail), 2);
-        k_agg_small<VERT, NORM><<<grid, AGS_BLOCK, smem, L.stream>>>(d, left, right, wsel, nb_main);
+        k_agg_small<VERT, NORM><<<grid, AGS_BLOCK, smem, L.stream>>>(d, left, right, 0, nb_main);
     }
     L.count(1);
 }
@@ -365,16 +671,19 @@ size_t aggregate_overread_floats(const Dims& d)
     return (size_t)(AGG_U + 1) * d.W * (size_t)(d.Dm > d.Rp ? d.Dm : d.Rp);
 }
 
-void aggregate(const Launcher& L, const Dims& d, const ViewPtrs& left, const ViewPtrs& right)
+void aggregate(const Launcher& L, const Dims& d, const ViewPtrs& left, const ViewPtrs& right, unsigned* work_counters)
 {
+    // two work counters (main items, tail items) per pass of the persistent kernel
+    cudaMemsetAsync(work_counters, 0, kAggCounterBytes, L.stream);
     bool hf = true;
-    for (int it = 0; it < kIterations; ++it) {
+    unsigned* ctr = work_counters;
+    for (int it = 0; it < kIterations; ++it, ctr += 4) {
         if (hf) {
-            launch_walk<false, false>(L, d, left, right, 0);
-            launch_walk<true, true>(L, d, left, right, 0);
+            launch_walk<false, false>(L, d, left, right, ctr);
+            launch_walk<true, true>(L, d, left, right, ctr + 2);
         } else {
-            launch_walk<true, false>(L, d, left, right, 1);
-            launch_walk<false, true>(L, d, left, right, 1);
+            launch_walk<true, false>(L, d, left, right, ctr);
+            launch_walk<false, true>(L, d, left, right, ctr + 2);
         }
         hf = !hf;
     }

@@ -45,7 +45,7 @@ struct tsm_ctx {
     Buf disp[2], fin, ftmp;
     Buf v_vote, v_lowcnt, v_off, v_mark, v_start, v_sums, v_flat;
     Buf e_gray, e_blur, e_mag, e_gx, e_gy, e_map, e_edges, e_hist, e_lut, e_changed;
-    Buf tab_ad, tab_c;
+    Buf tab_ad, tab_c, agg_ctr;
     int disp_cur = 0;  // which of disp[2] holds the working map
     float p1_lo = 0.f, p2_lo = 0.f;
     bool tables_ready = false;
@@ -197,6 +197,7 @@ int ensure_arena(tsm_ctx* c, const tsm_adcensus_config* cfg, int H, int W)
         if ((rc = ensure(c, c->wta_[k], npx * 4))) return rc;
         if ((rc = ensure(c, c->disp[k], npx * 4))) return rc;
     }
+    if ((rc = ensure(c, c->agg_ctr, kAggCounterBytes))) return rc;
     if ((rc = ensure(c, c->fin, npx * 4))) return rc;
     if ((rc = ensure(c, c->ftmp, npx * 4))) return rc;
     if ((rc = ensure(c, c->v_vote, npx * 4))) return rc;
@@ -279,7 +280,7 @@ int run_stages(tsm_ctx* c, int mask, int arg)
     }
     if (mask & TSM_STAGE_AGGREGATE) {
         ScopedStage s(c, "aggregate");
-        aggregate(L, d, vl, vr);
+        aggregate(L, d, vl, vr, (unsigned*)c->agg_ctr.p);
     }
     if (mask & TSM_STAGE_SCANLINE) {
         ScopedStage s(c, "scanline");
@@ -439,7 +440,7 @@ void tsm_destroy(tsm_ctx* c)
                   &c->desc_h[0], &c->desc_h[1], &c->desc_v[0], &c->desc_v[1], &c->flags[0], &c->flags[1], &c->tflags[0], &c->tflags[1], &c->vtail[0], &c->vtail[1], &c->dense, &c->vol[0], &c->vol[1], &c->wta_[0], &c->wta_[1],
                   &c->disp[0], &c->disp[1], &c->fin, &c->ftmp, &c->v_vote, &c->v_lowcnt, &c->v_off, &c->v_mark, &c->v_start,
                   &c->v_sums, &c->v_flat, &c->e_gray, &c->e_blur, &c->e_mag, &c->e_gx, &c->e_gy, &c->e_map, &c->e_edges,
-                  &c->e_hist, &c->e_lut, &c->e_changed, &c->tab_ad, &c->tab_c, &c->r_src, &c->r_map1[0], &c->r_map1[1],
+                  &c->e_hist, &c->e_lut, &c->e_changed, &c->tab_ad, &c->tab_c, &c->agg_ctr, &c->r_src, &c->r_map1[0], &c->r_map1[1],
                   &c->r_map2[0], &c->r_map2[1], &c->r_fmap[0][0], &c->r_fmap[0][1], &c->r_fmap[1][0], &c->r_fmap[1][1]};
     for (Buf* b : all) release(*b);
     if (c->h_pair) cudaFreeHost(c->h_pair);
