@@ -135,6 +135,7 @@ __device__ __forceinline__ float2 ld_stream(const char* p)
 }
 __device__ __forceinline__ void st_stream(char* p, float a, float b)
 {
+
     if (AGG_NC == 2) asm volatile("st.global.L1::no_allocate.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(a), "f"(b) : "memory");
     else asm volatile("st.global.L1::no_allocate.f32 [%0], %1;" ::"l"(p), "f"(a) : "memory");
 }

@@ -10,14 +10,20 @@
 // result is bit-identical to the reference's libm on whatever box it runs.
 // census = sum_c popc((ltL_c & gtR_c) | (gtL_c & ltR_c))  (sign-product < 0 test, :469).
 //
-// Mapping: one CTA = (view, row y, 64-pixel tile).  The signatures + BGRx pixels of the
-// MOVING view (the one sampled at x -/+ d) for the tile's whole disparity reach are staged
-// once in shared memory.  A warp handles 4 consecutive pixels of the fixed view at a time;
-// lane l of chunk k owns ONE moving column and evaluates it against the 4 fixed pixels
-// (disparities e, e+1, e+2, e+3 -- resp. e, e-1, ... for the right view), so each staged
-// signature is read once per 4 cells and every pixel's cost vector is still written as
-// lane-contiguous rows.  The six 32-bit match words of a cell are summed with a carry-save
-// adder tree (3 POPC instead of 6: POPC is a quarter-rate instruction).
+// Both views come from ONE evaluation: the cost depends only on the pair (xL, xR), so
+//   C_1[d](y, c) = C_0[d](y, c + d)   for c + d < W,   2.f otherwise (xL leaves the image)
+// i.e. the right volume is the left volume sheared along x.  The kernel computes the left tile and
+// writes every value twice.
+//
+// Mapping: one CTA = (row y, 64 left pixels).  The signatures + BGRx pixels of the right view for
+// the tile's whole disparity reach are staged once in shared memory.  A warp handles 4 consecutive
+// left pixels at a time; lane l of chunk k owns ONE right column and evaluates it against the 4
+// left pixels (disparities e, e+1, e+2, e+3), so each staged signature is read once per 4 cells.
+// The six 32-bit match words of a cell are summed with a carry-save adder tree (3 POPC instead of
+// 6: POPC is a quarter-rate instruction).  Costs land in a shared tile [64][Dn]; it is then
+// flushed twice: as rows (left pixel vectors, aligned 16-byte stores) and along its diagonals
+// (right pixel c holds tile[c + d - x0][d], a run of <= 64 consecutive d: 128-byte aligned warp
+// stores; the diagonal walk has an odd bank stride, so it is conflict-free).
 #include "tsm_common.cuh"
 
 namespace tsm {
@@ -52,29 +58,26 @@ __global__ void __launch_bounds__(COST_WARPS * 32)
 k_cost_init(Dims dm, ViewPtrs vl, ViewPtrs vr, const float* __restrict__ g_tab_ad, const float* __restrict__ g_tab_c)
 {
     extern __shared__ __align__(16) uint32_t smem[];
-    const int view = blockIdx.z, y = blockIdx.y, x0 = blockIdx.x * COST_TX;
+    const int y = blockIdx.y, x0 = blockIdx.x * COST_TX;
     const int H = dm.H, W = dm.W, Dn = dm.Dn;
-    const int ncol = (COST_TX + Dn - 1 + 3) & ~3;  // moving columns the tile can reach (padded to keep 16-byte alignment)
+    const int ncol = (COST_TX + Dn - 1 + 3) & ~3;  // right columns the tile can reach (padded to keep 16-byte alignment)
     float* tab_ad = reinterpret_cast<float*>(smem);
     float* tab_c = tab_ad + TAB_AD_N;
     uint32_t* mw = reinterpret_cast<uint32_t*>(tab_c + TAB_C_PAD);  // [ncol][13]: 12 signature words + pixel (stride 13: conflict-free)
     for (int i = threadIdx.x; i < TAB_AD_N; i += blockDim.x) tab_ad[i] = g_tab_ad[i];
     for (int i = threadIdx.x; i < TAB_C_N; i += blockDim.x) tab_c[i] = g_tab_c[i];
 
-    const ViewPtrs& vf = view == 0 ? vl : vr;  // fixed view: its pixel stays at x
-    const ViewPtrs& vm = view == 0 ? vr : vl;  // moving view: sampled at x - d (view 0) / x + d (view 1)
     const size_t npx = (size_t)H * W, row = (size_t)y * W;
     const int hw = kCensusW / 2;
     const bool yout = (y - kCensusH / 2 < 0) || (y + kCensusH / 2 >= H);
-    // first staged moving column: view 0 reaches down to x0 - (Dn-1); view 1 starts at x0
-    const int cbase = view == 0 ? x0 - (Dn - 1) : x0;
+    const int cbase = x0 - (Dn - 1);  // first staged right column
     for (int i = threadIdx.x; i < ncol; i += blockDim.x) {
         const int c = cbase + i;
         const bool ok = !yout && c - hw >= 0 && c + hw < W;
-        mw[13 * i + 12] = ok ? vm.img4[row + c] : kInvalidPix;
+        mw[13 * i + 12] = ok ? vr.img4[row + c] : kInvalidPix;
 #pragma unroll
         for (int p = 0; p < 6; ++p) {
-            const uint64_t s = ok ? vm.census[(size_t)p * npx + row + c] : 0ull;
+            const uint64_t s = ok ? vr.census[(size_t)p * npx + row + c] : 0ull;
             mw[13 * i + 2 * p] = (uint32_t)s;
             mw[13 * i + 2 * p + 1] = (uint32_t)(s >> 32);
         }
@@ -82,23 +85,22 @@ k_cost_init(Dims dm, ViewPtrs vl, ViewPtrs vr, const float* __restrict__ g_tab_a
     __syncthreads();
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const Vol vol = vf.vol;
     const int nchunk = (Dn + COST_J - 1 + 31) / 32;
     const int DnP = (Dn + 3) & ~3;
-    float* wtile = reinterpret_cast<float*>(mw + 13 * ncol);  // [COST_WARPS][COST_J][DnP], 16-byte aligned
+    float* ctile = reinterpret_cast<float*>(mw + 13 * ncol);  // [COST_TX][DnP], 16-byte aligned
     for (int g = warp; g < COST_TX / COST_J; g += COST_WARPS) {
         const int x = x0 + g * COST_J;
         if (x >= W) break;
-        // the four fixed pixels x .. x+3 (uniform across the warp)
+        // the four left pixels x .. x+3 (uniform across the warp)
         Sig f[COST_J];
 #pragma unroll
         for (int j = 0; j < COST_J; ++j) {
             const int xf = x + j;
             const bool ok = !yout && xf < W && xf - hw >= 0 && xf + hw < W;
-            f[j].pix = ok ? vf.img4[row + xf] : kInvalidPix;
+            f[j].pix = ok ? vl.img4[row + xf] : kInvalidPix;
 #pragma unroll
             for (int p = 0; p < 6; ++p) {
-                const uint64_t s = ok ? vf.census[(size_t)p * npx + row + xf] : 0ull;
+                const uint64_t s = ok ? vl.census[(size_t)p * npx + row + xf] : 0ull;
                 f[j].w[2 * p] = (uint32_t)s;
                 f[j].w[2 * p + 1] = (uint32_t)(s >> 32);
             }
@@ -107,24 +109,19 @@ k_cost_init(Dims dm, ViewPtrs vl, ViewPtrs vr, const float* __restrict__ g_tab_a
 #pragma unroll
         for (int j = 0; j < COST_J; ++j) {
             fok[j] = f[j].pix != kInvalidPix;
-            // keep the fixed signatures in registers: without this the compiler re-loads all 28 words
+            // keep the left signatures in registers: without this the compiler re-loads all 28 words
             // from global memory in every chunk iteration instead of keeping 52 registers live
 #pragma unroll
             for (int i = 0; i < 12; ++i) asm volatile("" : "+r"(f[j].w[i]));
             asm volatile("" : "+r"(f[j].pix));
         }
-        // Costs go to a per-warp shared tile [J][DnP] first: in this mapping a lane's disparity for
-        // pixel j is e +- j, so direct global stores would all be sector-misaligned partial writes.
-        float* tile = wtile + warp * (COST_J * DnP);
-        float* tj[COST_J];  // tj[j] + e addresses disparity d_j = e +- j of pixel j
+        float* tj[COST_J];  // tj[j] + e addresses disparity d_j = e + j of left pixel x + j
 #pragma unroll
-        for (int j = 0; j < COST_J; ++j) tj[j] = tile + j * DnP + (view == 0 ? j : -j);
+        for (int j = 0; j < COST_J; ++j) tj[j] = ctile + (g * COST_J + j) * DnP + j;
         for (int k = 0; k < nchunk; ++k) {
-            // e = disparity of this lane's moving column against fixed pixel j = 0
-            //   view 0: column c = x - e, d_j = e + j, e in [-(J-1), Dn-1]
-            //   view 1: column c = x + e, d_j = e - j, e in [0, Dn-1+J-1]
-            const int e = 32 * k + lane - (view == 0 ? COST_J - 1 : 0);
-            const int ci = (view == 0 ? x - e : x + e) - cbase;
+            // e = disparity of this lane's right column c = x - e against left pixel j = 0; d_j = e + j
+            const int e = 32 * k + lane - (COST_J - 1);
+            const int ci = x - e - cbase;
             const bool cin = ci >= 0 && ci < ncol;
             const int cs = cin ? ci : 0;
             Sig m;
@@ -135,7 +132,7 @@ k_cost_init(Dims dm, ViewPtrs vl, ViewPtrs vr, const float* __restrict__ g_tab_a
             const bool mok = cin && m.pix != kInvalidPix;
 #pragma unroll
             for (int j = 0; j < COST_J; ++j) {
-                const int d = view == 0 ? e + j : e - j;
+                const int d = e + j;
                 const int ad3 = min((int)__vsadu4(f[j].pix, m.pix), TAB_AD_N - 1);
                 const int cen = census_count(f[j], m);
                 float cost = __fsub_rn(__fsub_rn(2.f, tab_ad[ad3]), tab_c[cen]);
@@ -143,20 +140,49 @@ k_cost_init(Dims dm, ViewPtrs vl, ViewPtrs vr, const float* __restrict__ g_tab_a
                 if ((unsigned)d < (unsigned)Dn) tj[j][e] = cost;
             }
         }
-        __syncwarp();
-        // flush: 16-byte aligned vector stores of the main part, scalar stores of the tail part
-        const int nq = dm.Dm / 4;  // float4 per pixel in the main part
-        const int r = dm.tail();
-#pragma unroll
-        for (int j = 0; j < COST_J; ++j) {
-            if (x + j < W) {
-                const float4* src = reinterpret_cast<const float4*>(tile + j * DnP);
-                float4* dst = reinterpret_cast<float4*>(vol.main + (row + x + j) * dm.Dm);
-                for (int q = lane; q < nq; q += 32) dst[q] = src[q];
-                if (lane < r) vol.tail[(row + x + j) * dm.Rp + lane] = tile[j * DnP + dm.Dm + lane];
+    }
+    __syncthreads();
+
+    const int Dm = dm.Dm, Rp = dm.Rp, r = dm.tail();
+    const int npix = min(COST_TX, W - x0);
+    // ---- left view: rows of the tile.  16-byte aligned vector stores of the main part, scalar stores of the tail part
+    {
+        const int nq = Dm / 4;  // float4 per pixel in the main part
+        for (int j = warp; j < npix; j += COST_WARPS) {
+            const float4* src = reinterpret_cast<const float4*>(ctile + j * DnP);
+            float4* dst = reinterpret_cast<float4*>(vl.vol.main + (row + x0 + j) * Dm);
+            for (int q = lane; q < nq; q += 32) dst[q] = src[q];
+            if (lane < r) vl.vol.tail[(row + x0 + j) * Rp + lane] = ctile[j * DnP + Dm + lane];
+        }
+    }
+    // ---- right view: diagonals of the tile.  Right pixel c gets d in [x0 - c, x0 + npix - 1 - c] (clipped to [0, Dn)).
+    for (int i = warp; i < COST_TX + Dn - 1; i += COST_WARPS) {
+        const int c = cbase + i;
+        if (c < 0 || c >= W) continue;
+        const int d0 = max(0, x0 - c), d1 = min(Dn - 1, x0 + npix - 1 - c);
+        float* dst = vr.vol.main + (row + c) * Dm;
+        float* dst_t = vr.vol.tail + (row + c) * Rp;
+        const float* src = ctile + (c - x0) * DnP;  // + d * (DnP + 1)
+        for (int d = (d0 & ~31) + lane; d <= d1; d += 32) {
+            if (d >= d0) {
+                const float v = src[d * (DnP + 1)];
+                if (d < Dm) dst[d] = v;
+                else dst_t[d - Dm] = v;
             }
         }
-        __syncwarp();
+    }
+    // ---- right view, cells whose left pixel c + d lies beyond the image: 2.f (ADCensus.cpp:562-566).  Last tile of the row.
+    if (blockIdx.x == gridDim.x - 1) {
+        for (int c = max(0, W - Dn + 1) + warp; c < W; c += COST_WARPS) {
+            float* dst = vr.vol.main + (row + c) * Dm;
+            float* dst_t = vr.vol.tail + (row + c) * Rp;
+            for (int d = ((W - c) & ~31) + lane; d < Dn; d += 32) {
+                if (d >= W - c) {
+                    if (d < Dm) dst[d] = 2.f;
+                    else dst_t[d - Dm] = 2.f;
+                }
+            }
+        }
     }
 }
 
@@ -164,13 +190,13 @@ void cost_init(const Launcher& L, const Dims& d, const ViewPtrs& left, const Vie
                const float* d_tab_census)
 {
     const size_t ncol = (size_t)((COST_TX + d.Dn - 1 + 3) & ~3), dnp = (size_t)((d.Dn + 3) & ~3);
-    const size_t smem = (size_t)(TAB_AD_N + TAB_C_PAD) * 4 + 13 * ncol * 4 + (size_t)COST_WARPS * COST_J * dnp * 4;
+    const size_t smem = (size_t)(TAB_AD_N + TAB_C_PAD) * 4 + 13 * ncol * 4 + (size_t)COST_TX * dnp * 4;
     static size_t smem_set = 0;
     if (smem > smem_set) {
         cudaFuncSetAttribute(k_cost_init, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         smem_set = smem;
     }
-    dim3 grid((d.W + COST_TX - 1) / COST_TX, d.H, 2);
+    dim3 grid((d.W + COST_TX - 1) / COST_TX, d.H);
     k_cost_init<<<grid, COST_WARPS * 32, smem, L.stream>>>(d, left, right, d_tab_ad, d_tab_census);
     L.count(1);
 }

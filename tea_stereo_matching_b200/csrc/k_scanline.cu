@@ -53,6 +53,7 @@ struct ScanParams {
     int store_right_final;  // 0: the last pass of the right volume only feeds its WTA
     int stage_bytes;        // Dm*4 + tail chunk + table window, multiple of 16
     int tail_bytes;         // bytes of the tail chunk copied per step (0 when Dn % 32 == 0)
+    int zero;               // always 0 (see the stage refill in scan_dir)
 };
 
 // ---- mbarrier / TMA bulk-copy primitives (sm_90+ PTX) ----
@@ -190,11 +191,11 @@ __device__ __forceinline__ void scan_dir(float (&prev)[K], const Vol& vol, const
         fx = VERT ? line : (dir > 0 ? pos : pos + 1);
     };
     // lane 0: arm the stage's mbarrier and launch the three bulk copies of step i
-    auto issue = [&](int i, unsigned slot) {
+    auto issue = [&](int i, unsigned slot, uint32_t dep) {
         int y, x, fy, fx;
         pixel(i, y, x, fy, fx);
         const size_t p = (size_t)y * W + x;
-        const uint32_t st = pipe.stage0 + slot * (unsigned)sp.stage_bytes, bar = pipe.bar0 + slot * 8u;
+        const uint32_t st = pipe.stage0 + slot * (unsigned)sp.stage_bytes + dep, bar = pipe.bar0 + slot * 8u;
         mbar_expect_tx(bar, total_bytes);
         if (main_bytes) tma_load_1d(st, vol.main + p * dm.Dm, main_bytes, bar);
         if (tail_bytes) {
@@ -206,7 +207,7 @@ __device__ __forceinline__ void scan_dir(float (&prev)[K], const Vol& vol, const
     };
 
     if (lane == 0) {
-        for (int i = 0; i < SC_NST && i < count; ++i) issue(i, (pipe.it + i) % SC_NST);
+        for (int i = 0; i < SC_NST && i < count; ++i) issue(i, (pipe.it + i) % SC_NST, 0u);
     }
     float* dst = nullptr;
     float* tdst = nullptr;
@@ -242,11 +243,28 @@ __device__ __forceinline__ void scan_dir(float (&prev)[K], const Vol& vol, const
         const int w0 = kTfPad + fx - a;  // window index of the flag pixel itself
         const uint32_t tw = lds_u32(st + main_bytes + tail_bytes + (w0 + sgn * lane) * 4);
         const uint32_t ow = lds_u32(st + main_bytes + tail_bytes + w0 * 4);
-        __syncwarp();  // every lane has read the stage; it may be refilled
-        if (lane == 0 && i + SC_NST < count) issue(i + SC_NST, slot);
+        // Refill the stage.  The bulk copy writes shared memory through the async proxy and is NOT
+        // ordered behind this warp's outstanding ld.shared: with a shared-memory-heavy kernel of
+        // another stream co-resident on the SM (slow LDS) and the volume L2-resident (fast copy), the
+        // copy overtook the loads and a step consumed the data of step i+8 (seen as rare run-to-run
+        // differences with several contexts in flight).  So the copy's destination address is made
+        // data-dependent on every loaded register (`zero` is a kernel argument the compiler cannot
+        // fold): the copies cannot issue before the loads have returned.
+        uint32_t dep = tw ^ ow;
+#pragma unroll
+        for (int k = 0; k < K; ++k) dep ^= __float_as_uint(cur[k]);
+        dep &= (uint32_t)sp.zero;
+#ifndef TSM_SCAN_ISSUE_LATE
+        __syncwarp();  // every lane has read the stage
+        if (lane == 0 && i + SC_NST < count) issue(i + SC_NST, slot, dep);
+#endif
+        const bool changed = scan_step<K>(prev, cur, tw & 0xffffu, ow >> 31, lane, sp);
+#ifdef TSM_SCAN_ISSUE_LATE
+        __syncwarp();
+        if (lane == 0 && i + SC_NST < count) issue(i + SC_NST, slot, dep);
+#endif
         pipe.it++;
 
-        const bool changed = scan_step<K>(prev, cur, tw & 0xffffu, ow >> 31, lane, sp);
         if (changed && do_store) store_vec<K>(dst, tdst, prev, lane, has_tail, lastvalid);
         dst += vstep;
         tdst += wstep;
@@ -298,9 +316,12 @@ k_scanline(Dims dm, ViewPtrs v0, ViewPtrs v1, ScanParams sp, int32_t* wta0, int3
     }
     // forward: pos = 1 .. len-1 (pred pos-1); backward: pos = len-2 .. 0 (pred pos+1).
     scan_dir<K, VERT, false>(prev, v.vol, v.stab, dm, pipe, line, 1, 1, len - 1, sgn, lane, has_tail, lastvalid, true, nullptr, sp);
-    // the backward pass re-reads (through the async proxy) what this warp has just written
-    asm volatile("fence.proxy.async;" ::: "memory");
+    // The backward pass re-reads, through the async proxy (TMA), what the lanes of this warp have just
+    // written with ordinary stores: make the stores visible at device scope, synchronise the warp, then
+    // order them against the async proxy before lane 0 issues the first bulk copies.
+    __threadfence();
     __syncwarp();
+    asm volatile("fence.proxy.async;" ::: "memory");
     if (VERT) {
         scan_dir<K, VERT, false>(prev, v.vol, v.stab, dm, pipe, line, len - 2, -1, len - 1, sgn, lane, has_tail, lastvalid, true,
                                  nullptr, sp);
@@ -343,6 +364,7 @@ void scanline(const Launcher& L, const Dims& d, const ViewPtrs& left, const View
     sp.p1[0] = p1_lo; sp.p1[1] = 0.25f; sp.p1[2] = 1.f;
     sp.p2[0] = p2_lo; sp.p2[1] = 0.75f; sp.p2[2] = 3.f;
     sp.store_right_final = store_right_final ? 1 : 0;
+    sp.zero = 0;
     sp.tail_bytes = d.Rp == 0 ? 0 : (d.Rp >= 4 ? d.Rp * 4 : 16);
     sp.stage_bytes = d.Dm * 4 + sp.tail_bytes + SC_WIN * 4;
     const int K = (d.Dn + 31) / 32;
