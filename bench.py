@@ -306,9 +306,16 @@ def main():
     achieved = agg_bytes / (agg_ms * 1e-3) / 1e9
     scan_ms = stage_acc.get("scanline", float("nan")) / 2
     scan_bytes = 16.0 * cells_pair  # one launch = forward + backward pass: 2 x (read + write)
+    # DRAM bytes per launch of the same kernel from the committed `ncu --set full` capture (profiles/), if any
+    traffic, traffic_src = None, None
+    tfile = ROOT / "profiles" / "ncu_traffic.json"
+    if tfile.exists():
+        tj = json.loads(tfile.read_text())
+        traffic, traffic_src = tj.get("k_agg_persist_bytes_per_launch"), tj.get("source")
     roofline = {
-        "bound": "hbm", "kernel": "k_agg_walk (one aggregation1D pass over both views)", "achieved": achieved, "peak": peak,
-        "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+        "bound": "hbm", "kernel": "k_agg_persist (one aggregation1D pass over both views; stage time / 8 passes)",
+        "achieved": achieved, "peak": peak,
+        "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
         "algorithmic_bytes_per_launch": agg_bytes, "avg_launch_ms": agg_ms,
         "other_kernels": {
             "k_scanline (fwd+bwd pass pair, both views)": {"achieved": scan_bytes / (scan_ms * 1e-3) / 1e9,

@@ -54,7 +54,10 @@ __device__ __forceinline__ int census_count(const Sig& f, const Sig& m)
     return __popc(ones) + 2 * __popc(twos) + 4 * __popc(fours);
 }
 
-__global__ void __launch_bounds__(COST_WARPS * 32)
+#ifndef TSM_COST_MINB
+#define TSM_COST_MINB 3
+#endif
+__global__ void __launch_bounds__(COST_WARPS * 32, TSM_COST_MINB)
 k_cost_init(Dims dm, ViewPtrs vl, ViewPtrs vr, const float* __restrict__ g_tab_ad, const float* __restrict__ g_tab_c)
 {
     extern __shared__ __align__(16) uint32_t smem[];
