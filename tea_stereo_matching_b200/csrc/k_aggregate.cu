@@ -495,28 +495,35 @@ k_agg_tail_h(Dims dm, ViewPtrs v0, ViewPtrs v1)
     }
     if (tid == 0) P[0] = make_double2(0.0, 0.0);
     __syncthreads();
-    // inclusive scan: sequential inside a thread's segment, shuffles across the warp, shared memory across warps
-    const int per = (W + AGT_BLOCK - 1) / AGT_BLOCK, x0 = min(W, tid * per), x1 = min(W, x0 + per);
-    double s0 = 0.0, s1 = 0.0;
-    for (int x = x0; x < x1; ++x) {
-        s0 += P[x + 1].x;
-        s1 += P[x + 1].y;
-        P[x + 1] = make_double2(s0, s1);
-    }
-    double i0 = s0, i1 = s1;
+    // inclusive scan: warp w owns the contiguous range [w*R, (w+1)*R) and walks it 32 elements at a time
+    // (consecutive lanes = consecutive 16-byte slots: conflict-free) with a running carry; the warp totals are
+    // exchanged through shared memory once and added in a second sweep.
+    const int R = (((W + AGT_BLOCK / 32 - 1) / (AGT_BLOCK / 32)) + 31) & ~31;
+    const int xb = warp * R, xe = min(W, xb + R);
+    double c0 = 0.0, c1 = 0.0;
+    for (int x = xb + lane; x - lane < xe; x += 32) {
+        double i0 = 0.0, i1 = 0.0;
+        if (x < xe) { const double2 p = P[x + 1]; i0 = p.x; i1 = p.y; }
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const double t0 = __shfl_up_sync(0xffffffffu, i0, o), t1 = __shfl_up_sync(0xffffffffu, i1, o);
-        if (lane >= o) { i0 += t0; i1 += t1; }
+        for (int o = 1; o < 32; o <<= 1) {
+            const double t0 = __shfl_up_sync(0xffffffffu, i0, o), t1 = __shfl_up_sync(0xffffffffu, i1, o);
+            if (lane >= o) { i0 += t0; i1 += t1; }
+        }
+        i0 += c0; i1 += c1;
+        if (x < xe) P[x + 1] = make_double2(i0, i1);
+        c0 = __shfl_sync(0xffffffffu, i0, 31);
+        c1 = __shfl_sync(0xffffffffu, i1, 31);
     }
-    if (lane == 31) warp_tot[warp] = make_double2(i0, i1);
+    if (lane == 0) warp_tot[warp] = make_double2(c0, c1);
     __syncthreads();
-    double o0 = i0 - s0, o1 = i1 - s1;  // exclusive offset inside the warp
+    double o0 = 0.0, o1 = 0.0;
     for (int w = 0; w < warp; ++w) { o0 += warp_tot[w].x; o1 += warp_tot[w].y; }
-    for (int x = x0; x < x1; ++x) {
-        double2 p = P[x + 1];
-        p.x += o0; p.y += o1;
-        P[x + 1] = p;
+    if (warp > 0) {
+        for (int x = xb + lane; x < xe; x += 32) {
+            double2 p = P[x + 1];
+            p.x += o0; p.y += o1;
+            P[x + 1] = p;
+        }
     }
     __syncthreads();
     const uint32_t* desc = v.desc_h + (size_t)y * dm.Wd();
