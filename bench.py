@@ -39,6 +39,7 @@ sys.path.insert(0, str(ROOT))
 H, W, MAXD = 1080, 1920, 192
 DN = MAXD + 1
 BATCH = 64
+IN_FLIGHT = 3
 DISTINCT = 8  # distinct synthetic frames generated per rank; the batch cycles through them
 METRIC = "Mpix*disp/s ADCensus 1920x1080 D=192"
 UNIT = "Mpix*disp/s"
@@ -171,6 +172,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH, help="frames per step over all ranks (default 64 = config C3)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--in-flight", type=int, default=IN_FLIGHT, help="stereo pairs in flight per GPU (contexts / streams)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -229,9 +231,9 @@ def main():
     log(f"[rank {rank}] generated {n_distinct} distinct synthetic frames in {time.time() - t0:.1f}s; "
         f"{len(my_frames)} frames per step on this rank")
 
-    # Two contexts (= two streams, two arenas) per GPU: frames alternate between them so the small
+    # IN_FLIGHT contexts (= streams, arenas) per GPU: frames alternate between them so the small
     # serial refinement kernels of one pair overlap with the bandwidth kernels of the other.
-    NCTX = 2
+    NCTX = max(1, args.in_flight)
     streams = [torch.cuda.Stream() for _ in range(NCTX)]
     matchers = []
     for st in streams:
@@ -327,20 +329,23 @@ def main():
     }
 
     # ---- e2e: public operator, host buffers, 2 pairs in flight per GPU ----
-    m2 = [tsm.ADCensus(device=local_rank) for _ in range(2)]
+    m2 = [tsm.ADCensus(device=local_rank) for _ in range(NCTX)]
     for m in m2:
         m.setMatchingStrategy(tsm.ColorModel.RGB, False, False)
         m.setMinMaxDisparity(0, MAXD)
-    h_out = [np.empty((H, W), np.float32) for _ in range(2)]
+    h_out = [np.empty((H, W), np.float32) for _ in range(NCTX)]
 
     def step_e2e():
         n = len(my_frames)
-        for j in range(n + 1):
+        lag = NCTX - 1  # a context is waited for right before it is needed again
+        for j in range(n + lag):
+            if lag and j >= lag:
+                m2[(j - lag) % NCTX].wait(h_out[(j - lag) % NCTX])
             if j < n:
                 l, r = frames[j % n_distinct]
-                m2[j % 2].enqueue(l, r)
-            if j >= 1:
-                m2[(j - 1) % 2].wait(h_out[(j - 1) % 2])
+                m2[j % NCTX].enqueue(l, r)
+                if not lag:
+                    m2[0].wait(h_out[0])
 
     e2e_steps = max(1, min(args.steps, 2))
     step_e2e()  # warm (arena + pinned allocations)
@@ -353,7 +358,7 @@ def main():
     e2e_value = total_cells * e2e_steps / e2e_s / 1e6
     e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(args.batch * 2 * H * W * 3),
            "d2h_bytes_per_step": int(args.batch * H * W * 4), "ms_per_step": 1e3 * e2e_s / e2e_steps, "steps": e2e_steps,
-           "in_flight_per_gpu": 2}
+           "in_flight_per_gpu": NCTX}
 
     # ---- CPU baseline on this box's host cores (rank 0, N == 1 only) ----
     cpu_baseline = None
@@ -374,7 +379,7 @@ def main():
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "C3: synthetic 1920x1080 RGB stereo pairs (synth_v1), D=0..192 (Dn=193)",
                        "frames_per_step": args.batch, "frames_per_gpu": len(my_frames), "distinct_frames_per_gpu": n_distinct,
-                       "parallelism": f"frame-sharded x{n_gpus}, no data-path collective; 2 pairs in flight per GPU (2 streams)",
+                       "parallelism": f"frame-sharded x{n_gpus}, no data-path collective; {NCTX} pairs in flight per GPU ({NCTX} streams)",
                        "l2": "working set 3.2 GB per frame >> 126 MB L2 (no flush needed)"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_baseline,
             "stages_ms": stage_acc,

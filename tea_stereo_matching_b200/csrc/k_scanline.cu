@@ -164,13 +164,16 @@ __device__ __forceinline__ int warp_argmin(const float (&v)[K], int lane)
 struct ScanPipe {
     uint32_t stage0;  // shared address of stage 0
     uint32_t bar0;    // shared address of mbarrier 0
-    unsigned it;      // steps consumed so far (stage = it % SC_NST, parity = (it / SC_NST) & 1)
+    uint32_t slot;    // stage the consumer reads next
+    uint32_t parity;  // phase parity the consumer waits for on that stage
 };
 
 // One direction of one line: `count` pixels starting at `first`, stepping by `dir` (+1/-1);
 // the predecessor of a pixel is the previous one on the path.
 //   VERT : pixel stride = one image row; flag pixel = (max(pos, pred), line), table plane 0
 //   HORZ : pixel stride = one pixel;     flag pixel = (line, max(pos, pred)), table plane 1
+// All per-step geometry is kept as running offsets (pixel index, table word offset, global pointers,
+// stage address): the address arithmetic of the copy issue is lane-0-only code the whole warp waits for.
 template <int K, bool VERT, bool WTA>
 __device__ __forceinline__ void scan_dir(float (&prev)[K], const Vol& vol, const uint32_t* __restrict__ stab, const Dims& dm,
                                          ScanPipe& pipe, int line, int first, int dir, int count, int sgn, int lane,
@@ -180,69 +183,69 @@ __device__ __forceinline__ void scan_dir(float (&prev)[K], const Vol& vol, const
     const uint32_t* tab = stab + (size_t)(VERT ? 0 : 1) * dm.H * Wp;
     const unsigned main_bytes = (unsigned)dm.Dm * 4u, tail_bytes = (unsigned)sp.tail_bytes;
     const unsigned total_bytes = main_bytes + tail_bytes + SC_WIN * 4u;
+    const unsigned stage_bytes = (unsigned)sp.stage_bytes;
     const int lo_off = sgn > 0 ? 0 : -31;  // lowest table column a lane reads, relative to the flag column
+    const bool wide_tail = dm.Rp >= 4;     // else the 16-byte tail chunk holds two pixels
 
-    // geometry of step i
-    auto pixel = [&](int i, int& y, int& x, int& fy, int& fx) {
-        const int pos = first + i * dir;
-        y = VERT ? pos : line;
-        x = VERT ? line : pos;
-        fy = VERT ? (dir > 0 ? pos : pos + 1) : line;
-        fx = VERT ? line : (dir > 0 ? pos : pos + 1);
-    };
-    // lane 0: arm the stage's mbarrier and launch the three bulk copies of step i
-    auto issue = [&](int i, unsigned slot, uint32_t dep) {
-        int y, x, fy, fx;
-        pixel(i, y, x, fy, fx);
-        const size_t p = (size_t)y * W + x;
-        const uint32_t st = pipe.stage0 + slot * (unsigned)sp.stage_bytes + dep, bar = pipe.bar0 + slot * 8u;
+    // step i: pixel index p(i) = p0 + i*pstep; its flag pixel sits at table word t(i) = t0 + i*tstep
+    // (row*Wp + kTfPad + column; Wp % 4 == 0, so the 16-byte aligned window starts at (t + lo_off) & ~3)
+    const int pstep = dir * (VERT ? W : 1), tstep = dir * (VERT ? Wp : 1);
+    const int p0 = VERT ? first * W + line : line * W + first;
+    const int f0 = dir > 0 ? first : first + 1;  // flag pixel = max(pos, pred) along the path
+    const int t0 = (VERT ? f0 * Wp + line : line * Wp + f0) + kTfPad + lo_off;
+    const ptrdiff_t vstep = (ptrdiff_t)pstep * dm.Dm, wstep = (ptrdiff_t)pstep * dm.Rp;
+
+    // ---- producer (lane 0 issues; the running state is kept by every lane so the warp stays uniform) ----
+    const float* gmain = vol.main + (size_t)p0 * dm.Dm;
+    int pi = p0, ti = t0;
+    uint32_t islot = pipe.slot;
+    // arm the stage's mbarrier and launch the three bulk copies of the producer's current pixel
+    auto issue = [&](uint32_t st, uint32_t bar) {
         mbar_expect_tx(bar, total_bytes);
-        if (main_bytes) tma_load_1d(st, vol.main + p * dm.Dm, main_bytes, bar);
+        if (main_bytes) tma_load_1d(st, gmain, main_bytes, bar);
         if (tail_bytes) {
-            const size_t te = dm.Rp >= 4 ? p * dm.Rp : (p & ~(size_t)1) * 2;
+            const size_t te = wide_tail ? (size_t)pi * dm.Rp : (size_t)(pi & ~1) * 2;
             tma_load_1d(st + main_bytes, vol.tail + te, tail_bytes, bar);
         }
-        const int a = (kTfPad + fx + lo_off) & ~3;
-        tma_load_1d(st + main_bytes + tail_bytes, tab + (size_t)fy * Wp + a, SC_WIN * 4u, bar);
+        tma_load_1d(st + main_bytes + tail_bytes, tab + (ti & ~3), SC_WIN * 4u, bar);
     };
-
-    if (lane == 0) {
-        for (int i = 0; i < SC_NST && i < count; ++i) issue(i, (pipe.it + i) % SC_NST, 0u);
-    }
-    float* dst = nullptr;
-    float* tdst = nullptr;
-    int32_t* wdst = nullptr;
+    auto advance_producer = [&]() {
+        gmain += vstep;
+        pi += pstep;
+        ti += tstep;
+    };
     {
-        int y, x, fy, fx;
-        pixel(0, y, x, fy, fx);
-        const size_t p = (size_t)y * W + x;
-        dst = vol.main + p * dm.Dm;
-        tdst = vol.tail + p * dm.Rp;
-        if (WTA) wdst = wta_out + p;
+        const int npro = count < SC_NST ? count : SC_NST;
+        for (int i = 0; i < npro; ++i) {
+            if (lane == 0) issue(pipe.stage0 + islot * stage_bytes, pipe.bar0 + islot * 8u);
+            advance_producer();
+            islot = islot + 1 == SC_NST ? 0 : islot + 1;
+        }
     }
-    const ptrdiff_t vstep = (ptrdiff_t)dir * (VERT ? (ptrdiff_t)W * dm.Dm : (ptrdiff_t)dm.Dm);
-    const ptrdiff_t wstep = (ptrdiff_t)dir * (VERT ? (ptrdiff_t)W * dm.Rp : (ptrdiff_t)dm.Rp);
-    const ptrdiff_t pstep = (ptrdiff_t)dir * (VERT ? (ptrdiff_t)W : 1);
+
+    // ---- consumer ----
+    float* dst = vol.main + (size_t)p0 * dm.Dm;
+    float* tdst = vol.tail + (size_t)p0 * dm.Rp;
+    int32_t* wdst = WTA ? wta_out + p0 : nullptr;
+    int pc = p0, tc = t0;
+    uint32_t st = pipe.stage0 + pipe.slot * stage_bytes, bar = pipe.bar0 + pipe.slot * 8u;
 
     for (int i = 0; i < count; ++i) {
-        const unsigned slot = pipe.it % SC_NST, parity = (pipe.it / SC_NST) & 1u;
-        const uint32_t st = pipe.stage0 + slot * (unsigned)sp.stage_bytes;
-        int y, x, fy, fx;
-        pixel(i, y, x, fy, fx);
-        mbar_wait(pipe.bar0 + slot * 8u, parity);
+        mbar_wait(bar, pipe.parity);
         float cur[K];
 #pragma unroll
         for (int k = 0; k < K; ++k) {
             if (k < K - 1 || !has_tail) cur[k] = lds_f32(st + (lane + 32 * k) * 4);
             else {
-                const int toff = dm.Rp >= 4 ? 0 : (int)((((size_t)y * W + x) & 1) * 2);
+                const int toff = wide_tail ? 0 : (pc & 1) * 2;
                 cur[k] = lastvalid ? lds_f32(st + main_bytes + (toff + lane) * 4) : CUDART_INF_F;
             }
         }
-        const int a = (kTfPad + fx + lo_off) & ~3;
-        const int w0 = kTfPad + fx - a;  // window index of the flag pixel itself
-        const uint32_t tw = lds_u32(st + main_bytes + tail_bytes + (w0 + sgn * lane) * 4);
-        const uint32_t ow = lds_u32(st + main_bytes + tail_bytes + w0 * 4);
+        const int w0 = (tc & 3) - lo_off;  // window index of the flag pixel itself
+        const uint32_t wbase = st + main_bytes + tail_bytes;
+        const uint32_t tw = lds_u32(wbase + (w0 + sgn * lane) * 4);
+        const uint32_t ow = lds_u32(wbase + w0 * 4);
+
         // Refill the stage.  The bulk copy writes shared memory through the async proxy and is NOT
         // ordered behind this warp's outstanding ld.shared: with a shared-memory-heavy kernel of
         // another stream co-resident on the SM (slow LDS) and the volume L2-resident (fast copy), the
@@ -254,17 +257,11 @@ __device__ __forceinline__ void scan_dir(float (&prev)[K], const Vol& vol, const
 #pragma unroll
         for (int k = 0; k < K; ++k) dep ^= __float_as_uint(cur[k]);
         dep &= (uint32_t)sp.zero;
-#ifndef TSM_SCAN_ISSUE_LATE
         __syncwarp();  // every lane has read the stage
-        if (lane == 0 && i + SC_NST < count) issue(i + SC_NST, slot, dep);
-#endif
-        const bool changed = scan_step<K>(prev, cur, tw & 0xffffu, ow >> 31, lane, sp);
-#ifdef TSM_SCAN_ISSUE_LATE
-        __syncwarp();
-        if (lane == 0 && i + SC_NST < count) issue(i + SC_NST, slot, dep);
-#endif
-        pipe.it++;
+        if (lane == 0 && i + SC_NST < count) issue(st + dep, bar);
+        advance_producer();
 
+        const bool changed = scan_step<K>(prev, cur, tw & 0xffffu, ow >> 31, lane, sp);
         if (changed && do_store) store_vec<K>(dst, tdst, prev, lane, has_tail, lastvalid);
         dst += vstep;
         tdst += wstep;
@@ -272,6 +269,16 @@ __device__ __forceinline__ void scan_dir(float (&prev)[K], const Vol& vol, const
             const int best = warp_argmin<K>(prev, lane);
             if (lane == 0) *wdst = best;
             wdst += pstep;
+        }
+        pc += pstep;
+        tc += tstep;
+        st += stage_bytes;
+        bar += 8u;
+        if (++pipe.slot == SC_NST) {
+            pipe.slot = 0;
+            pipe.parity ^= 1u;
+            st = pipe.stage0;
+            bar = pipe.bar0;
         }
     }
 }
@@ -296,7 +303,8 @@ k_scanline(Dims dm, ViewPtrs v0, ViewPtrs v1, ScanParams sp, int32_t* wta0, int3
     const uint32_t warp_bytes = SC_NST * (unsigned)sp.stage_bytes + SC_NST * 8u;
     pipe.stage0 = (uint32_t)__cvta_generic_to_shared(scan_smem) + warp * ((warp_bytes + 127u) & ~127u);
     pipe.bar0 = pipe.stage0 + SC_NST * (unsigned)sp.stage_bytes;
-    pipe.it = 0;
+    pipe.slot = 0;
+    pipe.parity = 0;
     if (lane == 0) {
         for (int s = 0; s < SC_NST; ++s) mbar_init(pipe.bar0 + s * 8u, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
