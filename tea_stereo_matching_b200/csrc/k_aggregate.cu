@@ -21,8 +21,10 @@
 // AGG_PF steps.
 //
 // Division: the reference divides the fp32 sum by (float)N with an IEEE fp32 divide
-// (ADCensus.cpp:747); div_exact(fl32(sum), N) (tsm_common.cuh) is that divide, correctly rounded,
-// without the slow-path branch of __fdiv_rn.
+// (ADCensus.cpp:747).  The walk multiplies by the correctly rounded reciprocal stored next to the
+// step descriptors and applies one residual correction (div_exact_rn, tsm_common.cuh); the small
+// kernels refine rcp.approx themselves (div_exact).  Both equal __fdiv_rn for every N <= 4489
+// (tsm_selftest), without its slow-path branch.
 //
 // Per-position side data (the two arm lengths of the pass and N) come as ONE 32-bit step
 // descriptor (k_prep.cu), four consecutive positions per 16-byte load: small broadcast loads
@@ -43,11 +45,15 @@ constexpr int AGG_LAG = kMaxArm;          // 33
 #define TSM_AGG_PF 4
 #endif
 constexpr int AGG_PF = TSM_AGG_PF;        // prefetch distance
+// Register buffers of the walk: NB-1 batches of AGG_PF loads in flight, NB*AGG_PF steps unrolled per loop
+// iteration.  More buffers = deeper prefetch but a bigger loop body, and the instruction cache matters: with
+// two ring homes (two copies of the loop) resident per SM, 8 buffers spent more cycles in no_instruction
+// stalls than in memory stalls (ncu), 6 is the measured optimum; the single-copy kernel is best at 8.
 #ifndef TSM_AGG_NBUF
-#define TSM_AGG_NBUF 8
+#define TSM_AGG_NBUF 6
 #endif
-constexpr int AGG_NBUF = TSM_AGG_NBUF;    // register buffers: NBUF-1 batches in flight
-constexpr int AGG_U = AGG_NBUF * AGG_PF;  // steps per main-loop iteration
+constexpr int AGG_NBUF_PERSIST = TSM_AGG_NBUF, AGG_NBUF_STATIC = 8;
+constexpr int AGG_U = 8 * AGG_PF;         // upper bound of the steps per main-loop iteration (over-read slack, minimum line length)
 #ifndef TSM_AGG_SUB
 #define TSM_AGG_SUB 4
 #endif
@@ -146,9 +152,9 @@ static_assert(AGG_PF % 4 == 0, "descriptors are fetched four at a time; batches 
 // BYTES between consecutive positions (32-bit: keeps the pointer stepping to one add-with-carry), `desc_line` = the line's step descriptors.
 // Requires len >= AGG_LAG + 1 + AGG_U (host-checked) and AGG_U positions of over-read slack
 // behind every line end (the volumes are allocated with it).
-template <bool NORM, class Ring>
+template <bool NORM, int NB, class Ring>
 __device__ __forceinline__ void walk_line(const Ring ring, float* cell, const uint32_t cstride, const uint32_t* desc_line,
-                                          const int len)
+                                          const float* rcp_line, const int len)
 {
     constexpr int SLOT = Ring::SLOT, SPAN = Ring::SPAN;
     typedef typename Ring::Raw Raw;
@@ -184,12 +190,12 @@ __device__ __forceinline__ void walk_line(const Ring ring, float* cell, const ui
     if (nx == SPAN) nx = 0;
 
     // ---- main: steps t = AGG_LAG .. len-1: push in[t] -> P[t+1], emit o = t - AGG_LAG ----
-    // Software pipeline in BATCHES of AGG_PF steps over AGG_NBUF register buffers: all loads of a
+    // Software pipeline in BATCHES of AGG_PF steps over NB register buffers: all loads of a
     // batch are issued back to back, NBUF-1 batches ahead of their use.  Batching matters: a warp
     // has only six scoreboard slots and a slot completes when ALL loads charged to it have landed,
     // so independent loads must be grouped by the time they are needed, not interleaved one per step.
-    float2 vin[AGG_NBUF][AGG_PF];
-    uint32_t av[AGG_NBUF][AGG_PF];
+    float2 vin[NB][AGG_PF];
+    uint32_t av[NB][AGG_PF];
     auto load_batch = [&](int buf) {
 #pragma unroll
         for (int u = 0; u < AGG_PF; ++u) {
@@ -210,15 +216,28 @@ __device__ __forceinline__ void walk_line(const Ring ring, float* cell, const ui
     // ring stores, (B) all ring loads, (C) the outputs.  A warp issues in order, so finishing step u
     // right after its own ring loads would expose the ring-load -> DADD -> F2F -> STG latency on
     // every step; grouped like this it is paid once per sub-block.
+    // Reciprocals of the divisors (normalising passes): L1-resident broadcast loads, fetched one batch ahead.
+    float yv[2][AGG_PF];
+    const float* rcp_ptr = rcp_line;
+    auto load_rcp = [&](int par) {
+        if (NORM) {
+#pragma unroll
+            for (int j = 0; j < AGG_PF / 4; ++j) {
+                const float4 q = *reinterpret_cast<const float4*>(rcp_ptr + 4 * j);
+                yv[par][4 * j + 0] = q.x; yv[par][4 * j + 1] = q.y; yv[par][4 * j + 2] = q.z; yv[par][4 * j + 3] = q.w;
+            }
+            rcp_ptr += AGG_PF;
+        }
+    };
     auto run_batch = [&](int buf, int nsteps) {  // nsteps == AGG_PF in the steady state
+        const int par = buf & 1;
+        load_rcp(par ^ 1);  // next batch
 #pragma unroll
         for (int u0 = 0; u0 < AGG_PF; u0 += AGG_SUB) {
             Raw hi[AGG_SUB], lo[AGG_SUB];
-            RcpN rn[AGG_SUB];
 #pragma unroll
             for (int w = 0; w < AGG_SUB; ++w) {
                 const int u = u0 + w;
-                if (NORM && u < nsteps) rn[w] = rcp_prepare((float)(av[buf][u] >> 16));  // off the critical path
                 if (u < nsteps) {
                     P0 += (double)vin[buf][u].x;
                     P1 += (double)vin[buf][u].y;
@@ -251,8 +270,10 @@ __device__ __forceinline__ void walk_line(const Ring ring, float* cell, const ui
                     ring.unpack(lo[w], l0, l1);
                     float r0 = __double2float_rn(h0 - l0), r1 = __double2float_rn(h1 - l1);
                     if (NORM) {
-                        r0 = div_exact(r0, rn[w]);
-                        r1 = div_exact(r1, rn[w]);
+                        // N < 2^23: (float)N without the conversion pipe
+                        const float nf = __fsub_rn(__uint_as_float(0x4B000000u | (av[buf][u] >> 16)), 8388608.f);
+                        r0 = div_exact_rn(r0, nf, yv[par][u]);
+                        r1 = div_exact_rn(r1, nf, yv[par][u]);
                     }
                     st_stream(out_ptr, r0, r1);
                     out_ptr += cstride;
@@ -264,13 +285,15 @@ __device__ __forceinline__ void walk_line(const Ring ring, float* cell, const ui
     const int nB = len - AGG_LAG;
     uint32_t newest = hs;  // slot of the newest prefix
     int done = 0;
-    // AGG_NBUF register buffers: NBUF-1 batches are in flight while one is being processed.
+    // NB register buffers: NBUF-1 batches are in flight while one is being processed.
+    static_assert(NB % 2 == 0, "reciprocal double buffer follows the batch parity");
 #pragma unroll
-    for (int b = 0; b < AGG_NBUF - 1; ++b) load_batch(b);
-    for (; done + AGG_NBUF * AGG_PF <= nB; done += AGG_NBUF * AGG_PF) {
+    for (int b = 0; b < NB - 1; ++b) load_batch(b);
+    load_rcp(0);
+    for (; done + NB * AGG_PF <= nB; done += NB * AGG_PF) {
 #pragma unroll
-        for (int b = 0; b < AGG_NBUF; ++b) {
-            load_batch((b + AGG_NBUF - 1) % AGG_NBUF);
+        for (int b = 0; b < NB; ++b) {
+            load_batch((b + NB - 1) % NB);
             run_batch(b, AGG_PF);
             nx += AGG_PF * SLOT;
             if (nx == SPAN) nx = 0;
@@ -281,9 +304,9 @@ __device__ __forceinline__ void walk_line(const Ring ring, float* cell, const ui
         int rem = nB - done;
         newest = (nx == 0 ? SPAN : nx) - SLOT;
 #pragma unroll
-        for (int b = 0; b < AGG_NBUF; ++b) {
+        for (int b = 0; b < NB; ++b) {
             if (rem > 0) {
-                if (b == AGG_NBUF - 1) load_batch(b);  // the one buffer that was not prefetched
+                if (b == NB - 1) load_batch(b);  // the one buffer that was not prefetched
                 const int n = rem < AGG_PF ? rem : AGG_PF;
                 run_batch(b, n);
                 newest = nx + (uint32_t)(n - 1) * SLOT;
@@ -315,9 +338,9 @@ __device__ __forceinline__ void walk_line(const Ring ring, float* cell, const ui
         ring.unpack(lo, l0, l1);
         float r0 = __double2float_rn(h0 - l0), r1 = __double2float_rn(h1 - l1);
         if (NORM) {
-            const RcpN rn = rcp_prepare((float)(desc >> 16));
-            r0 = div_exact(r0, rn);
-            r1 = div_exact(r1, rn);
+            const float nf = (float)(desc >> 16), y = rcp_line[o];
+            r0 = div_exact_rn(r0, nf, y);
+            r1 = div_exact_rn(r1, nf, y);
         }
         st_stream(out_ptr, r0, r1);
         out_ptr += cstride;
@@ -329,6 +352,7 @@ struct ChainSel {
     float* cell;
     uint32_t cstride;  // bytes
     const uint32_t* desc_line;
+    const float* rcp_line;
 };
 template <bool VERT>
 __device__ __forceinline__ ChainSel select_chain(const Dims& dm, const ViewPtrs& v, bool tail_part, long long chain, int npair)
@@ -341,6 +365,7 @@ __device__ __forceinline__ ChainSel select_chain(const Dims& dm, const ViewPtrs&
     c.cell = part + line_px * pitch + d;
     c.cstride = (VERT ? (uint32_t)dm.W * (uint32_t)pitch : (uint32_t)pitch) * 4u;
     c.desc_line = VERT ? v.desc_v + (size_t)line * dm.Hd() : v.desc_h + (size_t)line * dm.Wd();
+    c.rcp_line = VERT ? v.rcp_v + (size_t)line * dm.Hd() : v.rcp_h + (size_t)line * dm.Wd();
     return c;
 }
 
@@ -361,7 +386,7 @@ k_agg_walk(Dims dm, ViewPtrs v0, ViewPtrs v1, int wsel, int nb_main)
     const ChainSel c = select_chain<VERT>(dm, v, tail_part, chain, npair);
     SmemRing<AGG_BLOCK> ring;
     ring.base = (uint32_t)__cvta_generic_to_shared(ring_raw) + threadIdx.x * (8 * AGG_NC);
-    walk_line<NORM>(ring, c.cell, c.cstride, c.desc_line, len);
+    walk_line<NORM, AGG_NBUF_STATIC>(ring, c.cell, c.cstride, c.desc_line, c.rcp_line, len);
 }
 
 // ---- kernel 2: persistent, shared-memory AND tensor-memory rings (Dm % 64 == 0) ----
@@ -425,7 +450,8 @@ k_agg_persist(Dims dm, ViewPtrs v0, ViewPtrs v1, int tm_warps, unsigned* ctr)
             const unsigned line = r / ngroups, grp = r - line * ngroups;
             float* cell = v.vol.main + line * line_step + 64 * grp + 2 * lane;
             const uint32_t* desc_line = (VERT ? v.desc_v : v.desc_h) + (size_t)line * desc_pitch;
-            walk_line<NORM>(ring, cell, cstride_main, desc_line, len);
+            const float* rcp_line = (VERT ? v.rcp_v : v.rcp_h) + (size_t)line * desc_pitch;
+            walk_line<NORM, AGG_NBUF_PERSIST>(ring, cell, cstride_main, desc_line, rcp_line, len);
             item = nxt;
         }
     } else {
@@ -448,7 +474,8 @@ k_agg_persist(Dims dm, ViewPtrs v0, ViewPtrs v1, int tm_warps, unsigned* ctr)
                 if (line < (unsigned)nlines) {
                     float* cell = v.vol.tail + line * tline_step + AGG_NC * pr;
                     const uint32_t* desc_line = (VERT ? v.desc_v : v.desc_h) + (size_t)line * desc_pitch;
-                    walk_line<NORM>(ring, cell, cstride_tail, desc_line, len);
+                    const float* rcp_line = (VERT ? v.rcp_v : v.rcp_h) + (size_t)line * desc_pitch;
+                    walk_line<NORM, AGG_NBUF_PERSIST>(ring, cell, cstride_tail, desc_line, rcp_line, len);
                 }
                 item = nxt;
             }
@@ -461,7 +488,8 @@ k_agg_persist(Dims dm, ViewPtrs v0, ViewPtrs v1, int tm_warps, unsigned* ctr)
             const unsigned line = r / ngroups, grp = r - line * ngroups;
             float* cell = v.vol.main + line * line_step + 64 * grp + 2 * lane;
             const uint32_t* desc_line = (VERT ? v.desc_v : v.desc_h) + (size_t)line * desc_pitch;
-            walk_line<NORM>(ring, cell, cstride_main, desc_line, len);
+            const float* rcp_line = (VERT ? v.rcp_v : v.rcp_h) + (size_t)line * desc_pitch;
+            walk_line<NORM, AGG_NBUF_PERSIST>(ring, cell, cstride_main, desc_line, rcp_line, len);
             item = nxt;
         }
     }
@@ -710,7 +738,9 @@ __global__ void k_selftest_div(unsigned long long* mismatches)
         if (i & 1) a = __uint_as_float(0x3a000000u + i * 1021u);  // ~[4.9e-4, 1.3e4], stride-1021 mantissa walk
         else a = b * (float)(i >> 1) * 0.001953125f;                // multiples of b / 512
         if (!(a >= 0.f && a < 16384.f)) continue;
-        if (__float_as_uint(div_exact(a, rn)) != __float_as_uint(__fdiv_rn(a, b))) ++bad;
+        const unsigned want = __float_as_uint(__fdiv_rn(a, b));
+        if (__float_as_uint(div_exact(a, rn)) != want) ++bad;
+        if (__float_as_uint(div_exact_rn(a, b, __frcp_rn(b))) != want) ++bad;
     }
     if (bad) atomicAdd(mismatches, bad);
 }

@@ -114,7 +114,7 @@ __global__ void k_arms(const uint32_t* __restrict__ img4, uchar4* __restrict__ a
 // The pass that ENDS an iteration divides by N (:743-749): a vertical pass ends a
 // horizontal-first iteration (N_hf), a horizontal pass a vertical-first one (N_vf).
 __global__ void k_agg_desc(const uchar4* __restrict__ arms, uint32_t* __restrict__ desc_h, uint32_t* __restrict__ desc_v,
-                           int H, int W, int Wd, int Hd)
+                           float* __restrict__ rcp_h, float* __restrict__ rcp_v, int H, int W, int Wd, int Hd)
 {
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
     if (x >= W || y >= H) return;
@@ -131,6 +131,9 @@ __global__ void k_agg_desc(const uchar4* __restrict__ arms, uint32_t* __restrict
     }
     desc_h[(size_t)y * Wd + x] = (uint32_t)a.z | ((uint32_t)a.w << 8) | ((uint32_t)nv << 16);
     desc_v[(size_t)x * Hd + y] = (uint32_t)a.x | ((uint32_t)a.y << 8) | ((uint32_t)nh << 16);
+    // correctly rounded reciprocals of the divisors: the normalising passes divide with one residual correction
+    rcp_h[(size_t)y * Wd + x] = __frcp_rn((float)nv);
+    rcp_v[(size_t)x * Hd + y] = __frcp_rn((float)nh);
 }
 
 // ---- similarity flags ---------------------------------------------------------
@@ -196,7 +199,8 @@ void prep_view(const Launcher& L, const Dims& d, int view, const uint8_t* img, u
     k_census<<<cg, cb, 0, L.stream>>>(img4, census, d.H, d.W);
     dim3 b(32, 8), g((d.W + 31) / 32, (d.H + 7) / 8);
     k_arms<<<g, b, 0, L.stream>>>(img4, arms, d.H, d.W);
-    k_agg_desc<<<g, b, 0, L.stream>>>(arms, desc_h, desc_v, d.H, d.W, d.Wd(), d.Hd());
+    k_agg_desc<<<g, b, 0, L.stream>>>(arms, desc_h, desc_v, reinterpret_cast<float*>(desc_h + d.desc_h_words()),
+                                      reinterpret_cast<float*>(desc_v + d.desc_v_words()), d.H, d.W, d.Wd(), d.Hd());
     k_flags<<<g, b, 0, L.stream>>>(img4, flags, d.H, d.W);
     L.count(5);
 }

@@ -188,8 +188,8 @@ int ensure_arena(tsm_ctx* c, const tsm_adcensus_config* cfg, int H, int W)
         if ((rc = ensure(c, c->img4[k], npx * 4))) return rc;
         if ((rc = ensure(c, c->census[k], npx * 6 * 8))) return rc;
         if ((rc = ensure(c, c->arms[k], npx * 4))) return rc;
-        if ((rc = ensure(c, c->desc_h[k], ((size_t)H * d.Wd() + 256) * 4, true))) return rc;
-        if ((rc = ensure(c, c->desc_v[k], ((size_t)W * d.Hd() + 256) * 4, true))) return rc;
+        if ((rc = ensure(c, c->desc_h[k], d.desc_h_words() * 8, true))) return rc;
+        if ((rc = ensure(c, c->desc_v[k], d.desc_v_words() * 8, true))) return rc;
         if ((rc = ensure(c, c->flags[k], npx))) return rc;
         if ((rc = ensure(c, c->tflags[k], ((size_t)2 * H * d.stab_pitch() + 64) * 4, true))) return rc;
         if ((rc = ensure(c, c->vol[k], (npx * d.Dm + aggregate_overread_floats(d)) * 4 + 256, true))) return rc;
@@ -229,6 +229,8 @@ ViewPtrs view_ptrs(tsm_ctx* c, int k)
     v.arms = (const uchar4*)c->arms[k].p;
     v.desc_h = (const uint32_t*)c->desc_h[k].p;
     v.desc_v = (const uint32_t*)c->desc_v[k].p;
+    v.rcp_h = (const float*)(v.desc_h + c->dm.desc_h_words());
+    v.rcp_v = (const float*)(v.desc_v + c->dm.desc_v_words());
     v.flags = (const uint8_t*)c->flags[k].p;
     v.stab = (const uint32_t*)c->tflags[k].p;
     v.vol.main = (float*)c->vol[k].p;
