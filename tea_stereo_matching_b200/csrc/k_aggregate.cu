@@ -196,15 +196,19 @@ __device__ __forceinline__ void walk_line(const Ring ring, float* cell, const ui
     // so independent loads must be grouped by the time they are needed, not interleaved one per step.
     float2 vin[NB][AGG_PF];
     uint32_t av[NB][AGG_PF];
+    // Address of step u of a batch = base + u*cstride as ONE 32x32+64 multiply-add; done in asm because
+    // the compiler otherwise re-associates the unrolled loop into base + k*cstride with all the multiples
+    // hoisted as loop invariants (77 extra live registers in the vertical pass).
+    auto step_addr = [&](const char* base, int u) {
+        const char* a;
+        asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(a) : "r"(cstride), "r"((uint32_t)u), "l"(base));
+        return a;
+    };
     auto load_batch = [&](int buf) {
 #pragma unroll
-        for (int u = 0; u < AGG_PF; ++u) {
-            vin[buf][u] = ld_stream(in_ptr);
-            in_ptr += cstride;
-            // Opaque step: otherwise the unrolled loop is re-associated into base + k*cstride with all
-            // 32 multiples hoisted as loop invariants (77 extra live registers in the vertical pass).
-            asm volatile("" : "+l"(in_ptr));
-        }
+        for (int u = 0; u < AGG_PF; ++u) vin[buf][u] = ld_stream(step_addr(in_ptr, u));
+        in_ptr = step_addr(in_ptr, AGG_PF);
+        asm volatile("" : "+l"(in_ptr));
 #pragma unroll
         for (int j = 0; j < AGG_PF / 4; ++j) {
             const uint4 q = *reinterpret_cast<const uint4*>(desc_ptr + 4 * j);
@@ -252,12 +256,12 @@ __device__ __forceinline__ void walk_line(const Ring ring, float* cell, const ui
                     const uint32_t desc = av[buf][u];
                     const int a = desc & 0xff, b = (desc >> 8) & 0xff;
                     const uint32_t top = nx + u * SLOT;
-                    int s1 = (int)top - (AGG_LAG - b) * SLOT;      // P[o + b + 1]
-                    int s0 = (int)top - (AGG_LAG + 1 + a) * SLOT;  // P[o - a]
-                    s1 += (s1 < 0) ? SPAN : 0;
-                    s0 += (s0 < 0) ? SPAN : 0;
-                    ring.ld(s1, hi[w]);
-                    ring.ld(s0, lo[w]);
+                    // slot offsets lie in (-SPAN, SPAN): a negative one wraps to a huge unsigned value,
+                    // so the unsigned minimum with the offset + SPAN is the wrapped offset
+                    const uint32_t s1 = top - (uint32_t)(AGG_LAG - b) * SLOT;      // P[o + b + 1]
+                    const uint32_t s0 = top - (uint32_t)(AGG_LAG + 1 + a) * SLOT;  // P[o - a]
+                    ring.ld(min(s1, s1 + SPAN), hi[w]);
+                    ring.ld(min(s0, s0 + SPAN), lo[w]);
                 }
             }
             ring.ld_fence();
@@ -275,12 +279,12 @@ __device__ __forceinline__ void walk_line(const Ring ring, float* cell, const ui
                         r0 = div_exact_rn(r0, nf, yv[par][u]);
                         r1 = div_exact_rn(r1, nf, yv[par][u]);
                     }
-                    st_stream(out_ptr, r0, r1);
-                    out_ptr += cstride;
-                    asm volatile("" : "+l"(out_ptr));
+                    st_stream(const_cast<char*>(step_addr(out_ptr, u)), r0, r1);
                 }
             }
         }
+        out_ptr = const_cast<char*>(step_addr(out_ptr, nsteps));
+        asm volatile("" : "+l"(out_ptr));
     };
     const int nB = len - AGG_LAG;
     uint32_t newest = hs;  // slot of the newest prefix
