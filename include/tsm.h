@@ -124,6 +124,28 @@ int tsm_rectify_adcensus(tsm_ctx* ctx, const tsm_adcensus_config* cfg,
                          float* disparity, size_t dstep);
 void tsm_invalidate_maps(tsm_ctx* ctx);
 
+/* ---- consumers of the disparity map: the free functions of source/stereo.cpp that follow
+ * ADCensus::compute.  `disparity` is a host CV_32FC1 map (row stride `step`
+ * bytes), or NULL: then the map the last tsm_adcensus_* call of THIS context produced is consumed
+ * where it lies in device memory (H, W must match it) -- no D2H / H2D round trip.  Outputs are host
+ * buffers.  Pixels with d < 0 or d == inf stay 0 like in the reference.
+ *   tsm_reproject_to_depth   stereo::reprojectToDepth(disparity, f, B, depth)            stereo.cpp:139-151
+ *   tsm_reproject_to_3d      stereo::reprojectTo3D(disparity, f, B, cx, cy, XYZ)         stereo.cpp:153-172
+ *   tsm_reproject_to_3d_q    stereo::reprojectTo3D(disparity, Q, XYZ), Q = 4x4 row-major stereo.cpp:174-202
+ *   tsm_apply_colormap       stereo::applyColorMap(src, dst[, minVal, maxVal], colorMap)  stereo.cpp:95-137
+ *                            colormap = 256 x BGR bytes, NULL = stereo::JETColorMap()
+ *   tsm_jet_colormap         stereo::JETColorMap()                                        stereo.cpp:75-93
+ * xyz is CV_32FC3 (3 floats per pixel), dst of the colour map CV_8UC3. */
+int tsm_reproject_to_depth(tsm_ctx* ctx, const float* disparity, size_t step, int H, int W, float focal_length, float baseline,
+                           float* depth, size_t dstep);
+int tsm_reproject_to_3d(tsm_ctx* ctx, const float* disparity, size_t step, int H, int W, float focal_length, float baseline,
+                        float cx, float cy, float* xyz, size_t xstep);
+int tsm_reproject_to_3d_q(tsm_ctx* ctx, const float* disparity, size_t step, int H, int W, const double* Q, float* xyz,
+                          size_t xstep);
+int tsm_apply_colormap(tsm_ctx* ctx, const float* disparity, size_t step, int H, int W, int auto_range, float min_val,
+                       float max_val, const uint8_t* colormap, uint8_t* dst, size_t dstep);
+void tsm_jet_colormap(uint8_t* table768);
+
 /* ---- parity taps: the analogue of the reference's writeProcess debug dumps
  * (source/ADCensus.cpp:573-580, 785-792, 1003-1010).  tsm_stage_begin uploads a pair and
  * sizes the arena; tsm_stage_run runs the stages in `mask` (TSM_STAGE_* bits, in pipeline

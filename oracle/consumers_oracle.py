@@ -1,0 +1,111 @@
+"""TEST INFRASTRUCTURE -- CPU restatement (numpy, one IEEE fp32 operation per numpy call, reference order) of the
+disparity consumers of the reference's source/stereo.cpp:75-202.  Only tests/ may import this.
+
+The reference functions need OpenCV C++ (cv::Mat iterators, cv::gemm, cv::divide) and are therefore not compiled
+here; the two OpenCV calls are pinned against cv2 4.13 in tests/test_consumers_oracle.py (live when cv2 imports,
+plus committed vectors tests/golden/consumers_cv_golden.npz made by tests/golden/make_consumers_golden.py).
+"""
+import numpy as np
+
+F = np.float32
+
+
+def jet_colormap() -> np.ndarray:
+    """stereo::JETColorMap, stereo.cpp:75-93 (1x256 BGR)."""
+    t = np.zeros((256, 3), np.int64)
+    for i in range(32):
+        t[i] = (128 + 4 * i, 0, 0)
+    t[32] = (255, 0, 0)
+    for i in range(63):
+        t[33 + i] = (255, 4 + 4 * i, 0)
+    t[96] = (254, 255, 2)
+    for i in range(62):
+        t[97 + i] = (250 - 4 * i, 255, 6 + 4 * i)
+    t[159] = (1, 255, 254)
+    for i in range(64):
+        t[160 + i] = (0, 252 - 4 * i, 255)
+    for i in range(32):
+        t[224 + i] = (0, 0, 252 - 4 * i)
+    return t.astype(np.uint8).reshape(1, 256, 3)
+
+
+def _to_uchar_x86(t: np.ndarray) -> np.ndarray:
+    """static_cast<unsigned char>(float) as gcc/x86-64 does it: cvttss2si (INT_MIN when NaN / out of range), low byte."""
+    bad = ~np.isfinite(t) | (t >= F(2147483648.0)) | (t < F(-2147483648.0))
+    i = np.where(bad, np.int64(-2147483648), np.trunc(np.where(bad, 0, t)).astype(np.int64))
+    return (i & 0xFF).astype(np.uint8)
+
+
+def apply_colormap(src: np.ndarray, color_map: np.ndarray, min_val=None, max_val=None) -> np.ndarray:
+    """stereo::applyColorMap, stereo.cpp:95-118 (auto range) and :120-137 (explicit range)."""
+    src = np.asarray(src, F)
+    cm = np.asarray(color_map, np.uint8).reshape(256, 3)
+    with np.errstate(all="ignore"):
+        if min_val is None:
+            use = ~((src < 0) | np.isinf(src) | np.isnan(src))  # NaN never wins a std::min / std::max
+            mn = src[use].min() if use.any() else F(np.inf)
+            mx = src[use].max() if use.any() else F(-np.inf)
+            mn, mx = F(abs(mn)) if mn == 0 else F(mn), F(mx)
+            black = src < 0
+        else:
+            mn, mx = F(min_val), F(max_val)
+            black = (src < mn) | (src > mx)
+        t = ((src - mn) / F(mx - mn)) * F(255)
+    out = cm[_to_uchar_x86(t.astype(F))]
+    out[black] = 0
+    return out
+
+
+def reproject_to_depth(disp: np.ndarray, focal: float, baseline: float) -> np.ndarray:
+    """stereo::reprojectToDepth, stereo.cpp:139-151."""
+    disp = np.asarray(disp, F)
+    fb = F(focal) * F(baseline)
+    skip = (disp < 0) | np.isinf(disp)
+    with np.errstate(all="ignore"):
+        depth = (fb / disp).astype(F)
+    depth[skip] = 0
+    return depth
+
+
+def reproject_to_3d(disp: np.ndarray, focal: float, baseline: float, cx: float, cy: float) -> np.ndarray:
+    """stereo::reprojectTo3D(disparity, focalLength, baseline, cx, cy, XYZ), stereo.cpp:153-172."""
+    disp = np.asarray(disp, F)
+    H, W = disp.shape
+    fb = F(focal) * F(baseline)
+    u = np.arange(W, dtype=np.int64).astype(F)[None, :]
+    v = np.arange(H, dtype=np.int64).astype(F)[:, None]
+    skip = (disp < 0) | np.isinf(disp)
+    with np.errstate(all="ignore"):
+        Z = (fb / disp).astype(F)
+        zf = (Z / F(focal)).astype(F)
+        X = ((u - F(cx)).astype(F) * zf).astype(F)
+        Y = ((v - F(cy)).astype(F) * zf).astype(F)
+    xyz = np.stack([X, Y, Z], axis=-1)
+    xyz[skip] = 0
+    return xyz
+
+
+def gemm32f(A: np.ndarray, B: np.ndarray) -> np.ndarray:
+    """cv::gemm on CV_32F operands as OpenCV 4.13 computes a 4x4 by 4xN product: fp32 products and fp32 sums,
+    k ascending, no fused multiply-add (pinned against cv2.gemm on 800 000 columns: 0 mismatching bit patterns;
+    double accumulation or FMA mismatch on 40 % of them)."""
+    A, B = np.asarray(A, F), np.asarray(B, F)
+    s = np.zeros((A.shape[0], B.shape[1]), F)
+    with np.errstate(all="ignore"):
+        for k in range(A.shape[1]):
+            s = (s + (A[:, k : k + 1] * B[k : k + 1, :]).astype(F)).astype(F)
+    return s
+
+
+def reproject_to_3d_q(disp: np.ndarray, Q: np.ndarray) -> np.ndarray:
+    """stereo::reprojectTo3D(disparity, Q, XYZ), stereo.cpp:174-202."""
+    disp = np.asarray(disp, F)
+    H, W = disp.shape
+    u = np.broadcast_to(np.arange(W, dtype=F)[None, :], (H, W)).reshape(1, -1)
+    v = np.broadcast_to(np.arange(H, dtype=F)[:, None], (H, W)).reshape(1, -1)
+    pix = np.concatenate([u, v, disp.reshape(1, -1), np.ones((1, H * W), F)], axis=0)
+    Q32 = np.asarray(Q, np.float64).astype(F)
+    xyzw = gemm32f(Q32, pix)
+    with np.errstate(all="ignore"):
+        xyz = (xyzw[:3] / xyzw[3:4]).astype(F)  # cv::divide on floats: plain IEEE division
+    return np.ascontiguousarray(xyz.T.reshape(H, W, 3))

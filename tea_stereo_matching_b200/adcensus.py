@@ -114,6 +114,7 @@ class ADCensus:
         self._ctx = context
         self._device = device
         self._stream = stream
+        self.last_shape = (0, 0)  # geometry of the map of the last compute / enqueue (consumers.py)
 
     # -- reference API ----------------------------------------------------
     def setMinMaxDisparity(self, minDisparity: int, maxDisparity: int) -> None:
@@ -139,13 +140,14 @@ class ADCensus:
         ctx = self.context
         ctx.check(ctx._lib.tsm_adcensus_compute(ctx.handle, C.byref(self._config()), _ptr(left), left.strides[0],
                                                  _ptr(right), right.strides[0], H, W, _ptr(out), out.strides[0]))
+        self.last_shape = (H, W)
         return out
 
     # -- extras over the reference ------------------------------------------
     def enqueue(self, leftImage, rightImage) -> None:
         left, right = self._check_pair(leftImage, rightImage)
         H, W, _ = left.shape
-        self._pending_shape = (H, W)
+        self._pending_shape = self.last_shape = (H, W)
         ctx = self.context
         ctx.check(ctx._lib.tsm_adcensus_enqueue(ctx.handle, C.byref(self._config()), _ptr(left), left.strides[0],
                                                  _ptr(right), right.strides[0], H, W))
@@ -163,6 +165,7 @@ class ADCensus:
         ctx = self.context
         ctx.check(ctx._lib.tsm_adcensus_compute_device(ctx.handle, C.byref(self._config()), C.c_void_p(d_left),
                                                         C.c_void_p(d_right), H, W, C.c_void_p(d_out)))
+        self.last_shape = (H, W)
 
     @property
     def context(self) -> Context:

@@ -25,6 +25,8 @@
 #define CV_16UC1 CV_MAKETYPE(CV_16U, 1)
 #define CV_32SC1 CV_MAKETYPE(CV_32S, 1)
 #define CV_32FC1 CV_MAKETYPE(CV_32F, 1)
+#define CV_32FC3 CV_MAKETYPE(CV_32F, 3)
+#define CV_64FC1 CV_MAKETYPE(CV_64F, 1)
 #endif
 
 namespace cv {

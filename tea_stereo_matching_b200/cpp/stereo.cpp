@@ -275,3 +275,92 @@ void stereo::ADCensus::compute(EpipolarRectify& rectify, const cv::Mat& stereoIm
 	if (rc != TSM_OK) throw std::runtime_error(tsm_last_error(impl->ctx[0].h));
 	disparity = out;
 }
+
+// ---- consumers of the disparity map -------------------------------------------
+namespace {
+// One library context for the free functions (the reference's are stateless); device = env TSM_DEVICE or 0.
+tsm_ctx* consumer_ctx()
+{
+	static tsm_ctx* ctx = [] {
+		tsm_ctx* c = nullptr;
+		const char* e = std::getenv("TSM_DEVICE");
+		if (tsm_create(e ? std::atoi(e) : 0, &c) != TSM_OK) throw std::runtime_error(tsm_last_error(nullptr));
+		return c;
+	}();
+	return ctx;
+}
+void check_disparity(const cv::Mat& m, const char* who)
+{
+	if (m.empty() or m.type() != CV_32FC1) throw std::runtime_error(std::string(who) + ": disparity must be a non-empty CV_32FC1 map");
+}
+void consumer_check(tsm_ctx* c, int rc)
+{
+	if (rc != TSM_OK) throw std::runtime_error(tsm_last_error(c));
+}
+}
+
+cv::Mat stereo::JETColorMap()
+{
+	cv::Mat colorMap(1, 256, CV_8UC3);
+	tsm_jet_colormap(colorMap.data);
+	return colorMap;
+}
+
+static void apply_color_map(const cv::Mat& src, cv::Mat& dst, bool autoRange, float minVal, float maxVal, const cv::Mat& colorMap)
+{
+	check_disparity(src, "applyColorMap");
+	if (colorMap.empty() or colorMap.type() != CV_8UC3 or colorMap.rows * colorMap.cols != 256 or !colorMap.isContinuous())
+		throw std::runtime_error("applyColorMap: colorMap must be a continuous 1x256 CV_8UC3 table");
+	cv::Mat out(src.rows, src.cols, CV_8UC3);
+	tsm_ctx* c = consumer_ctx();
+	consumer_check(c, tsm_apply_colormap(c, (const float*)src.data, src.step, src.rows, src.cols, autoRange ? 1 : 0, minVal, maxVal,
+		colorMap.data, out.data, out.step));
+	dst = out;
+}
+
+void stereo::applyColorMap(const cv::Mat& src, cv::Mat& dst, const cv::Mat& colorMap)
+{
+	apply_color_map(src, dst, true, 0.f, 0.f, colorMap);
+}
+
+void stereo::applyColorMap(const cv::Mat& src, cv::Mat& dst, float minVal, float maxVal, const cv::Mat& colorMap)
+{
+	apply_color_map(src, dst, false, minVal, maxVal, colorMap);
+}
+
+void stereo::reprojectToDepth(const cv::Mat& disparity, float focalLength, float baseline, cv::Mat& depth)
+{
+	check_disparity(disparity, "reprojectToDepth");
+	cv::Mat out(disparity.rows, disparity.cols, CV_32FC1);
+	tsm_ctx* c = consumer_ctx();
+	consumer_check(c, tsm_reproject_to_depth(c, (const float*)disparity.data, disparity.step, disparity.rows, disparity.cols,
+		focalLength, baseline, (float*)out.data, out.step));
+	depth = out;
+}
+
+void stereo::reprojectTo3D(const cv::Mat& disparity, float focalLength, float baseline, float cx, float cy, cv::Mat& XYZPoints)
+{
+	check_disparity(disparity, "reprojectTo3D");
+	cv::Mat out(disparity.rows, disparity.cols, CV_32FC3);
+	tsm_ctx* c = consumer_ctx();
+	consumer_check(c, tsm_reproject_to_3d(c, (const float*)disparity.data, disparity.step, disparity.rows, disparity.cols,
+		focalLength, baseline, cx, cy, (float*)out.data, out.step));
+	XYZPoints = out;
+}
+
+void stereo::reprojectTo3D(const cv::Mat& disparity, const cv::Mat& Q, cv::Mat& XYZPoints)
+{
+	check_disparity(disparity, "reprojectTo3D");
+	if (Q.rows != 4 or Q.cols != 4 or (Q.type() != CV_64FC1 and Q.type() != CV_32FC1))
+		throw std::runtime_error("reprojectTo3D: Q must be a 4x4 CV_64FC1 or CV_32FC1 matrix");
+	double q[16];
+	for (int i = 0; i < 4; ++i)
+		for (int j = 0; j < 4; ++j)
+			q[4 * i + j] = Q.type() == CV_64FC1 ? ((const double*)(Q.data + (size_t)i * Q.step))[j]
+				: (double)((const float*)(Q.data + (size_t)i * Q.step))[j];
+	cv::Mat out(disparity.rows, disparity.cols, CV_32FC3);
+	tsm_ctx* c = consumer_ctx();
+	consumer_check(c, tsm_reproject_to_3d_q(c, (const float*)disparity.data, disparity.step, disparity.rows, disparity.cols, q,
+		(float*)out.data, out.step));
+	XYZPoints = out;
+}

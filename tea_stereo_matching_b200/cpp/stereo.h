@@ -107,4 +107,13 @@ private:
 	std::unique_ptr<ADCensusImpl> impl;
 };
 
+// ---- consumers of the disparity map: same free functions as the reference (include/stereo.h:194-235,
+// source/stereo.cpp:75-202), computed on the device (csrc/k_consumers.cu).  disparity is CV_32FC1.
+cv::Mat JETColorMap();
+void applyColorMap(const cv::Mat& src, cv::Mat& dst, const cv::Mat& colorMap);
+void applyColorMap(const cv::Mat& src, cv::Mat& dst, float minVal, float maxVal, const cv::Mat& colorMap);
+void reprojectToDepth(const cv::Mat& disparity, float focalLength, float baseline, cv::Mat& depth);
+void reprojectTo3D(const cv::Mat& disparity, float focalLength, float baseline, float cx, float cy, cv::Mat& XYZPoints);
+void reprojectTo3D(const cv::Mat& disparity, const cv::Mat& Q, cv::Mat& XYZPoints);  // Q: 4x4 CV_64FC1 or CV_32FC1
+
 }

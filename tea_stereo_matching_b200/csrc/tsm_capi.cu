@@ -46,6 +46,8 @@ struct tsm_ctx {
     Buf v_vote, v_lowcnt, v_off, v_mark, v_start, v_sums, v_flat;
     Buf e_gray, e_blur, e_mag, e_gx, e_gy, e_map, e_edges, e_hist, e_lut, e_changed;
     Buf tab_ad, tab_c, agg_ctr;
+    Buf k_in, k_out, k_tab, k_range;  // disparity consumers: staged input map, output, colour table, min/max
+    int fin_H = 0, fin_W = 0;        // geometry of the map in `fin` (0 = none yet)
     int disp_cur = 0;  // which of disp[2] holds the working map
     float p1_lo = 0.f, p2_lo = 0.f;
     bool tables_ready = false;
@@ -345,6 +347,8 @@ int run_stages(tsm_ctx* c, int mask, int arg)
     if (mask & TSM_STAGE_SUBPIXEL) {
         ScopedStage s(c, "subpixel");
         subpixel(L, d, (const int32_t*)c->disp[c->disp_cur].p, vl.vol, (float*)c->ftmp.p, (float*)c->fin.p);
+        c->fin_H = d.H;
+        c->fin_W = d.W;
     }
     CK(c, cudaGetLastError());
     return TSM_OK;
@@ -442,7 +446,7 @@ void tsm_destroy(tsm_ctx* c)
                   &c->desc_h[0], &c->desc_h[1], &c->desc_v[0], &c->desc_v[1], &c->flags[0], &c->flags[1], &c->tflags[0], &c->tflags[1], &c->vtail[0], &c->vtail[1], &c->dense, &c->vol[0], &c->vol[1], &c->wta_[0], &c->wta_[1],
                   &c->disp[0], &c->disp[1], &c->fin, &c->ftmp, &c->v_vote, &c->v_lowcnt, &c->v_off, &c->v_mark, &c->v_start,
                   &c->v_sums, &c->v_flat, &c->e_gray, &c->e_blur, &c->e_mag, &c->e_gx, &c->e_gy, &c->e_map, &c->e_edges,
-                  &c->e_hist, &c->e_lut, &c->e_changed, &c->tab_ad, &c->tab_c, &c->agg_ctr, &c->r_src, &c->r_map1[0], &c->r_map1[1],
+                  &c->e_hist, &c->e_lut, &c->e_changed, &c->tab_ad, &c->tab_c, &c->agg_ctr, &c->k_in, &c->k_out, &c->k_tab, &c->k_range, &c->r_src, &c->r_map1[0], &c->r_map1[1],
                   &c->r_map2[0], &c->r_map2[1], &c->r_fmap[0][0], &c->r_fmap[0][1], &c->r_fmap[1][0], &c->r_fmap[1][1]};
     for (Buf* b : all) release(*b);
     if (c->h_pair) cudaFreeHost(c->h_pair);
@@ -752,6 +756,112 @@ int tsm_poke(tsm_ctx* c, int buffer, const void* src, size_t bytes)
     CK(c, cudaMemcpyAsync(b->p, src, need, cudaMemcpyHostToDevice, c->stream));
     CK(c, cudaStreamSynchronize(c->stream));
     return TSM_OK;
+}
+
+// ---- disparity consumers -------------------------------------------------------------------------
+// Resolves the input map: a host map is staged densely into k_in; NULL selects the context's last result.
+static int consumer_input(tsm_ctx* c, const float* disparity, size_t step, int H, int W, const float** d_in)
+{
+    if (H <= 0 || W <= 0) return fail(c, TSM_E_ARG, "disparity consumer: empty map");
+    const size_t n = (size_t)H * W;
+    if (!disparity) {
+        if (c->fin_H != H || c->fin_W != W || !c->fin.p)
+            return fail(c, TSM_E_STATE, "disparity consumer: no %dx%d disparity map of this context to consume", W, H);
+        *d_in = (const float*)c->fin.p;
+        return TSM_OK;
+    }
+    if (step < (size_t)W * 4) return fail(c, TSM_E_ARG, "disparity consumer: row stride too small");
+    int rc;
+    if ((rc = ensure(c, c->k_in, n * 4))) return rc;
+    CK(c, cudaMemcpy2DAsync(c->k_in.p, (size_t)W * 4, disparity, step, (size_t)W * 4, H, cudaMemcpyHostToDevice, c->stream));
+    *d_in = (const float*)c->k_in.p;
+    return TSM_OK;
+}
+
+int tsm_reproject_to_depth(tsm_ctx* c, const float* disparity, size_t step, int H, int W, float focal, float baseline, float* depth,
+                           size_t dstep)
+{
+    if (!c) return TSM_E_ARG;
+    if (!depth || dstep < (size_t)W * 4) return fail(c, TSM_E_ARG, "tsm_reproject_to_depth: destination error");
+    CK(c, cudaSetDevice(c->device));
+    const float* d_in = nullptr;
+    int rc;
+    if ((rc = consumer_input(c, disparity, step, H, W, &d_in))) return rc;
+    const size_t n = (size_t)H * W;
+    if ((rc = ensure(c, c->k_out, n * 12))) return rc;
+    Launcher L{c->stream, &c->launches};
+    reproject_depth(L, d_in, (float*)c->k_out.p, n, focal, baseline);
+    CK(c, cudaGetLastError());
+    CK(c, cudaMemcpy2DAsync(depth, dstep, c->k_out.p, (size_t)W * 4, (size_t)W * 4, H, cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    return TSM_OK;
+}
+
+static int reproject_3d_common(tsm_ctx* c, const float* disparity, size_t step, int H, int W, float* xyz, size_t xstep,
+                               const double* Q, float focal, float baseline, float cx, float cy)
+{
+    if (!xyz || xstep < (size_t)W * 12) return fail(c, TSM_E_ARG, "tsm_reproject_to_3d: destination error");
+    CK(c, cudaSetDevice(c->device));
+    const float* d_in = nullptr;
+    int rc;
+    if ((rc = consumer_input(c, disparity, step, H, W, &d_in))) return rc;
+    const size_t n = (size_t)H * W;
+    if ((rc = ensure(c, c->k_out, n * 12))) return rc;
+    Launcher L{c->stream, &c->launches};
+    if (Q) reproject_xyz_q(L, d_in, (float*)c->k_out.p, H, W, Q);
+    else reproject_xyz_fb(L, d_in, (float*)c->k_out.p, H, W, focal, baseline, cx, cy);
+    CK(c, cudaGetLastError());
+    CK(c, cudaMemcpy2DAsync(xyz, xstep, c->k_out.p, (size_t)W * 12, (size_t)W * 12, H, cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    return TSM_OK;
+}
+
+int tsm_reproject_to_3d(tsm_ctx* c, const float* disparity, size_t step, int H, int W, float focal, float baseline, float cx, float cy,
+                        float* xyz, size_t xstep)
+{
+    if (!c) return TSM_E_ARG;
+    return reproject_3d_common(c, disparity, step, H, W, xyz, xstep, nullptr, focal, baseline, cx, cy);
+}
+
+int tsm_reproject_to_3d_q(tsm_ctx* c, const float* disparity, size_t step, int H, int W, const double* Q, float* xyz, size_t xstep)
+{
+    if (!c) return TSM_E_ARG;
+    if (!Q) return fail(c, TSM_E_ARG, "tsm_reproject_to_3d_q: Q is empty");
+    return reproject_3d_common(c, disparity, step, H, W, xyz, xstep, Q, 0.f, 0.f, 0.f, 0.f);
+}
+
+int tsm_apply_colormap(tsm_ctx* c, const float* disparity, size_t step, int H, int W, int auto_range, float min_val, float max_val,
+                       const uint8_t* colormap, uint8_t* dst, size_t dstep)
+{
+    if (!c) return TSM_E_ARG;
+    if (!dst || dstep < (size_t)W * 3) return fail(c, TSM_E_ARG, "tsm_apply_colormap: destination error");
+    CK(c, cudaSetDevice(c->device));
+    const float* d_in = nullptr;
+    int rc;
+    if ((rc = consumer_input(c, disparity, step, H, W, &d_in))) return rc;
+    const size_t n = (size_t)H * W;
+    if ((rc = ensure(c, c->k_out, n * 12))) return rc;
+    if ((rc = ensure(c, c->k_tab, 768))) return rc;
+    if ((rc = ensure(c, c->k_range, 8))) return rc;
+    uint8_t jet[768];
+    if (!colormap) {
+        jet_colormap(jet);
+        colormap = jet;
+    }
+    CK(c, cudaMemcpyAsync(c->k_tab.p, colormap, 768, cudaMemcpyHostToDevice, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));  // `jet` lives on this stack frame
+    Launcher L{c->stream, &c->launches};
+    apply_colormap(L, d_in, (uint8_t*)c->k_out.p, n, auto_range != 0, min_val, max_val, (const uint8_t*)c->k_tab.p,
+                   (int*)c->k_range.p);
+    CK(c, cudaGetLastError());
+    CK(c, cudaMemcpy2DAsync(dst, dstep, c->k_out.p, (size_t)W * 3, (size_t)W * 3, H, cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    return TSM_OK;
+}
+
+void tsm_jet_colormap(uint8_t* table768)
+{
+    if (table768) jet_colormap(table768);
 }
 
 int tsm_set_profiling(tsm_ctx* c, int enabled)

@@ -4,6 +4,8 @@
 //   api                     -- error behaviour only (no GPU needed)
 //   run in.bin out.bin      -- in.bin = int32 H, W, D + left BGR + right BGR; out.bin = float32 H*W
 //   batch in.bin out.bin n  -- the batched overload on n copies of the pair
+//   consume in.bin out.bin  -- disparity, then the README demo's consumers (README.md demo 5): out.bin = disparity,
+//                              reprojectToDepth (f=700,B=0.1), reprojectTo3D(f,B,cx,cy), reprojectTo3D(Q), applyColorMap(JET)
 #include "../../tea_stereo_matching_b200/cpp/stereo.h"
 #include <cstdio>
 #include <cstring>
@@ -62,6 +64,21 @@ int main(int argc, char** argv)
             std::vector<cv::Mat> ls(n, left), rs(n, right), ds;
             adcensus.compute(ls, rs, ds);
             for (auto& d : ds) o.write((const char*)d.data, (std::streamsize)H * W * 4);
+        } else if (!std::strcmp(argv[1], "consume")) {
+            cv::Mat disparity, depth, xyz, xyzq, color;
+            adcensus.compute(left, right, disparity);
+            stereo::reprojectToDepth(disparity, 700.f, 0.1f, depth);
+            stereo::reprojectTo3D(disparity, 700.f, 0.1f, W / 2.f, H / 2.f, xyz);
+            cv::Mat Q(4, 4, CV_64FC1);
+            const double q[16] = {1, 0, 0, -W / 2.0, 0, 1, 0, -H / 2.0, 0, 0, 0, 700.0, 0, 0, 10.0, 0.5};
+            std::memcpy(Q.data, q, sizeof q);
+            stereo::reprojectTo3D(disparity, Q, xyzq);
+            stereo::applyColorMap(disparity, color, stereo::JETColorMap());
+            o.write((const char*)disparity.data, (std::streamsize)H * W * 4);
+            o.write((const char*)depth.data, (std::streamsize)H * W * 4);
+            o.write((const char*)xyz.data, (std::streamsize)H * W * 12);
+            o.write((const char*)xyzq.data, (std::streamsize)H * W * 12);
+            o.write((const char*)color.data, (std::streamsize)H * W * 3);
         } else {
             cv::Mat disparity;
             adcensus.compute(left, right, disparity);

@@ -55,3 +55,31 @@ def test_facade_compute_matches_python_mirror_and_oracle(demo, pair_0600, port, 
     assert r.returncode == 0, r.stderr
     b = np.fromfile(out, np.float32).reshape(3, H, W)
     assert all(np.array_equal(b[i], got) for i in range(3))
+
+
+@pytest.mark.gpu
+def test_facade_consumers_match_oracle(demo, pair_0600, tmp_path):
+    from oracle import consumers_oracle as co
+
+    left, right = pair_0600
+    H, W, _ = left.shape
+    inp, out = tmp_path / "in.bin", tmp_path / "out.bin"
+    with open(inp, "wb") as f:
+        f.write(np.array([H, W, 48], np.int32).tobytes())
+        f.write(left.tobytes())
+        f.write(right.tobytes())
+    r = subprocess.run([str(demo), "consume", str(inp), str(out)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    raw = np.fromfile(out, np.uint8)
+    n = H * W
+    disp = raw[: 4 * n].view(np.float32).reshape(H, W)
+    depth = raw[4 * n : 8 * n].view(np.float32).reshape(H, W)
+    xyz = raw[8 * n : 20 * n].view(np.float32).reshape(H, W, 3)
+    xyzq = raw[20 * n : 32 * n].view(np.float32).reshape(H, W, 3)
+    color = raw[32 * n : 35 * n].reshape(H, W, 3)
+    Q = np.array([[1, 0, 0, -W / 2.0], [0, 1, 0, -H / 2.0], [0, 0, 0, 700.0], [0, 0, 10.0, 0.5]])
+    eq = lambda a, b: np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    assert eq(depth, co.reproject_to_depth(disp, 700.0, 0.1))
+    assert eq(xyz, co.reproject_to_3d(disp, 700.0, 0.1, W / 2.0, H / 2.0))
+    assert eq(xyzq, co.reproject_to_3d_q(disp, Q))
+    assert np.array_equal(color, co.apply_colormap(disp, co.jet_colormap()))
