@@ -28,7 +28,6 @@
 
 namespace tsm {
 
-constexpr int COST_TX = 64;     // pixels per CTA
 constexpr int COST_WARPS = 8;
 constexpr int COST_J = 4;       // fixed pixels per warp iteration
 constexpr int TAB_AD_N = 766, TAB_C_N = 192;
@@ -57,6 +56,8 @@ __device__ __forceinline__ int census_count(const Sig& f, const Sig& m)
 #ifndef TSM_COST_MINB
 #define TSM_COST_MINB 3
 #endif
+// COST_TX = left pixels per CTA: 64, or 32 when the shared tile [COST_TX][Dn] would otherwise leave one CTA per SM
+template <int COST_TX>
 __global__ void __launch_bounds__(COST_WARPS * 32, TSM_COST_MINB)
 k_cost_init(Dims dm, ViewPtrs vl, ViewPtrs vr, const float* __restrict__ g_tab_ad, const float* __restrict__ g_tab_c)
 {
@@ -189,19 +190,27 @@ k_cost_init(Dims dm, ViewPtrs vl, ViewPtrs vr, const float* __restrict__ g_tab_a
     }
 }
 
-void cost_init(const Launcher& L, const Dims& d, const ViewPtrs& left, const ViewPtrs& right, const float* d_tab_ad,
-               const float* d_tab_census)
+template <int COST_TX>
+static void launch_cost(const Launcher& L, const Dims& d, const ViewPtrs& left, const ViewPtrs& right, const float* d_tab_ad,
+                        const float* d_tab_census)
 {
     const size_t ncol = (size_t)((COST_TX + d.Dn - 1 + 3) & ~3), dnp = (size_t)((d.Dn + 3) & ~3);
     const size_t smem = (size_t)(TAB_AD_N + TAB_C_PAD) * 4 + 13 * ncol * 4 + (size_t)COST_TX * dnp * 4;
     static size_t smem_set = 0;
     if (smem > smem_set) {
-        cudaFuncSetAttribute(k_cost_init, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(k_cost_init<COST_TX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         smem_set = smem;
     }
     dim3 grid((d.W + COST_TX - 1) / COST_TX, d.H);
-    k_cost_init<<<grid, COST_WARPS * 32, smem, L.stream>>>(d, left, right, d_tab_ad, d_tab_census);
+    k_cost_init<COST_TX><<<grid, COST_WARPS * 32, smem, L.stream>>>(d, left, right, d_tab_ad, d_tab_census);
     L.count(1);
+}
+
+void cost_init(const Launcher& L, const Dims& d, const ViewPtrs& left, const ViewPtrs& right, const float* d_tab_ad,
+               const float* d_tab_census)
+{
+    if (d.Dn > 256) launch_cost<32>(L, d, left, right, d_tab_ad, d_tab_census);
+    else launch_cost<64>(L, d, left, right, d_tab_ad, d_tab_census);
 }
 
 }  // namespace tsm

@@ -98,13 +98,14 @@ void lrc(const Launcher& L, const Dims& d, const int32_t* dl, const int32_t* dr,
 // with ONE histogram that is cleared only after a high-vote outlier (:1150), so the
 // votes of every low-vote outlier (vote <= 20) leak into the next high-vote outlier.
 // Exact parallel form:
-//   1. k_vote_count : per outlier, own vote count; low-vote ones publish their count
-//   2. exclusive sum-scan over raster order -> CSR offsets of the low-vote lists
+//   1. k_vote_pass_a : per outlier ONE traversal of its region: histogram + vote count; high-vote outliers
+//                      are decided from their own histogram, low-vote ones park their (<= 20) votes
+//   2. exclusive sum-scan of the low vote counts over raster order -> CSR offsets
 //   3. k_vote_mark + exclusive max-scan     -> start of the run of low-vote outliers
 //                                              preceding each high-vote outlier
-//   4. k_vote_fill  : low-vote outliers write their (<= 20) votes into the CSR payload
-//   5. k_vote_high  : per high-vote outlier, histogram of own region + leaked slice
-//                     [start, off), first arg-max, ratio test (float)h/(float)vote > 0.4f
+//   4. k_vote_copy   : parked votes -> CSR payload
+//   5. k_vote_pass_b : only the high-vote outliers whose slice [start, off) is not empty are redone with
+//                      own region + leaked slice (first arg-max, ratio test (float)h/(float)vote > 0.4f)
 // Cross region of p (arms of the LEFT view): horizontal_first: rows y-up..y+down, each
 // with its own left/right arm; else columns x-left..x+right, each with its own up/down arm.
 
@@ -166,28 +167,98 @@ __device__ __forceinline__ int tile_compact(bool want, int local, int* list, int
     return *count;
 }
 
+// Adds the warp's votes to its shared-memory histogram: equal values are grouped first (match.any), so a
+// region full of one disparity costs one shared atomic instead of a 32-way serialised one.
+__device__ __forceinline__ void hist_add(int* hist, bool valid, int v, int lane)
+{
+    const unsigned act = __ballot_sync(0xffffffffu, valid);
+    if (!act) return;
+    if (valid) {
+        const unsigned peers = __match_any_sync(act, v);
+        if (lane == __ffs(peers) - 1) atomicAdd(&hist[v], __popc(peers));
+    }
+}
+
+// First arg-max over d ascending + the ratio test of ADCensus.cpp:1138-1152.
+__device__ __forceinline__ int vote_decide(const int* hist, int Dn, int nv, int dp, int lane)
+{
+    int best = 0, bd = INT_MAX;
+    for (int d = lane; d < Dn; d += 32) {
+        const int h = hist[d];
+        if (h > best) { best = h; bd = d; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const int oh = __shfl_xor_sync(0xffffffffu, best, o);
+        const int od = __shfl_xor_sync(0xffffffffu, bd, o);
+        if (oh > best || (oh == best && od < bd)) { best = oh; bd = od; }
+    }
+    const float ratio = __fdiv_rn((float)best, (float)nv);  // hist[d] / (float)vote, :1144
+    return (best > 0 && ratio > kVotingRatio) ? bd : dp;
+}
+
+// Pass A: ONE traversal of the cross region per outlier builds its histogram and its vote count.
+//   vote > 20 : decided right here from the own histogram -- final unless low-vote outliers precede it in raster
+//               order since the last high-vote one (their votes leak in, pass B redoes exactly those pixels);
+//   0 < vote <= 20 : pixel unchanged; its votes are parked in stash[p][0..vote) for the leak;
+//   vote == 0, valid pixels : unchanged.
 template <bool HF>
 __global__ void __launch_bounds__(VOTE_TILE)
-k_vote_count(const int32_t* __restrict__ disp, const uchar4* __restrict__ arms, int32_t* __restrict__ vote,
-             int32_t* __restrict__ lowcnt, size_t npx, int W)
+k_vote_pass_a(const int32_t* __restrict__ disp, const uchar4* __restrict__ arms, int32_t* __restrict__ vote,
+              int32_t* __restrict__ lowcnt, uint16_t* __restrict__ stash, int32_t* __restrict__ out, size_t npx, int W, int Dn)
 {
+    extern __shared__ int hist_all[];  // [VOTE_WARPS][Dn]
     __shared__ int list[VOTE_TILE];
     __shared__ int count;
     if (threadIdx.x == 0) count = 0;
     __syncthreads();
     const size_t p0 = (size_t)blockIdx.x * VOTE_TILE, pt = p0 + threadIdx.x;
-    const bool outlier = pt < npx && disp[pt] < 0;
-    if (pt < npx && !outlier) { vote[pt] = 0; lowcnt[pt] = 0; }
+    bool outlier = false;
+    if (pt < npx) {
+        const int dp = disp[pt];
+        outlier = dp < 0;
+        if (!outlier) { vote[pt] = 0; lowcnt[pt] = 0; out[pt] = dp; }
+    }
     const int n = tile_compact(outlier, threadIdx.x, list, &count);
-    const int lane = threadIdx.x & 31;
-    for (int i = threadIdx.x >> 5; i < n; i += VOTE_WARPS) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int* hist = hist_all + warp * Dn;
+    for (int i = warp; i < n; i += VOTE_WARPS) {
         const size_t p = p0 + list[i];
+        const int dp = disp[p];
+        for (int d = lane; d < Dn; d += 32) hist[d] = 0;
+        __syncwarp();
         int cnt = 0;
-        for_each_region<HF>(disp, arms, W, p, lane, [&](bool valid, int) { cnt += __popc(__ballot_sync(0xffffffffu, valid)); });
+        for_each_region<HF>(disp, arms, W, p, lane, [&](bool valid, int v) {
+            cnt += __popc(__ballot_sync(0xffffffffu, valid));
+            hist_add(hist, valid, v, lane);
+        });
+        __syncwarp();
+        int res = dp;
+        if (cnt > kVotingThresh) {
+            res = vote_decide(hist, Dn, cnt, dp, lane);
+        } else if (cnt > 0) {
+            // park the votes (order is irrelevant for a histogram): bin d contributes hist[d] copies of d
+            uint16_t* dst = stash + p * kVotingThresh;
+            int base = 0;
+            for (int d0 = 0; d0 < Dn; d0 += 32) {
+                const int d = d0 + lane;
+                const int h = d < Dn ? hist[d] : 0;
+                int incl = h;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += t;
+                }
+                for (int k = 0; k < h; ++k) dst[base + incl - h + k] = (uint16_t)d;
+                base += __shfl_sync(0xffffffffu, incl, 31);
+            }
+        }
         if (lane == 0) {
             vote[p] = cnt;
             lowcnt[p] = cnt <= kVotingThresh ? cnt : 0;
+            out[p] = res;
         }
+        __syncwarp();
     }
 }
 
@@ -199,40 +270,25 @@ __global__ void k_vote_mark(const int32_t* __restrict__ disp, const int32_t* __r
     mark[p] = (disp[p] < 0 && vote[p] > kVotingThresh) ? off[p] : 0;
 }
 
-template <bool HF>
-__global__ void __launch_bounds__(VOTE_TILE)
-k_vote_fill(const int32_t* __restrict__ disp, const uchar4* __restrict__ arms, const int32_t* __restrict__ vote,
-            const int32_t* __restrict__ off, uint16_t* __restrict__ flat, size_t npx, int W)
+// parked votes -> CSR payload in raster order of their pixels
+__global__ void k_vote_copy(const int32_t* __restrict__ lowcnt, const int32_t* __restrict__ off, const uint16_t* __restrict__ stash,
+                            uint16_t* __restrict__ flat, size_t npx)
 {
-    __shared__ int list[VOTE_TILE];
-    __shared__ int count;
-    if (threadIdx.x == 0) count = 0;
-    __syncthreads();
-    const size_t p0 = (size_t)blockIdx.x * VOTE_TILE, pt = p0 + threadIdx.x;
-    bool low = false;
-    if (pt < npx && disp[pt] < 0) {
-        const int nv = vote[pt];
-        low = nv > 0 && nv <= kVotingThresh;
-    }
-    const int n = tile_compact(low, threadIdx.x, list, &count);
-    const int lane = threadIdx.x & 31;
-    for (int i = threadIdx.x >> 5; i < n; i += VOTE_WARPS) {
-        const size_t p = p0 + list[i];
-        uint16_t* dst = flat + off[p];
-        int base = 0;
-        for_each_region<HF>(disp, arms, W, p, lane, [&](bool valid, int v) {
-            const unsigned b = __ballot_sync(0xffffffffu, valid);
-            if (valid) dst[base + __popc(b & ((1u << lane) - 1u))] = (uint16_t)v;
-            base += __popc(b);
-        });
-    }
+    const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= npx) return;
+    const int n = lowcnt[p];
+    if (n == 0) return;
+    const uint16_t* src = stash + p * kVotingThresh;
+    uint16_t* dst = flat + off[p];
+    for (int k = 0; k < n; ++k) dst[k] = src[k];
 }
 
+// Pass B: high-vote outliers that inherit leaked votes (start < off): own region again + the slice.
 template <bool HF>
 __global__ void __launch_bounds__(VOTE_TILE)
-k_vote_high(const int32_t* __restrict__ disp, const uchar4* __restrict__ arms, const int32_t* __restrict__ vote,
-            const int32_t* __restrict__ off, const int32_t* __restrict__ start, const uint16_t* __restrict__ flat,
-            int32_t* __restrict__ out, size_t npx, int W, int Dn)
+k_vote_pass_b(const int32_t* __restrict__ disp, const uchar4* __restrict__ arms, const int32_t* __restrict__ vote,
+              const int32_t* __restrict__ off, const int32_t* __restrict__ start, const uint16_t* __restrict__ flat,
+              int32_t* __restrict__ out, size_t npx, int W, int Dn)
 {
     extern __shared__ int hist_all[];  // [VOTE_WARPS][Dn]
     __shared__ int list[VOTE_TILE];
@@ -240,40 +296,24 @@ k_vote_high(const int32_t* __restrict__ disp, const uchar4* __restrict__ arms, c
     if (threadIdx.x == 0) count = 0;
     __syncthreads();
     const size_t p0 = (size_t)blockIdx.x * VOTE_TILE, pt = p0 + threadIdx.x;
-    bool high = false;
-    if (pt < npx) {
-        const int dp = disp[pt];
-        high = dp < 0 && vote[pt] > kVotingThresh;
-        if (!high) out[pt] = dp;  // valid pixel or low-vote outlier: unchanged (:1077-1080, :1132-1135)
-    }
-    const int n = tile_compact(high, threadIdx.x, list, &count);
+    bool redo = false;
+    if (pt < npx) redo = disp[pt] < 0 && vote[pt] > kVotingThresh && start[pt] < off[pt];
+    const int n = tile_compact(redo, threadIdx.x, list, &count);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int* hist = hist_all + warp * Dn;
     for (int i = warp; i < n; i += VOTE_WARPS) {
         const size_t p = p0 + list[i];
-        const int dp = disp[p], nv = vote[p];
         for (int d = lane; d < Dn; d += 32) hist[d] = 0;
         __syncwarp();
-        for_each_region<HF>(disp, arms, W, p, lane, [&](bool valid, int v) {
-            if (valid) atomicAdd(&hist[v], 1);
-        });
-        for (int j = start[p] + lane; j < off[p]; j += 32) atomicAdd(&hist[flat[j]], 1);  // the leak
+        for_each_region<HF>(disp, arms, W, p, lane, [&](bool valid, int v) { hist_add(hist, valid, v, lane); });
+        for (int j0 = start[p]; j0 < off[p]; j0 += 32) {  // the leak
+            const int j = j0 + lane;
+            const bool in = j < off[p];
+            hist_add(hist, in, in ? (int)flat[j] : 0, lane);
+        }
         __syncwarp();
-        int best = 0, bd = INT_MAX;
-        for (int d = lane; d < Dn; d += 32) {
-            const int h = hist[d];
-            if (h > best) { best = h; bd = d; }
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const int oh = __shfl_xor_sync(0xffffffffu, best, o);
-            const int od = __shfl_xor_sync(0xffffffffu, bd, o);
-            if (oh > best || (oh == best && od < bd)) { best = oh; bd = od; }
-        }
-        if (lane == 0) {
-            const float ratio = __fdiv_rn((float)best, (float)nv);  // hist[d] / (float)vote, :1144
-            out[p] = (best > 0 && ratio > kVotingRatio) ? bd : dp;
-        }
+        const int res = vote_decide(hist, Dn, vote[p], disp[p], lane);
+        if (lane == 0) out[p] = res;
         __syncwarp();
     }
 }
@@ -384,15 +424,15 @@ static void region_voting_t(const Launcher& L, const Dims& d, const int32_t* dis
 {
     const size_t npx = d.npx();
     const unsigned wblocks = (unsigned)((npx + VOTE_TILE - 1) / VOTE_TILE);
-    k_vote_count<HF><<<wblocks, VOTE_TILE, 0, L.stream>>>(disp_in, arms, s.vote, s.lowcnt, npx, d.W);
+    const size_t smem = (size_t)VOTE_WARPS * d.Dn * sizeof(int);
+    k_vote_pass_a<HF><<<wblocks, VOTE_TILE, smem, L.stream>>>(disp_in, arms, s.vote, s.lowcnt, s.stash, disp_out, npx, d.W, d.Dn);
     L.count(1);
     exclusive_scan<OpSum>(L, s.lowcnt, s.off, s.blocksums, npx);
     k_vote_mark<<<(unsigned)((npx + 255) / 256), 256, 0, L.stream>>>(disp_in, s.vote, s.off, s.mark, npx);
     L.count(1);
     exclusive_scan<OpMax>(L, s.mark, s.start, s.blocksums, npx);
-    k_vote_fill<HF><<<wblocks, VOTE_TILE, 0, L.stream>>>(disp_in, arms, s.vote, s.off, s.flat, npx, d.W);
-    const size_t smem = (size_t)VOTE_WARPS * d.Dn * sizeof(int);
-    k_vote_high<HF><<<wblocks, VOTE_TILE, smem, L.stream>>>(
+    k_vote_copy<<<(unsigned)((npx + 255) / 256), 256, 0, L.stream>>>(s.lowcnt, s.off, s.stash, s.flat, npx);
+    k_vote_pass_b<HF><<<wblocks, VOTE_TILE, smem, L.stream>>>(
         disp_in, arms, s.vote, s.off, s.start, s.flat, disp_out, npx, d.W, d.Dn);
     L.count(2);
 }

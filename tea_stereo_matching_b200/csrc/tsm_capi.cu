@@ -43,7 +43,7 @@ struct tsm_ctx {
     Buf dense;  // [H][W][Dn] staging for volume taps / pokes
     bool stage_mode = false;  // tsm_stage_run: keep every tap-able buffer complete
     Buf disp[2], fin, ftmp;
-    Buf v_vote, v_lowcnt, v_off, v_mark, v_start, v_sums, v_flat;
+    Buf v_vote, v_lowcnt, v_off, v_mark, v_start, v_sums, v_flat, v_stash;
     Buf e_gray, e_blur, e_mag, e_gx, e_gy, e_map, e_edges, e_hist, e_lut, e_changed;
     Buf tab_ad, tab_c, agg_ctr;
     Buf k_in, k_out, k_tab, k_range;  // disparity consumers: staged input map, output, colour table, min/max
@@ -209,6 +209,7 @@ int ensure_arena(tsm_ctx* c, const tsm_adcensus_config* cfg, int H, int W)
     if ((rc = ensure(c, c->v_start, npx * 4))) return rc;
     if ((rc = ensure(c, c->v_sums, (npx / 2048 + 2) * 4))) return rc;
     if ((rc = ensure(c, c->v_flat, npx * kVotingThresh * 2))) return rc;
+    if ((rc = ensure(c, c->v_stash, npx * kVotingThresh * 2))) return rc;
     if ((rc = ensure(c, c->e_gray, npx))) return rc;
     if ((rc = ensure(c, c->e_blur, npx))) return rc;
     if ((rc = ensure(c, c->e_mag, npx * 4))) return rc;
@@ -311,6 +312,7 @@ int run_stages(tsm_ctx* c, int mask, int arg)
         vs.start = (int32_t*)c->v_start.p;
         vs.blocksums = (int32_t*)c->v_sums.p;
         vs.flat = (uint16_t*)c->v_flat.p;
+        vs.stash = (uint16_t*)c->v_stash.p;
         vs.flat_capacity = c->v_flat.bytes / 2;
         // multiOptimize: 5 calls, horizontalFirst = F,T,F,T,F (ADCensus.cpp:1382-1387)
         for (int i = 0; i < 5; ++i) {
@@ -444,7 +446,7 @@ void tsm_destroy(tsm_ctx* c)
     cudaStreamSynchronize(c->stream);
     Buf* all[] = {&c->img[0], &c->img[1], &c->img4[0], &c->img4[1], &c->census[0], &c->census[1], &c->arms[0], &c->arms[1],
                   &c->desc_h[0], &c->desc_h[1], &c->desc_v[0], &c->desc_v[1], &c->flags[0], &c->flags[1], &c->tflags[0], &c->tflags[1], &c->vtail[0], &c->vtail[1], &c->dense, &c->vol[0], &c->vol[1], &c->wta_[0], &c->wta_[1],
-                  &c->disp[0], &c->disp[1], &c->fin, &c->ftmp, &c->v_vote, &c->v_lowcnt, &c->v_off, &c->v_mark, &c->v_start,
+                  &c->disp[0], &c->disp[1], &c->fin, &c->ftmp, &c->v_vote, &c->v_lowcnt, &c->v_off, &c->v_mark, &c->v_start, &c->v_stash,
                   &c->v_sums, &c->v_flat, &c->e_gray, &c->e_blur, &c->e_mag, &c->e_gx, &c->e_gy, &c->e_map, &c->e_edges,
                   &c->e_hist, &c->e_lut, &c->e_changed, &c->tab_ad, &c->tab_c, &c->agg_ctr, &c->k_in, &c->k_out, &c->k_tab, &c->k_range, &c->r_src, &c->r_map1[0], &c->r_map1[1],
                   &c->r_map2[0], &c->r_map2[1], &c->r_fmap[0][0], &c->r_fmap[0][1], &c->r_fmap[1][0], &c->r_fmap[1][1]};
