@@ -159,19 +159,23 @@ k_cost_init(Dims dm, ViewPtrs vl, ViewPtrs vr, const float* __restrict__ g_tab_a
             if (lane < r) vl.vol.tail[(row + x0 + j) * Rp + lane] = ctile[j * DnP + Dm + lane];
         }
     }
-    // ---- right view: diagonals of the tile.  Right pixel c gets d in [x0 - c, x0 + npix - 1 - c] (clipped to [0, Dn)).
-    for (int i = warp; i < COST_TX + Dn - 1; i += COST_WARPS) {
-        const int c = cbase + i;
-        if (c < 0 || c >= W) continue;
-        const int d0 = max(0, x0 - c), d1 = min(Dn - 1, x0 + npix - 1 - c);
-        float* dst = vr.vol.main + (row + c) * Dm;
-        float* dst_t = vr.vol.tail + (row + c) * Rp;
-        const float* src = ctile + (c - x0) * DnP;  // + d * (DnP + 1)
-        for (int d = (d0 & ~31) + lane; d <= d1; d += 32) {
-            if (d >= d0) {
-                const float v = src[d * (DnP + 1)];
-                if (d < Dm) dst[d] = v;
-                else dst_t[d - Dm] = v;
+    // ---- right view: diagonals of the tile.  Right pixel c gets d in [x0 - c, x0 + npix - 1 - c] (clipped to [0, Dn)),
+    // a run of at most COST_TX consecutive d: lanes over d from the run's start (the stores are 4-byte aligned
+    // 128-byte pieces either way; starting at d0 instead of a multiple of 32 saves a third of the iterations).
+    {
+        const int stride = DnP + 1;
+        float* const rmain = vr.vol.main + row * Dm;
+        float* const rtail = vr.vol.tail + row * Rp - Dm;  // indexed with d >= Dm
+        for (int i = warp; i < COST_TX + Dn - 1; i += COST_WARPS) {
+            const int c = cbase + i;
+            if ((unsigned)c >= (unsigned)W) continue;
+            const int d0 = max(0, x0 - c), d1 = min(Dn - 1, x0 + npix - 1 - c);
+            const float* src = ctile + (c - x0) * DnP;  // + d * stride
+            float* const pm = rmain + (size_t)c * Dm;
+            float* const pt = rtail + (size_t)c * Rp;
+            for (int d = d0 + lane; d <= d1; d += 32) {
+                float* q = d < Dm ? pm + d : pt + d;
+                *q = src[d * stride];
             }
         }
     }
