@@ -124,6 +124,17 @@ int tsm_rectify_adcensus(tsm_ctx* ctx, const tsm_adcensus_config* cfg,
                          float* disparity, size_t dstep);
 void tsm_invalidate_maps(tsm_ctx* ctx);
 
+/* ---- stereo::EpipolarRectifyMap::compute, source/stereo_utils.cpp:157-169 ----
+ * One cv::initUndistortRectifyMap(cameraMatrix, distCoeffs, R, newCameraMatrix, Size(W, H), CV_16SC2,
+ * map1, map2): map1 = CV_16SC2 (H x W x 2 int16), map2 = CV_16UC1, exactly the pair tsm_remap takes as
+ * TSM_MAP_FIXED_16SC2_16UC1.  camera_matrix, R, new_camera_matrix: 3x3 row-major doubles (R NULL =
+ * identity; new_camera_matrix NULL = camera_matrix with the principal point moved to the image centre, as
+ * cv::getDefaultNewCameraMatrix(K, size, true) does; for a 3x4 projection matrix P pass ld_new = 4).
+ * dist_coeffs: 0, 4, 5, 8, 12 or 14 doubles in OpenCV order (k1 k2 p1 p2 k3 k4 k5 k6 s1 s2 s3 s4 tx ty). */
+int tsm_init_undistort_rectify_map(tsm_ctx* ctx, const double* camera_matrix, const double* dist_coeffs, int n_dist,
+                                   const double* R, const double* new_camera_matrix, int ld_new, int H, int W,
+                                   int16_t* map1, size_t step1, uint16_t* map2, size_t step2);
+
 /* ---- consumers of the disparity map: the free functions of source/stereo.cpp that follow
  * ADCensus::compute.  `disparity` is a host CV_32FC1 map (row stride `step`
  * bytes), or NULL: then the map the last tsm_adcensus_* call of THIS context produced is consumed

@@ -7,10 +7,11 @@ Host-side mirror of the reference's operator interface for this one path
 from ._native import LIB_PATH, NativeLibraryMissing, build_native, lib
 from .adcensus import ADCensus, ADCensusError, ColorModel, Context, StageRunner
 from .consumers import JETColorMap, applyColorMap, reprojectTo3D, reprojectToDepth
-from .rectify import EpipolarRectify, EpipolarRectifyMap
+from .rectify import (CameraIntrinsic, EpipolarRectify, EpipolarRectifyMap, StereoPair, StereoParams,
+                      initUndistortRectifyMap)
 
 __all__ = [
     "ADCensus", "ADCensusError", "ColorModel", "Context", "StageRunner", "EpipolarRectify", "EpipolarRectifyMap",
-    "JETColorMap", "applyColorMap", "reprojectToDepth", "reprojectTo3D",
+    "CameraIntrinsic", "StereoPair", "StereoParams", "initUndistortRectifyMap", "JETColorMap", "applyColorMap", "reprojectToDepth", "reprojectTo3D",
     "build_native", "lib", "LIB_PATH", "NativeLibraryMissing",
 ]

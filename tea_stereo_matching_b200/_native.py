@@ -33,7 +33,7 @@ EXPORTS = [
     "tsm_adcensus_enqueue", "tsm_adcensus_wait", "tsm_remap", "tsm_rectify_stereo", "tsm_rectify_adcensus",
     "tsm_invalidate_maps", "tsm_stage_begin", "tsm_stage_run", "tsm_volume_pitch", "tsm_buffer_bytes", "tsm_tap",
     "tsm_poke", "tsm_set_profiling", "tsm_get_stage_times", "tsm_launch_count", "tsm_selftest",
-    "tsm_reproject_to_depth", "tsm_reproject_to_3d", "tsm_reproject_to_3d_q", "tsm_apply_colormap", "tsm_jet_colormap",
+    "tsm_init_undistort_rectify_map", "tsm_reproject_to_depth", "tsm_reproject_to_3d", "tsm_reproject_to_3d_q", "tsm_apply_colormap", "tsm_jet_colormap",
 ]
 
 
@@ -117,6 +117,8 @@ def lib() -> C.CDLL:
     L.tsm_reproject_to_3d.argtypes = [vp, vp, sz, i32, i32, f32, f32, f32, f32, vp, sz]
     L.tsm_reproject_to_3d_q.argtypes = [vp, vp, sz, i32, i32, C.POINTER(C.c_double), vp, sz]
     L.tsm_apply_colormap.argtypes = [vp, vp, sz, i32, i32, i32, f32, f32, vp, vp, sz]
+    dp = C.POINTER(C.c_double)
+    L.tsm_init_undistort_rectify_map.argtypes = [vp, dp, dp, i32, dp, dp, i32, i32, i32, vp, sz, vp, sz]
     L.tsm_jet_colormap.argtypes = [vp]
     L.tsm_jet_colormap.restype = None
     _lib = L

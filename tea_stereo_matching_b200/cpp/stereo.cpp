@@ -5,6 +5,11 @@
 // but loadEpipolarRectifyMap throws std::runtime_error on empty maps (:35-40).
 #include "stereo.h"
 #include "../../include/tsm.h"
+#include <algorithm>
+#include <fstream>
+#include <map>
+#include <sstream>
+#include <iterator>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -363,4 +368,154 @@ void stereo::reprojectTo3D(const cv::Mat& disparity, const cv::Mat& Q, cv::Mat& 
 	consumer_check(c, tsm_reproject_to_3d_q(c, (const float*)disparity.data, disparity.step, disparity.rows, disparity.cols, q,
 		(float*)out.data, out.step));
 	XYZPoints = out;
+}
+
+// ---- rectify-map generation and calibration files ---------------------------
+namespace {
+// The subset of OpenCV FileStorage YAML the reference reads: "key: !!opencv-matrix" blocks and "key: [ a, b ]".
+struct YamlDoc {
+	std::map<std::string, cv::Mat> mats;
+	std::map<std::string, std::vector<double>> seqs;
+};
+
+bool parse_opencv_yaml(const std::string& path, YamlDoc& doc)
+{
+	std::ifstream f(path);
+	if (!f) return false;
+	std::string text((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+	size_t pos = 0;
+	auto number_list = [&](size_t open) {  // parses "[ a, b, ... ]" starting at text[open] == '['
+		std::vector<double> v;
+		size_t close = text.find(']', open);
+		std::string body = text.substr(open + 1, close == std::string::npos ? std::string::npos : close - open - 1);
+		for (char& ch : body) if (ch == ',' or ch == '\n' or ch == '\r') ch = ' ';
+		std::istringstream is(body);
+		double x;
+		while (is >> x) v.push_back(x);
+		pos = close == std::string::npos ? text.size() : close + 1;
+		return v;
+	};
+	while (pos < text.size()) {
+		size_t eol = text.find('\n', pos);
+		if (eol == std::string::npos) eol = text.size();
+		std::string line = text.substr(pos, eol - pos);
+		size_t colon = line.find(':');
+		if (line.empty() or line[0] == ' ' or line[0] == '%' or line[0] == '-' or colon == std::string::npos) { pos = eol + 1; continue; }
+		const std::string key = line.substr(0, colon);
+		if (line.find("!!opencv-matrix") != std::string::npos) {
+			int rows = 0, cols = 0;
+			std::string dt = "d";
+			size_t p = eol + 1;
+			for (int k = 0; k < 3; ++k) {  // rows / cols / dt lines
+				size_t e = text.find('\n', p);
+				std::string l = text.substr(p, e - p);
+				if (l.find("rows:") != std::string::npos) rows = std::atoi(l.c_str() + l.find(':') + 1);
+				else if (l.find("cols:") != std::string::npos) cols = std::atoi(l.c_str() + l.find(':') + 1);
+				else if (l.find("dt:") != std::string::npos) { dt = l.substr(l.find(':') + 1); dt.erase(std::remove_if(dt.begin(), dt.end(), [](char c) { return c == ' ' or c == '"' or c == '\r'; }), dt.end()); }
+				p = e + 1;
+			}
+			size_t open = text.find('[', p);
+			if (open == std::string::npos) return false;
+			std::vector<double> v = number_list(open);
+			const char kind = dt.empty() ? 'd' : dt.back();
+			const int ch = dt.size() > 1 ? std::atoi(dt.c_str()) : 1;
+			int type = kind == 'd' ? CV_64FC1 : kind == 'f' ? CV_32FC1 : kind == 's' and ch == 2 ? CV_16SC2 : kind == 'w' ? CV_16UC1 : -1;
+			if (type < 0 or (size_t)rows * cols * ch != v.size()) return false;
+			cv::Mat m(rows, cols, type);
+			for (size_t i = 0; i < v.size(); ++i) {
+				if (type == CV_64FC1) ((double*)m.data)[i] = v[i];
+				else if (type == CV_32FC1) ((float*)m.data)[i] = (float)v[i];
+				else if (type == CV_16SC2) ((int16_t*)m.data)[i] = (int16_t)v[i];
+				else ((uint16_t*)m.data)[i] = (uint16_t)v[i];
+			}
+			doc.mats[key] = m;
+		} else if (line.find('[', colon) != std::string::npos) {
+			doc.seqs[key] = number_list(pos + line.find('[', colon));
+		} else {
+			pos = eol + 1;
+		}
+	}
+	return true;
+}
+
+cv::Mat yaml_mat(const YamlDoc& d, const char* key)
+{
+	auto it = d.mats.find(key);
+	return it == d.mats.end() ? cv::Mat() : it->second;
+}
+
+void to_doubles(const cv::Mat& m, std::vector<double>& out)
+{
+	out.clear();
+	for (int r = 0; r < m.rows; ++r)
+		for (int c = 0; c < m.cols; ++c)
+			out.push_back(m.type() == CV_64FC1 ? ((const double*)(m.data + (size_t)r * m.step))[c] : (double)((const float*)(m.data + (size_t)r * m.step))[c]);
+}
+
+void undistort_rectify_map(const cv::Mat& K, const cv::Mat& D, const cv::Mat& R, const cv::Mat& P, const cv::Size& sz, cv::Mat& m1, cv::Mat& m2)
+{
+	std::vector<double> k, d, r, p;
+	to_doubles(K, k);
+	to_doubles(D, d);
+	to_doubles(R, r);
+	to_doubles(P, p);
+	if (k.size() != 9 or (!r.empty() and r.size() != 9) or (!p.empty() and p.size() != 9 and p.size() != 12))
+		throw std::runtime_error("EpipolarRectifyMap::compute: K and R must be 3x3, P 3x3 or 3x4");
+	cv::Mat a(sz.height, sz.width, CV_16SC2), b(sz.height, sz.width, CV_16UC1);
+	tsm_ctx* c = consumer_ctx();
+	consumer_check(c, tsm_init_undistort_rectify_map(c, k.data(), d.empty() ? nullptr : d.data(), (int)d.size(), r.empty() ? nullptr : r.data(),
+		p.empty() ? nullptr : p.data(), p.empty() ? 0 : (int)p.size() / 3, sz.height, sz.width, (int16_t*)a.data, a.step, (uint16_t*)b.data, b.step));
+	m1 = a;
+	m2 = b;
+}
+}
+
+void stereo::EpipolarRectifyMap::compute(const StereoPair<CameraIntrinsic>& intrinsic, const cv::Size& imgsz)
+{
+	if (intrinsic.left.empty() or intrinsic.right.empty()) return;  // stereo_utils.cpp:159-160
+	undistort_rectify_map(intrinsic.left.intrinsic_matrix, intrinsic.left.distortion_coefficients, R1, P1, imgsz, map00, map01);
+	undistort_rectify_map(intrinsic.right.intrinsic_matrix, intrinsic.right.distortion_coefficients, R2, P2, imgsz, map10, map11);
+}
+
+void stereo::EpipolarRectifyMap::loadRectifyMapsYMLFile(const std::string& ymlFilePath)
+{
+	YamlDoc doc;
+	if (!parse_opencv_yaml(ymlFilePath, doc)) throw std::runtime_error("Cannot open rectify maps yml file.");  // :138-145
+	map00 = yaml_mat(doc, "map00");
+	map01 = yaml_mat(doc, "map01");
+	map10 = yaml_mat(doc, "map10");
+	map11 = yaml_mat(doc, "map11");
+	if (empty()) std::fprintf(stderr, "[ERROR] Cannot load rectify maps from yml file.\n");
+}
+
+void stereo::StereoParams::loadYAMLFile(const std::string& ymlFilePath)
+{
+	if (ymlFilePath.empty()) throw std::invalid_argument("Stereo YAML file path is empty.");  // :187-192
+	YamlDoc doc;
+	if (!parse_opencv_yaml(ymlFilePath, doc)) throw std::runtime_error("Cannot open stereo yml file.");  // :197-203
+	intrinsic.left = CameraIntrinsic(yaml_mat(doc, "leftK"), yaml_mat(doc, "leftD"));
+	intrinsic.right = CameraIntrinsic(yaml_mat(doc, "rightK"), yaml_mat(doc, "rightD"));
+	extrinsic.E = yaml_mat(doc, "E");
+	extrinsic.F = yaml_mat(doc, "F");
+	extrinsic.R = yaml_mat(doc, "R");
+	extrinsic.T = yaml_mat(doc, "T");
+	map.R1 = yaml_mat(doc, "R1");
+	map.R2 = yaml_mat(doc, "R2");
+	map.P1 = yaml_mat(doc, "P1");
+	map.P2 = yaml_mat(doc, "P2");
+	Q = yaml_mat(doc, "Q");
+	auto sz = doc.seqs.find("imgsz");
+	if (sz != doc.seqs.end() and sz->second.size() == 2) imgsz = cv::Size((int)sz->second[0], (int)sz->second[1]);
+	if (Q.empty()) return;
+	auto q = [&](int r, int c) { return ((const double*)(Q.data + (size_t)r * Q.step))[c]; };
+	rectified_f = static_cast<float>(q(2, 3));   // :222-225
+	rectified_cx = static_cast<float>(-q(0, 3));
+	rectified_cy = static_cast<float>(-q(1, 3));
+	baseline = 1.f / static_cast<float>(q(3, 2));
+	map.compute(intrinsic, imgsz);
+}
+
+bool stereo::StereoParams::empty() const
+{
+	return intrinsic.left.empty() or intrinsic.right.empty() or extrinsic.empty() or map.empty() or Q.empty();
 }

@@ -52,12 +52,44 @@ public:
 	int maxSearchDepth, blurKernelSize, cannyThresh1, cannyThresh2, cannyKernelSize;
 };
 
+// include/stereo_utils.h:16-80 of the reference
+template <typename T>
+struct StereoPair
+{
+	T left, right;
+	StereoPair() : left(), right() {}
+	StereoPair(const T& left, const T& right) : left(left), right(right) {}
+	void swap() { using std::swap; swap(left, right); }
+};
+
+class CameraIntrinsic
+{
+public:
+	cv::Mat intrinsic_matrix;        // 3x3 CV_64FC1
+	cv::Mat distortion_coefficients; // 1xN / Nx1 CV_64FC1, N = 4, 5, 8, 12 or 14
+	CameraIntrinsic() = default;
+	CameraIntrinsic(const cv::Mat& intrinsic_matrix, const cv::Mat& distortion_coefficients)
+		: intrinsic_matrix(intrinsic_matrix), distortion_coefficients(distortion_coefficients) {}
+	bool empty() const { return intrinsic_matrix.empty(); }
+};
+
+class StereoExtrinsic
+{
+public:
+	cv::Mat E, F, R, T;
+	bool empty() const { return R.empty() or T.empty(); }
+};
+
 class EpipolarRectifyMap
 {
 public:
 	cv::Mat R1, R2, P1, P2;
 	cv::Mat map00, map01, map10, map11;
 	EpipolarRectifyMap() = default;
+	// stereo_utils.cpp:157-169: the four CV_16SC2 / CV_16UC1 maps, computed on the device (row f2)
+	void compute(const StereoPair<CameraIntrinsic>& intrinsic, const cv::Size& imgsz);
+	// stereo_utils.cpp:134-155: map00 / map01 / map10 / map11 from an OpenCV FileStorage YAML file
+	void loadRectifyMapsYMLFile(const std::string& ymlFilePath);
 	EpipolarRectifyMap(const cv::Mat& R1, const cv::Mat& R2, const cv::Mat& P1, const cv::Mat& P2,
 		const cv::Mat& map00, const cv::Mat& map01, const cv::Mat& map10, const cv::Mat& map11);
 	bool empty() const;
@@ -105,6 +137,22 @@ public:
 private:
 	class ADCensusImpl;
 	std::unique_ptr<ADCensusImpl> impl;
+};
+
+// include/stereo_utils.h:151-190, source/stereo_utils.cpp:176-238
+class StereoParams
+{
+public:
+	StereoPair<CameraIntrinsic> intrinsic;
+	StereoExtrinsic extrinsic;
+	EpipolarRectifyMap map;
+	cv::Mat Q;
+	float rectified_f = 0.f, rectified_cx = 0.f, rectified_cy = 0.f, baseline = 0.f;
+	cv::Size imgsz;
+	StereoParams() = default;
+	StereoParams(const std::string& ymlFilePath) { loadYAMLFile(ymlFilePath); }
+	void loadYAMLFile(const std::string& ymlFilePath);
+	bool empty() const;
 };
 
 // ---- consumers of the disparity map: same free functions as the reference (include/stereo.h:194-235,

@@ -114,4 +114,66 @@ void convert_maps(const Launcher& L, const float* mx, const float* my, int H, in
     L.count(1);
 }
 
+// ---- rectify-map generation ------------------------------------------------------
+// cv::initUndistortRectifyMap(K, D, R, P, size, CV_16SC2, map1, map2) as called by
+// EpipolarRectifyMap::compute (source/stereo_utils.cpp:157-169): for every destination pixel (j, i)
+//   [x y w]^T = (P_3x3 R)^-1 [j i 1]^T, x /= w, y /= w, r2 = x^2 + y^2,
+//   kr = (1 + ((k3 r2 + k2) r2 + k1) r2) / (1 + ((k6 r2 + k5) r2 + k4) r2),
+//   xd = x kr + p1 2xy + p2 (r2 + 2x^2) + s1 r2 + s2 r2^2,  yd likewise, tilt, u = fx xd + cx, v = fy yd + cy,
+// then the fixed-point split of cv::convertMaps: iu = round(32 u), map1 = (iu >> 5, iv >> 5),
+// map2 = (iv & 31) * 32 + (iu & 31).  All in fp64 like OpenCV; OpenCV's scalar loop accumulates
+// x += ir[0] per column and its AVX2 path uses FMAs, so the last bits of u differ between OpenCV's own
+// code paths -- only a value within ~1e-11 of a rounding tie of 32 u could differ after quantisation.
+struct UndistortParams {
+    double ir[9];      // (P_3x3 * R)^-1
+    double k[14];      // k1 k2 p1 p2 k3 k4 k5 k6 s1 s2 s3 s4 tauX tauY
+    double tilt[9];    // tilt projection matrix (identity when tauX = tauY = 0)
+    double fx, fy, u0, v0;
+};
+
+__global__ void k_init_undistort_rectify_map(UndistortParams q, int H, int W, short2* __restrict__ map1, uint16_t* __restrict__ map2)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
+    if (j >= W) return;
+    const double _x = (double)i * q.ir[1] + q.ir[2] + (double)j * q.ir[0];
+    const double _y = (double)i * q.ir[4] + q.ir[5] + (double)j * q.ir[3];
+    const double _w = (double)i * q.ir[7] + q.ir[8] + (double)j * q.ir[6];
+    const double w = 1. / _w, x = _x * w, y = _y * w;
+    const double x2 = x * x, y2 = y * y;
+    const double r2 = x2 + y2, _2xy = 2 * x * y;
+    const double k1 = q.k[0], k2 = q.k[1], p1 = q.k[2], p2 = q.k[3], k3 = q.k[4], k4 = q.k[5], k5 = q.k[6], k6 = q.k[7];
+    const double s1 = q.k[8], s2 = q.k[9], s3 = q.k[10], s4 = q.k[11];
+    const double kr = (1 + ((k3 * r2 + k2) * r2 + k1) * r2) / (1 + ((k6 * r2 + k5) * r2 + k4) * r2);
+    const double xd = (x * kr + p1 * _2xy + p2 * (r2 + 2 * x2) + s1 * r2 + s2 * r2 * r2);
+    const double yd = (y * kr + p1 * (r2 + 2 * y2) + p2 * _2xy + s3 * r2 + s4 * r2 * r2);
+    const double tx = q.tilt[0] * xd + q.tilt[1] * yd + q.tilt[2];
+    const double ty = q.tilt[3] * xd + q.tilt[4] * yd + q.tilt[5];
+    const double tz = q.tilt[6] * xd + q.tilt[7] * yd + q.tilt[8];
+    const double inv = tz ? 1. / tz : 1;
+    const double u = q.fx * inv * tx + q.u0;
+    const double v = q.fy * inv * ty + q.v0;
+    // saturate_cast<int>(double) = cvRound = round half to even, saturating
+    auto sat_round = [](double t) {
+        if (!(t > -2147483648.0)) return t != t ? (int)0x80000000 : (int)0x80000000;
+        if (t >= 2147483647.0) return 2147483647;
+        return __double2int_rn(t);
+    };
+    const int iu = sat_round(u * 32.0), iv = sat_round(v * 32.0);
+    const size_t o = (size_t)i * W + j;
+    map1[o] = make_short2((short)(iu >> 5), (short)(iv >> 5));
+    map2[o] = (uint16_t)((iv & 31) * 32 + (iu & 31));
+}
+
+void init_undistort_rectify_map(const Launcher& L, const double* ir, const double* k14, const double* tilt, double fx, double fy,
+                                double u0, double v0, int H, int W, int16_t* map1, uint16_t* map2)
+{
+    UndistortParams q;
+    for (int a = 0; a < 9; ++a) { q.ir[a] = ir[a]; q.tilt[a] = tilt[a]; }
+    for (int a = 0; a < 14; ++a) q.k[a] = k14[a];
+    q.fx = fx; q.fy = fy; q.u0 = u0; q.v0 = v0;
+    dim3 g((W + 127) / 128, H);
+    k_init_undistort_rectify_map<<<g, 128, 0, L.stream>>>(q, H, W, reinterpret_cast<short2*>(map1), map2);
+    L.count(1);
+}
+
 }  // namespace tsm

@@ -2,6 +2,7 @@
 // orchestration.  Mirrors the call sequence of stereo::ADCensus::compute
 // (reference source/ADCensus.cpp:330-407) and multiOptimize (:1376-1392).
 #include "tsm_common.cuh"
+#include <algorithm>
 #include <limits.h>
 #include <math.h>
 #include <stdarg.h>
@@ -756,6 +757,97 @@ int tsm_poke(tsm_ctx* c, int buffer, const void* src, size_t bytes)
         return TSM_OK;
     }
     CK(c, cudaMemcpyAsync(b->p, src, need, cudaMemcpyHostToDevice, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    return TSM_OK;
+}
+
+// ---- rectify-map generation ----------------------------------------------------------------------
+static bool invert3x3(const double* m, double* inv)
+{
+    // LU with partial pivoting on [m | I] (cv::invert DECOMP_LU)
+    double a[3][6];
+    for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) { a[r][c] = m[3 * r + c]; a[r][3 + c] = r == c ? 1.0 : 0.0; }
+    for (int col = 0; col < 3; ++col) {
+        int piv = col;
+        for (int r = col + 1; r < 3; ++r)
+            if (fabs(a[r][col]) > fabs(a[piv][col])) piv = r;
+        if (fabs(a[piv][col]) < 1e-300) return false;
+        if (piv != col)
+            for (int c = 0; c < 6; ++c) std::swap(a[piv][c], a[col][c]);
+        const double d = 1.0 / a[col][col];
+        for (int r = col + 1; r < 3; ++r) {
+            const double f = a[r][col] * d;
+            for (int c = col; c < 6; ++c) a[r][c] -= f * a[col][c];
+        }
+    }
+    for (int c = 3; c < 6; ++c)
+        for (int r = 2; r >= 0; --r) {
+            double s = a[r][c];
+            for (int k = r + 1; k < 3; ++k) s -= a[r][k] * a[k][c];
+            a[r][c] = s / a[r][r];
+        }
+    for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) inv[3 * r + c] = a[r][3 + c];
+    return true;
+}
+
+int tsm_init_undistort_rectify_map(tsm_ctx* c, const double* K, const double* dist, int n_dist, const double* R,
+                                   const double* newK, int ld_new, int H, int W, int16_t* map1, size_t step1, uint16_t* map2,
+                                   size_t step2)
+{
+    if (!c) return TSM_E_ARG;
+    if (!K || H <= 0 || W <= 0 || !map1 || !map2 || step1 < (size_t)W * 4 || step2 < (size_t)W * 2)
+        return fail(c, TSM_E_ARG, "tsm_init_undistort_rectify_map: bad argument");
+    if (!(n_dist == 0 || n_dist == 4 || n_dist == 5 || n_dist == 8 || n_dist == 12 || n_dist == 14) || (n_dist && !dist))
+        return fail(c, TSM_E_ARG, "tsm_init_undistort_rectify_map: distortion coefficients must be 0, 4, 5, 8, 12 or 14 values");
+    if (newK && ld_new != 3 && ld_new != 4) return fail(c, TSM_E_ARG, "tsm_init_undistort_rectify_map: ld_new must be 3 or 4");
+    CK(c, cudaSetDevice(c->device));
+    double Ar[9], Rm[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, ArR[9], ir[9], k[14] = {0}, tilt[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    for (int r = 0; r < 3; ++r)
+        for (int q = 0; q < 3; ++q) Ar[3 * r + q] = newK ? newK[ld_new * r + q] : K[3 * r + q];
+    if (!newK) {  // cv::getDefaultNewCameraMatrix(K, size, centerPrincipalPoint = true)
+        Ar[2] = (W - 1) * 0.5;
+        Ar[5] = (H - 1) * 0.5;
+    }
+    if (R) memcpy(Rm, R, sizeof Rm);
+    for (int r = 0; r < 3; ++r)
+        for (int q = 0; q < 3; ++q) {
+            double s = 0;
+            for (int t = 0; t < 3; ++t) s += Ar[3 * r + t] * Rm[3 * t + q];
+            ArR[3 * r + q] = s;
+        }
+    if (!invert3x3(ArR, ir)) return fail(c, TSM_E_ARG, "tsm_init_undistort_rectify_map: new camera matrix * R is singular");
+    for (int i = 0; i < n_dist; ++i) k[i] = dist[i];
+    if (k[12] != 0 || k[13] != 0) {
+        // computeTiltProjectionMatrix(tauX, tauY): matTilt = projZ(Ry Rx) * Ry Rx
+        const double cx_ = cos(k[12]), sx_ = sin(k[12]), cy_ = cos(k[13]), sy_ = sin(k[13]);
+        const double rx[9] = {1, 0, 0, 0, cx_, sx_, 0, -sx_, cx_}, ry[9] = {cy_, 0, -sy_, 0, 1, 0, sy_, 0, cy_};
+        double rxy[9];
+        for (int r = 0; r < 3; ++r)
+            for (int q = 0; q < 3; ++q) {
+                double s = 0;
+                for (int t = 0; t < 3; ++t) s += ry[3 * r + t] * rx[3 * t + q];
+                rxy[3 * r + q] = s;
+            }
+        const double pz[9] = {rxy[8], 0, -rxy[2], 0, rxy[8], -rxy[5], 0, 0, 1};
+        for (int r = 0; r < 3; ++r)
+            for (int q = 0; q < 3; ++q) {
+                double s = 0;
+                for (int t = 0; t < 3; ++t) s += pz[3 * r + t] * rxy[3 * t + q];
+                tilt[3 * r + q] = s;
+            }
+    }
+    int rc;
+    const size_t n = (size_t)H * W;
+    if ((rc = ensure(c, c->k_out, n * 12))) return rc;
+    int16_t* d1 = (int16_t*)c->k_out.p;
+    uint16_t* d2 = (uint16_t*)(d1 + 2 * n);
+    Launcher L{c->stream, &c->launches};
+    init_undistort_rectify_map(L, ir, k, tilt, K[0], K[4], K[2], K[5], H, W, d1, d2);
+    CK(c, cudaGetLastError());
+    CK(c, cudaMemcpy2DAsync(map1, step1, d1, (size_t)W * 4, (size_t)W * 4, H, cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaMemcpy2DAsync(map2, step2, d2, (size_t)W * 2, (size_t)W * 2, H, cudaMemcpyDeviceToHost, c->stream));
     CK(c, cudaStreamSynchronize(c->stream));
     return TSM_OK;
 }

@@ -19,8 +19,45 @@ from .adcensus import ADCensusError, Context, _as_bgr, _ptr
 
 
 @dataclass
+class CameraIntrinsic:
+    """stereo::CameraIntrinsic (include/stereo_utils.h): 3x3 K and the OpenCV distortion vector."""
+
+    intrinsic_matrix: np.ndarray | None = None
+    distortion_coefficients: np.ndarray | None = None
+
+    def empty(self) -> bool:
+        return self.intrinsic_matrix is None or np.asarray(self.intrinsic_matrix).size == 0
+
+
+@dataclass
+class StereoPair:
+    left: CameraIntrinsic | None = None
+    right: CameraIntrinsic | None = None
+
+
+def initUndistortRectifyMap(cameraMatrix, distCoeffs, R, newCameraMatrix, size: tuple[int, int], context: Context | None = None):
+    """cv::initUndistortRectifyMap(cameraMatrix, distCoeffs, R, newCameraMatrix, size, CV_16SC2, map1, map2) on the
+    device (csrc/k_rectify.cu); size = (width, height).  Returns (map1 CV_16SC2, map2 CV_16UC1)."""
+    ctx = context or Context(0)
+    W, H = int(size[0]), int(size[1])
+    dbl = C.POINTER(C.c_double)
+    K = np.ascontiguousarray(cameraMatrix, np.float64).reshape(3, 3)
+    D = np.zeros(0) if distCoeffs is None else np.ascontiguousarray(distCoeffs, np.float64).reshape(-1)
+    Rm = None if R is None or np.asarray(R).size == 0 else np.ascontiguousarray(R, np.float64).reshape(3, 3)
+    P = None if newCameraMatrix is None or np.asarray(newCameraMatrix).size == 0 else np.ascontiguousarray(newCameraMatrix, np.float64)
+    if P is not None and P.shape not in ((3, 3), (3, 4)):
+        raise ADCensusError("[EpipolarRectify] newCameraMatrix must be 3x3 or 3x4")
+    map1, map2 = np.empty((H, W, 2), np.int16), np.empty((H, W), np.uint16)
+    ctx.check(ctx._lib.tsm_init_undistort_rectify_map(
+        ctx.handle, K.ctypes.data_as(dbl), D.ctypes.data_as(dbl) if D.size else None, int(D.size),
+        Rm.ctypes.data_as(dbl) if Rm is not None else None, P.ctypes.data_as(dbl) if P is not None else None,
+        0 if P is None else P.shape[1], H, W, _ptr(map1), map1.strides[0], _ptr(map2), map2.strides[0]))
+    return map1, map2
+
+
+@dataclass
 class EpipolarRectifyMap:
-    """R1,R2,P1,P2 are carried for API parity; only the four maps are used on this path."""
+    """stereo::EpipolarRectifyMap (include/stereo_utils.h:109-148, source/stereo_utils.cpp:134-174)."""
 
     R1: np.ndarray | None = None
     R2: np.ndarray | None = None
@@ -33,6 +70,17 @@ class EpipolarRectifyMap:
 
     def empty(self) -> bool:  # stereo_utils.cpp:171-174
         return any(m is None or np.asarray(m).size == 0 for m in (self.map00, self.map01, self.map10, self.map11))
+
+    def compute(self, intrinsic: StereoPair, imgsz: tuple[int, int], context: Context | None = None) -> None:
+        """EpipolarRectifyMap::compute (stereo_utils.cpp:157-169): the four CV_16SC2 / CV_16UC1 maps from
+        K, D of both cameras and this object's R1, R2, P1, P2; a no-op when an intrinsic is empty."""
+        if intrinsic.left is None or intrinsic.right is None or intrinsic.left.empty() or intrinsic.right.empty():
+            return
+        ctx = context or Context(0)
+        self.map00, self.map01 = initUndistortRectifyMap(intrinsic.left.intrinsic_matrix, intrinsic.left.distortion_coefficients,
+                                                         self.R1, self.P1, imgsz, ctx)
+        self.map10, self.map11 = initUndistortRectifyMap(intrinsic.right.intrinsic_matrix, intrinsic.right.distortion_coefficients,
+                                                         self.R2, self.P2, imgsz, ctx)
 
 
 def _log_error(msg: str) -> None:
@@ -135,3 +183,65 @@ class EpipolarRectify:
         ctx.check(ctx._lib.tsm_remap(ctx.handle, _ptr(src), src.strides[0], src.shape[0], src.shape[1], _ptr(m1), _ptr(m2),
                                       self._kind, H, W, _ptr(dst), dst.strides[0]))
         return dst
+
+
+# ---- stereo::StereoParams (include/stereo_utils.h, source/stereo_utils.cpp:176-232) --------------------
+def _read_opencv_yaml(path: str) -> dict:
+    """Reads the subset of OpenCV FileStorage YAML the reference writes: `key: !!opencv-matrix` blocks
+    (rows, cols, dt, data) and flow sequences `key: [ a, b ]`."""
+    import re
+
+    with open(path, "r") as f:
+        text = f.read()
+    out: dict = {}
+    for m in re.finditer(r"^(\w+):\s*!!opencv-matrix\s*\n\s*rows:\s*(\d+)\s*\n\s*cols:\s*(\d+)\s*\n\s*dt:\s*\"?(\w+)\"?\s*\n\s*data:\s*\[(.*?)\]",
+                         text, re.S | re.M):
+        key, rows, cols, dt, data = m.group(1), int(m.group(2)), int(m.group(3)), m.group(4), m.group(5)
+        vals = [float(v) for v in data.replace("\n", " ").split(",") if v.strip()]
+        np_dt = {"d": np.float64, "f": np.float32, "i": np.int32, "s": np.int16, "w": np.uint16, "u": np.uint8}[dt[-1]]
+        ch = int(dt[:-1]) if len(dt) > 1 else 1
+        a = np.array(vals, np_dt)
+        out[key] = a.reshape(rows, cols, ch) if ch > 1 else a.reshape(rows, cols)
+    for m in re.finditer(r"^(\w+):\s*\[([^\]]*)\]\s*$", text, re.M):
+        out.setdefault(m.group(1), [float(v) for v in m.group(2).split(",") if v.strip()])
+    return out
+
+
+class StereoParams:
+    """Loads a stereo calibration YAML like the reference and computes the rectify maps on the device."""
+
+    def __init__(self, ymlFilePath: str | None = None, context: Context | None = None):
+        self.intrinsic = StereoPair(CameraIntrinsic(), CameraIntrinsic())
+        self.E = self.F = self.R = self.T = self.Q = None
+        self.map = EpipolarRectifyMap()
+        self.rectified_f = self.rectified_cx = self.rectified_cy = self.baseline = 0.0
+        self.imgsz = (0, 0)
+        self._ctx = context
+        if ymlFilePath is not None:
+            self.loadYAMLFile(ymlFilePath)
+
+    def loadYAMLFile(self, ymlFilePath: str) -> None:
+        if not ymlFilePath:
+            raise ValueError("Stereo YAML file path is empty.")  # std::invalid_argument, stereo_utils.cpp:187-192
+        try:
+            y = _read_opencv_yaml(ymlFilePath)
+        except OSError:
+            raise RuntimeError("Cannot open stereo yml file.") from None  # :197-203
+        self.intrinsic = StereoPair(CameraIntrinsic(y.get("leftK"), y.get("leftD")), CameraIntrinsic(y.get("rightK"), y.get("rightD")))
+        self.E, self.F, self.R, self.T, self.Q = (y.get(k) for k in ("E", "F", "R", "T", "Q"))
+        self.map.R1, self.map.R2, self.map.P1, self.map.P2 = (y.get(k) for k in ("R1", "R2", "P1", "P2"))
+        if "imgsz" in y:
+            sz = np.asarray(y["imgsz"]).reshape(-1)
+            self.imgsz = (int(sz[0]), int(sz[1]))
+        if self.Q is None:
+            return
+        Q = np.asarray(self.Q, np.float64)
+        self.rectified_f = float(np.float32(Q[2, 3]))      # :222-225
+        self.rectified_cx = float(np.float32(-Q[0, 3]))
+        self.rectified_cy = float(np.float32(-Q[1, 3]))
+        self.baseline = float(np.float32(1.0) / np.float32(Q[3, 2]))
+        self.map.compute(self.intrinsic, self.imgsz, self._ctx)
+
+    def empty(self) -> bool:  # :234-238
+        return (self.intrinsic.left.empty() or self.intrinsic.right.empty() or self.R is None or self.T is None
+                or self.map.empty() or self.Q is None)

@@ -4,6 +4,7 @@
 //   api                     -- error behaviour only (no GPU needed)
 //   run in.bin out.bin      -- in.bin = int32 H, W, D + left BGR + right BGR; out.bin = float32 H*W
 //   batch in.bin out.bin n  -- the batched overload on n copies of the pair
+//   params calib.yml out.bin -- stereo::StereoParams(calib.yml): out.bin = map00, map01, map10, map11, then f, cx, cy, B
 //   consume in.bin out.bin  -- disparity, then the README demo's consumers (README.md demo 5): out.bin = disparity,
 //                              reprojectToDepth (f=700,B=0.1), reprojectTo3D(f,B,cx,cy), reprojectTo3D(Q), applyColorMap(JET)
 #include "../../tea_stereo_matching_b200/cpp/stereo.h"
@@ -46,6 +47,21 @@ static int api_checks()
 int main(int argc, char** argv)
 {
     if (argc >= 2 && !std::strcmp(argv[1], "api")) return api_checks();
+    if (argc >= 4 && !std::strcmp(argv[1], "params")) {
+        try {
+            stereo::StereoParams sp(argv[2]);
+            if (sp.empty()) { std::fprintf(stderr, "StereoParams is empty\n"); return 5; }
+            std::ofstream o(argv[3], std::ios::binary);
+            const int H = sp.imgsz.height, W = sp.imgsz.width;
+            o.write((const char*)sp.map.map00.data, (std::streamsize)H * W * 4);
+            o.write((const char*)sp.map.map01.data, (std::streamsize)H * W * 2);
+            o.write((const char*)sp.map.map10.data, (std::streamsize)H * W * 4);
+            o.write((const char*)sp.map.map11.data, (std::streamsize)H * W * 2);
+            const float tail[4] = {sp.rectified_f, sp.rectified_cx, sp.rectified_cy, sp.baseline};
+            o.write((const char*)tail, sizeof tail);
+        } catch (const std::exception& e) { std::fprintf(stderr, "exception: %s\n", e.what()); return 4; }
+        return 0;
+    }
     if (argc < 4) { std::fprintf(stderr, "usage: %s api | run in out | batch in out n\n", argv[0]); return 2; }
     std::ifstream f(argv[2], std::ios::binary);
     int32_t hdr[3];

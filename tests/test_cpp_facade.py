@@ -83,3 +83,25 @@ def test_facade_consumers_match_oracle(demo, pair_0600, tmp_path):
     assert eq(xyz, co.reproject_to_3d(disp, 700.0, 0.1, W / 2.0, H / 2.0))
     assert eq(xyzq, co.reproject_to_3d_q(disp, Q))
     assert np.array_equal(color, co.apply_colormap(disp, co.jet_colormap()))
+
+
+@pytest.mark.gpu
+def test_facade_stereo_params_yaml_to_maps(demo, tmp_path):
+    gold = ROOT / "tests" / "golden"
+    out = tmp_path / "maps.bin"
+    r = subprocess.run([str(demo), "params", str(gold / "stereo_calib.yml"), str(out)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    want = np.load(gold / "stereo_calib_maps.npz")
+    H, W = want["map01"].shape
+    raw = np.fromfile(out, np.uint8)
+    n = H * W
+    o = 0
+    for k, nb, dt, shape in (("map00", 4, np.int16, (H, W, 2)), ("map01", 2, np.uint16, (H, W)), ("map10", 4, np.int16, (H, W, 2)),
+                             ("map11", 2, np.uint16, (H, W))):
+        got = raw[o : o + n * nb].view(dt).reshape(shape)
+        assert np.array_equal(got, want[k]), k
+        o += n * nb
+    f, cx, cy, B = raw[o : o + 16].view(np.float32)
+    Q = want["Q"]
+    assert f == np.float32(Q[2, 3]) and cx == np.float32(-Q[0, 3]) and cy == np.float32(-Q[1, 3])
+    assert B == np.float32(1.0) / np.float32(Q[3, 2])
