@@ -33,7 +33,7 @@ enum tsm_status {
     TSM_E_ARG = 1,         /* bad argument (NULL, size mismatch, empty image, min>=max, ...) */
     TSM_E_CUDA = 2,        /* CUDA runtime / launch failure, or no device */
     TSM_E_OOM = 3,         /* device or pinned-host allocation failed */
-    TSM_E_UNSUPPORTED = 4, /* valid in the reference but not built yet (HSI, roi/mask, minD != 0) */
+    TSM_E_UNSUPPORTED = 4, /* valid in the reference but not built yet (roi/mask matching, minD != 0) */
     TSM_E_STATE = 5        /* call sequence error (wait without enqueue, tap before run, ...) */
 };
 
@@ -49,7 +49,7 @@ enum tsm_color_model { TSM_COLOR_RGB = 0, TSM_COLOR_HSI = 1 };
 typedef struct tsm_adcensus_config {
     int32_t min_disparity; /* only 0 is built; others -> TSM_E_UNSUPPORTED */
     int32_t max_disparity; /* Dn = max - min + 1 cost planes (ADCensus.cpp:345) */
-    int32_t color_model;   /* tsm_color_model; HSI -> TSM_E_UNSUPPORTED */
+    int32_t color_model;   /* tsm_color_model (the reference default-constructs HSI, ADCensus.cpp:409-420) */
     int32_t roi_matching;  /* != 0 -> TSM_E_UNSUPPORTED */
     int32_t mask_matching; /* != 0 -> TSM_E_UNSUPPORTED */
     int32_t offset;        /* only used by roi/mask modes */
@@ -188,7 +188,10 @@ enum tsm_buffer {
     TSM_BUF_CENSUS_LEFT = 9,  /* uint64 [6][H][W]: lt_B, lt_G, lt_R, gt_B, gt_G, gt_R */
     TSM_BUF_CENSUS_RIGHT = 10,
     TSM_BUF_IMG_LEFT = 11, /* uint8 [H][W][3] */
-    TSM_BUF_IMG_RIGHT = 12
+    TSM_BUF_IMG_RIGHT = 12,
+    TSM_BUF_IMG4_LEFT = 13, /* uint32 [H][W]: the image the matching stages see, channel c in byte c (B,G,R or, for the
+                               HSI model, H,S,I after bgr2hsi + computeGaussMedian) */
+    TSM_BUF_IMG4_RIGHT = 14
 };
 int tsm_stage_begin(tsm_ctx* ctx, const tsm_adcensus_config* cfg,
                     const uint8_t* left, size_t lstep, const uint8_t* right, size_t rstep, int H, int W);

@@ -71,14 +71,24 @@ double now_s()
 {
     return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
-void set_images(stereo::ADCensus& a, const uint8_t* left, const uint8_t* right, int H, int W, int minD, int maxD)
+/* model: 0 = RGB, 1 = HSI (plain: no ROI / mask), the preprocessing of ADCensus::compute, ADCensus.cpp:350-371 */
+void set_images(stereo::ADCensus& a, const uint8_t* left, const uint8_t* right, int H, int W, int minD, int maxD, int model = 0)
 {
-    a.setMatchingStrategy(stereo::ColorModel::RGB, false, false);
+    a.setMatchingStrategy(model == 1 ? stereo::ColorModel::HSI : stereo::ColorModel::RGB, false, false);
     a.setMinMaxDisparity(minD, maxD);
     auto& im = *a.impl;
     cv::Mat L(cv::Size(W, H), CV_8UC3), R(cv::Size(W, H), CV_8UC3);
     std::memcpy(L.data, left, (size_t)H * W * 3);
     std::memcpy(R.data, right, (size_t)H * W * 3);
+    if (model == 1) {
+        cv::Mat hl, hr, fl, fr;
+        im.bgr2hsi(L, hl, false);
+        im.bgr2hsi(R, hr, false);
+        im.computeGaussMedian(hl, fl, 3);
+        im.computeGaussMedian(hr, fr, 3);
+        L = fl.clone();
+        R = fr.clone();
+    }
     im.m_images[0] = L;
     im.m_images[1] = R;
     im.m_imageSize = cv::Size(W, H);
@@ -119,13 +129,26 @@ struct RefTaps {
     double t_init, t_agg, t_scan, t_multi; /* seconds, out */
 };
 
+int ref_adcensus_staged_model(const uint8_t* left, const uint8_t* right, int H, int W, int minD, int maxD,
+                              int serial_scanline, int model, uint8_t* pre_left, uint8_t* pre_right, RefTaps* t);
+
 int ref_adcensus_staged(const uint8_t* left, const uint8_t* right, int H, int W, int minD, int maxD,
                         int serial_scanline, RefTaps* t)
 {
+    return ref_adcensus_staged_model(left, right, H, W, minD, maxD, serial_scanline, 0, nullptr, nullptr, t);
+}
+
+/* Same with the colour model selectable (0 RGB, 1 HSI); pre_left / pre_right (optional, H*W*3 bytes) receive the
+ * images the matching stages actually see (HSI: bgr2hsi + computeGaussMedian). */
+int ref_adcensus_staged_model(const uint8_t* left, const uint8_t* right, int H, int W, int minD, int maxD,
+                              int serial_scanline, int model, uint8_t* pre_left, uint8_t* pre_right, RefTaps* t)
+{
     try {
         stereo::ADCensus a;
-        set_images(a, left, right, H, W, minD, maxD);
+        set_images(a, left, right, H, W, minD, maxD, model);
         auto& im = *a.impl;
+        if (pre_left) std::memcpy(pre_left, im.m_images[0].data, (size_t)H * W * 3);
+        if (pre_right) std::memcpy(pre_right, im.m_images[1].data, (size_t)H * W * 3);
         const int Dn = maxD - minD + 1;
         double t0 = now_s();
         im.costInitialize();

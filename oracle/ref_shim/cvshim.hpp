@@ -7,7 +7,9 @@
  * and the reference does not vendor them.  Storage types are written from
  * scratch here; the five imgproc functions forward to oracle/cvport.c, whose
  * arithmetic is pinned against Python cv2 4.13.0.  HSI-only helpers
- * (getGaussianKernel / filter2D) throw: the RGB configs never reach them.
+ * getGaussianKernel / filter2D / Mat::t / Mat*Mat cover exactly what computeGaussMedian (HSI path,
+ * ADCensus.cpp:1475-1499) needs: a 3-tap fixed Gaussian, its outer product, and a float-kernel filter2D on
+ * CV_8UC3 with BORDER_CONSTANT; pinned against cv2 4.13 in tests/test_cvport.py.
  */
 #pragma once
 #include <cstdint>
@@ -142,7 +144,13 @@ public:
     template <typename T> const T* begin() const { return (const T*)data; }
     template <typename T> const T* end() const { return (const T*)(data + step * (size_t)rows); }
 
-    Mat t() const { throw std::runtime_error("cvshim: Mat::t unsupported (HSI path)"); }
+    Mat t() const {  // CV_32FC1 only (computeGaussMedian, ADCensus.cpp:1478)
+        if (type_ != CV_32F) throw std::runtime_error("cvshim: Mat::t only for CV_32FC1");
+        Mat m(Size(rows, cols), CV_32F);
+        for (int y = 0; y < rows; ++y)
+            for (int x = 0; x < cols; ++x) m.at<float>(x, y) = at<float>(y, x);
+        return m;
+    }
 
 private:
     int type_ = 0;
@@ -150,10 +158,45 @@ private:
 };
 template <typename T> using MatIterator_ = T*;
 
-inline Mat operator*(const Mat&, const Mat&) { throw std::runtime_error("cvshim: Mat*Mat unsupported (HSI path)"); }
-inline Mat getGaussianKernel(int, double, int = CV_64F) { throw std::runtime_error("cvshim: getGaussianKernel unsupported (HSI path)"); }
-inline void filter2D(const Mat&, Mat&, int, const Mat&, Point = Point(-1, -1), double = 0, int = BORDER_DEFAULT) {
-    throw std::runtime_error("cvshim: filter2D unsupported (HSI path)");
+inline Mat operator*(const Mat& a, const Mat& b) {  // CV_32FC1 matrix product, fp32 products and sums (cv::gemm, 4.13)
+    if (a.type() != CV_32F || b.type() != CV_32F || a.cols != b.rows) throw std::runtime_error("cvshim: Mat*Mat only CV_32FC1");
+    Mat m(Size(b.cols, a.rows), CV_32F);
+    for (int y = 0; y < a.rows; ++y)
+        for (int x = 0; x < b.cols; ++x) {
+            float s = 0.f;
+            for (int k = 0; k < a.cols; ++k) s += a.at<float>(y, k) * b.at<float>(k, x);
+            m.at<float>(y, x) = s;
+        }
+    return m;
+}
+// cv::getGaussianKernel(ksize, sigma <= 0, CV_32F) for ksize 3: OpenCV's fixed small kernel {0.25, 0.5, 0.25}
+inline Mat getGaussianKernel(int ksize, double sigma, int ktype = CV_64F) {
+    if (ksize != 3 || sigma > 0 || ktype != CV_32F) throw std::runtime_error("cvshim: getGaussianKernel only (3, sigma <= 0, CV_32F)");
+    Mat k(Size(1, 3), CV_32F);
+    k.at<float>(0, 0) = 0.25f; k.at<float>(1, 0) = 0.5f; k.at<float>(2, 0) = 0.25f;
+    return k;
+}
+// cv::filter2D(src CV_8UC3, dst, -1, float 3x3 kernel, anchor centre, delta 0, BORDER_CONSTANT): fp32 sum of
+// kernel * pixel over the window (zeros outside), saturate_cast<uchar> = round half to even.  With the dyadic
+// Gaussian weights every partial sum is exact, so the accumulation order cannot matter.
+inline void filter2D(const Mat& src, Mat& dst, int, const Mat& kernel, Point = Point(-1, -1), double = 0, int border = BORDER_DEFAULT) {
+    if (src.type() != CV_8UC3 || kernel.type() != CV_32F || kernel.rows != 3 || kernel.cols != 3 || border != BORDER_CONSTANT)
+        throw std::runtime_error("cvshim: filter2D only CV_8UC3 / 3x3 CV_32F / BORDER_CONSTANT");
+    Mat out(src.size(), CV_8UC3);
+    for (int y = 0; y < src.rows; ++y)
+        for (int x = 0; x < src.cols; ++x)
+            for (int c = 0; c < 3; ++c) {
+                float s = 0.f;
+                for (int i = -1; i <= 1; ++i)
+                    for (int j = -1; j <= 1; ++j) {
+                        const int yy = y + i, xx = x + j;
+                        if (yy < 0 || yy >= src.rows || xx < 0 || xx >= src.cols) continue;
+                        s += kernel.at<float>(i + 1, j + 1) * (float)src.ptr<uchar>(yy)[3 * xx + c];
+                    }
+                const long r = std::lrintf(s);
+                out.ptr<uchar>(y)[3 * x + c] = (uchar)(r < 0 ? 0 : r > 255 ? 255 : r);
+            }
+    dst = out;
 }
 inline bool imwrite(const std::string&, const Mat&) { return false; }
 

@@ -23,7 +23,7 @@ STAGE_LRC, STAGE_VOTE, STAGE_INTERP, STAGE_DISCONT, STAGE_SUBPIXEL = 32, 64, 128
 STAGE_ALL = 1023
 # enum tsm_buffer
 (BUF_VOL_LEFT, BUF_VOL_RIGHT, BUF_ARMS_LEFT, BUF_ARMS_RIGHT, BUF_WTA_LEFT, BUF_WTA_RIGHT, BUF_DISP, BUF_EDGES,
- BUF_FINAL, BUF_CENSUS_LEFT, BUF_CENSUS_RIGHT, BUF_IMG_LEFT, BUF_IMG_RIGHT) = range(13)
+ BUF_FINAL, BUF_CENSUS_LEFT, BUF_CENSUS_RIGHT, BUF_IMG_LEFT, BUF_IMG_RIGHT, BUF_IMG4_LEFT, BUF_IMG4_RIGHT) = range(15)
 MAP_FIXED, MAP_FLOAT = 0, 1
 
 # every symbol include/tsm.h declares (tests check the .so exports them all)

@@ -189,12 +189,12 @@ class ADCensus:
 class StageRunner:
     """Parity harness over tsm_stage_begin / tsm_stage_run / tsm_tap / tsm_poke (tests only)."""
 
-    def __init__(self, left, right, max_disparity: int, device: int = 0):
+    def __init__(self, left, right, max_disparity: int, device: int = 0, model: "ColorModel | None" = None):
         self.ctx = Context(device)
         self.left, self.right = _as_bgr(left), _as_bgr(right)
         self.H, self.W, _ = self.left.shape
         self.Dn = max_disparity + 1
-        self.cfg = N.Config(0, max_disparity, 0, 0, 0, 0)
+        self.cfg = N.Config(0, max_disparity, int(ColorModel.RGB if model is None else model), 0, 0, 0)
         L = self.ctx._lib
         self.ctx.check(L.tsm_stage_begin(self.ctx.handle, C.byref(self.cfg), _ptr(self.left), self.left.strides[0],
                                          _ptr(self.right), self.right.strides[0], self.H, self.W))
@@ -216,6 +216,11 @@ class StageRunner:
         v = np.zeros((self.H, self.W, self.Dp), np.float32)
         v[:, :, : self.Dn] = vol
         self.ctx.check(self.ctx._lib.tsm_poke(self.ctx.handle, N.BUF_VOL_LEFT + view, _ptr(v), v.nbytes))
+
+    def image(self, view: int) -> np.ndarray:
+        """The 3-channel image the matching stages see (BGR, or H,S,I after the HSI preprocessing)."""
+        v = self._tap_raw(N.BUF_IMG4_LEFT + view, np.uint8, (self.H, self.W, 4))
+        return np.ascontiguousarray(v[:, :, :3])
 
     def arms(self, view: int) -> np.ndarray:
         return self._tap_raw(N.BUF_ARMS_LEFT + view, np.uint8, (self.H, self.W, 4))

@@ -30,8 +30,8 @@ namespace tsm {
 
 constexpr int COST_WARPS = 8;
 constexpr int COST_J = 4;       // fixed pixels per warp iteration
-constexpr int TAB_AD_N = 766, TAB_C_N = 192;
-constexpr int TAB_C_PAD = 194;  // (766 + 194) * 4 bytes = 3840: keeps what follows 16-byte aligned
+constexpr int TAB_C_N = kTabCensus;
+constexpr int TAB_C_PAD = 194;  // RGB: (766 + 194) * 4 = 3840 bytes, HSI: (2806 + 194) * 4 = 12000: what follows stays 16-byte aligned
 constexpr uint32_t kInvalidPix = 0xffffffffu;
 
 struct Sig {
@@ -57,7 +57,9 @@ __device__ __forceinline__ int census_count(const Sig& f, const Sig& m)
 #define TSM_COST_MINB 3
 #endif
 // COST_TX = left pixels per CTA: 64, or 32 when the shared tile [COST_TX][Dn] would otherwise leave one CTA per SM
-template <int COST_TX>
+// HSI: adCost = min(|dH|, 255 - |dH|) * 1 + |dS| * 2.5 + |dI| * 2.5 (computeHSIADCost, :439-452) is exact in fp32,
+// so the table is indexed with 2 * adCost = 2 hd + 5 (ds + di) <= 2804.
+template <int COST_TX, bool HSI>
 __global__ void __launch_bounds__(COST_WARPS * 32, TSM_COST_MINB)
 k_cost_init(Dims dm, ViewPtrs vl, ViewPtrs vr, const float* __restrict__ g_tab_ad, const float* __restrict__ g_tab_c)
 {
@@ -65,10 +67,12 @@ k_cost_init(Dims dm, ViewPtrs vl, ViewPtrs vr, const float* __restrict__ g_tab_a
     const int y = blockIdx.y, x0 = blockIdx.x * COST_TX;
     const int H = dm.H, W = dm.W, Dn = dm.Dn;
     const int ncol = (COST_TX + Dn - 1 + 3) & ~3;  // right columns the tile can reach (padded to keep 16-byte alignment)
+    constexpr int TAB_AD_N = HSI ? kTabAdHsi + 1 : kTabAdRgb;  // + 1: keeps the 16-byte alignment
+    constexpr int TAB_AD_USED = HSI ? kTabAdHsi : kTabAdRgb;
     float* tab_ad = reinterpret_cast<float*>(smem);
     float* tab_c = tab_ad + TAB_AD_N;
     uint32_t* mw = reinterpret_cast<uint32_t*>(tab_c + TAB_C_PAD);  // [ncol][13]: 12 signature words + pixel (stride 13: conflict-free)
-    for (int i = threadIdx.x; i < TAB_AD_N; i += blockDim.x) tab_ad[i] = g_tab_ad[i];
+    for (int i = threadIdx.x; i < TAB_AD_USED; i += blockDim.x) tab_ad[i] = g_tab_ad[i];
     for (int i = threadIdx.x; i < TAB_C_N; i += blockDim.x) tab_c[i] = g_tab_c[i];
 
     const size_t npx = (size_t)H * W, row = (size_t)y * W;
@@ -137,7 +141,14 @@ k_cost_init(Dims dm, ViewPtrs vl, ViewPtrs vr, const float* __restrict__ g_tab_a
 #pragma unroll
             for (int j = 0; j < COST_J; ++j) {
                 const int d = e + j;
-                const int ad3 = min((int)__vsadu4(f[j].pix, m.pix), TAB_AD_N - 1);
+                int ad3;
+                if (HSI) {
+                    const uint32_t dv = __vabsdiffu4(f[j].pix, m.pix);  // |dH|, |dS|, |dI| (byte 3 is 0 or 255 for invalid)
+                    const int hd = dv & 0xffu;
+                    ad3 = min(2 * min(hd, 255 - hd) + 5 * (int)(((dv >> 8) & 0xffu) + ((dv >> 16) & 0xffu)), TAB_AD_USED - 1);
+                } else {
+                    ad3 = min((int)__vsadu4(f[j].pix, m.pix), TAB_AD_USED - 1);
+                }
                 const int cen = census_count(f[j], m);
                 float cost = __fsub_rn(__fsub_rn(2.f, tab_ad[ad3]), tab_c[cen]);
                 cost = (fok[j] && mok) ? cost : 2.f;
@@ -194,27 +205,33 @@ k_cost_init(Dims dm, ViewPtrs vl, ViewPtrs vr, const float* __restrict__ g_tab_a
     }
 }
 
-template <int COST_TX>
+template <int COST_TX, bool HSI>
 static void launch_cost(const Launcher& L, const Dims& d, const ViewPtrs& left, const ViewPtrs& right, const float* d_tab_ad,
                         const float* d_tab_census)
 {
+    constexpr int tab_ad_n = HSI ? kTabAdHsi + 1 : kTabAdRgb;
     const size_t ncol = (size_t)((COST_TX + d.Dn - 1 + 3) & ~3), dnp = (size_t)((d.Dn + 3) & ~3);
-    const size_t smem = (size_t)(TAB_AD_N + TAB_C_PAD) * 4 + 13 * ncol * 4 + (size_t)COST_TX * dnp * 4;
+    const size_t smem = (size_t)(tab_ad_n + TAB_C_PAD) * 4 + 13 * ncol * 4 + (size_t)COST_TX * dnp * 4;
     static size_t smem_set = 0;
     if (smem > smem_set) {
-        cudaFuncSetAttribute(k_cost_init<COST_TX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(k_cost_init<COST_TX, HSI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         smem_set = smem;
     }
     dim3 grid((d.W + COST_TX - 1) / COST_TX, d.H);
-    k_cost_init<COST_TX><<<grid, COST_WARPS * 32, smem, L.stream>>>(d, left, right, d_tab_ad, d_tab_census);
+    k_cost_init<COST_TX, HSI><<<grid, COST_WARPS * 32, smem, L.stream>>>(d, left, right, d_tab_ad, d_tab_census);
     L.count(1);
 }
 
 void cost_init(const Launcher& L, const Dims& d, const ViewPtrs& left, const ViewPtrs& right, const float* d_tab_ad,
-               const float* d_tab_census)
+               const float* d_tab_census, bool hsi)
 {
-    if (d.Dn > 256) launch_cost<32>(L, d, left, right, d_tab_ad, d_tab_census);
-    else launch_cost<64>(L, d, left, right, d_tab_ad, d_tab_census);
+    if (hsi) {
+        if (d.Dn > 256) launch_cost<32, true>(L, d, left, right, d_tab_ad, d_tab_census);
+        else launch_cost<64, true>(L, d, left, right, d_tab_ad, d_tab_census);
+    } else {
+        if (d.Dn > 256) launch_cost<32, false>(L, d, left, right, d_tab_ad, d_tab_census);
+        else launch_cost<64, false>(L, d, left, right, d_tab_ad, d_tab_census);
+    }
 }
 
 }  // namespace tsm

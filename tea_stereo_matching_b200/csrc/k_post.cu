@@ -449,7 +449,8 @@ void region_voting(const Launcher& L, const Dims& d, const int32_t* disp_in, int
 __constant__ int c_dirW[16] = {0, 2, 2, 2, 0, -2, -2, -2, 1, 2, 2, 1, -1, -2, -2, -1};
 __constant__ int c_dirH[16] = {2, 2, 0, -2, -2, -2, 0, 2, 2, 1, -1, -2, -2, -1, 1, 2};
 
-__global__ void k_interpolate(const int32_t* __restrict__ disp, int32_t* __restrict__ out, const uint32_t* __restrict__ img4, int H, int W)
+__global__ void k_interpolate(const int32_t* __restrict__ disp, int32_t* __restrict__ out, const uint32_t* __restrict__ img4, int H, int W,
+                              int hsi)
 {
     const int w = blockIdx.x * blockDim.x + threadIdx.x, h = blockIdx.y * blockDim.y + threadIdx.y;
     if (w >= W || h >= H) return;
@@ -476,7 +477,8 @@ __global__ void k_interpolate(const int32_t* __restrict__ disp, int32_t* __restr
                 const int v = disp[(size_t)hD * W + wD];
                 if (v >= 0) {
                     nd = v;
-                    nf = color_diff_u32(pc, img4[(size_t)hD * W + wD]);
+                    const uint32_t qc = img4[(size_t)hD * W + wD];
+                    nf = hsi ? hue_diff_u32(pc, qc) : color_diff_u32(pc, qc);
                     got = true;
                 }
             }
@@ -488,10 +490,11 @@ __global__ void k_interpolate(const int32_t* __restrict__ disp, int32_t* __restr
     out[p] = (own == kOcclusion) ? occ_min : md;
 }
 
-void proper_interpolation(const Launcher& L, const Dims& d, const int32_t* disp_in, int32_t* disp_out, const uint32_t* img4_left)
+void proper_interpolation(const Launcher& L, const Dims& d, const int32_t* disp_in, int32_t* disp_out, const uint32_t* img4_left,
+                          bool hsi)
 {
     dim3 b(32, 8), g((d.W + 31) / 32, (d.H + 7) / 8);
-    k_interpolate<<<g, b, 0, L.stream>>>(disp_in, disp_out, img4_left, d.H, d.W);
+    k_interpolate<<<g, b, 0, L.stream>>>(disp_in, disp_out, img4_left, d.H, d.W, hsi ? 1 : 0);
     L.count(1);
 }
 

@@ -25,6 +25,11 @@ __global__ void k_pack_bgrx(const uint8_t* __restrict__ img, uint32_t* __restric
 constexpr int CT_W = 32, CT_H = 8, CH_W = kCensusW / 2, CH_H = kCensusH / 2;
 constexpr int CS_W = CT_W + 2 * CH_W, CS_H = CT_H + 2 * CH_H;
 
+// HSI model (computeHSICensusCost, ADCensus.cpp:476-498): saturation and intensity keep the sign-product test;
+// the hue term of a neighbour costs 0 only when BOTH views satisfy A = (dH <= -127 or 0 <= dH <= 127), i.e. it
+// costs popc(nA_L | nA_R) with nA = not A.  Stored as plane "lt" = nA and plane "gt" = all ones, the generic
+// match word (lt_L & gt_R) | (gt_L & lt_R) of k_cost_init evaluates exactly that.
+template <bool HSI>
 __global__ void __launch_bounds__(CT_W* CT_H)
 k_census(const uint32_t* __restrict__ img4, uint64_t* __restrict__ census, int H, int W)
 {
@@ -51,8 +56,14 @@ k_census(const uint32_t* __restrict__ img4, uint64_t* __restrict__ census, int H
                 const uint32_t a = tile[threadIdx.y + i][threadIdx.x + j];
                 const int ab = a & 0xff, ag = (a >> 8) & 0xff, ar = (a >> 16) & 0xff;
                 const uint64_t m = 1ull << bit;
-                if (ab < cb) lt[0] |= m;
-                if (ab > cb) gt[0] |= m;
+                if (HSI) {
+                    const int dh = ab - cb;
+                    if (!(dh <= -127 || (dh >= 0 && dh <= 127))) lt[0] |= m;
+                    gt[0] |= m;
+                } else {
+                    if (ab < cb) lt[0] |= m;
+                    if (ab > cb) gt[0] |= m;
+                }
                 if (ag < cg) lt[1] |= m;
                 if (ag > cg) gt[1] |= m;
                 if (ar < cr) lt[2] |= m;
@@ -68,9 +79,11 @@ k_census(const uint32_t* __restrict__ img4, uint64_t* __restrict__ census, int H
 }
 
 // ---- cross arms -------------------------------------------------------------
-__device__ __forceinline__ int arm_length(const uint32_t* __restrict__ img4, int H, int W, int y, int x, int dy, int dx)
+__device__ __forceinline__ int arm_length(const uint32_t* __restrict__ img4, int H, int W, int y, int x, int dy, int dx,
+                                          const ModelParams mp)
 {
-    // Literal walk of computeLimit (RGB): ADCensus.cpp:609-658.
+    // Literal walk of computeLimit: ADCensus.cpp:609-658.  RGB: max-channel colour difference; HSI: the
+    // intensity tests (the hue and saturation assignments before them are overwritten, :631-645).
     const uint32_t p = img4[(size_t)y * W + x];
     int d = 1;
     int y1 = y + dy, x1 = x + dx;
@@ -80,10 +93,17 @@ __device__ __forceinline__ int arm_length(const uint32_t* __restrict__ img4, int
         bool color_cond = true, wlimit_cond = true, fcolor_cond = true;
         while (color_cond && wlimit_cond && fcolor_cond && inside) {
             const uint32_t p1 = img4[(size_t)y1 * W + x1];
-            const int cd = color_diff_u32(p, p1);
-            color_cond = cd < kTau1 && color_diff_u32(p1, p2) < kTau1;
-            wlimit_cond = d < kL1;
-            fcolor_cond = (d <= kL2) || (cd < kTau2);
+            int cd, cd2;
+            if (mp.hsi) {
+                cd = abs((int)((p >> 16) & 0xffu) - (int)((p1 >> 16) & 0xffu));
+                cd2 = abs((int)((p1 >> 16) & 0xffu) - (int)((p2 >> 16) & 0xffu));
+            } else {
+                cd = color_diff_u32(p, p1);
+                cd2 = color_diff_u32(p1, p2);
+            }
+            color_cond = cd < mp.tau1 && cd2 < mp.tau1;
+            wlimit_cond = d < mp.L1;
+            fcolor_cond = (d <= mp.L2) || (cd < mp.tau2);
             p2 = p1;
             y1 += dy;
             x1 += dx;
@@ -95,15 +115,15 @@ __device__ __forceinline__ int arm_length(const uint32_t* __restrict__ img4, int
     return d - 1;
 }
 
-__global__ void k_arms(const uint32_t* __restrict__ img4, uchar4* __restrict__ arms, int H, int W)
+__global__ void k_arms(const uint32_t* __restrict__ img4, uchar4* __restrict__ arms, int H, int W, ModelParams mp)
 {
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
     if (x >= W || y >= H) return;
     uchar4 a;
-    a.x = (unsigned char)arm_length(img4, H, W, y, x, -1, 0);
-    a.y = (unsigned char)arm_length(img4, H, W, y, x, 1, 0);
-    a.z = (unsigned char)arm_length(img4, H, W, y, x, 0, -1);
-    a.w = (unsigned char)arm_length(img4, H, W, y, x, 0, 1);
+    a.x = (unsigned char)arm_length(img4, H, W, y, x, -1, 0, mp);
+    a.y = (unsigned char)arm_length(img4, H, W, y, x, 1, 0, mp);
+    a.z = (unsigned char)arm_length(img4, H, W, y, x, 0, -1, mp);
+    a.w = (unsigned char)arm_length(img4, H, W, y, x, 0, 1, mp);
     arms[(size_t)y * W + x] = a;
 }
 
@@ -137,15 +157,15 @@ __global__ void k_agg_desc(const uchar4* __restrict__ arms, uint32_t* __restrict
 }
 
 // ---- similarity flags ---------------------------------------------------------
-__global__ void k_flags(const uint32_t* __restrict__ img4, uint8_t* __restrict__ flags, int H, int W)
+__global__ void k_flags(const uint32_t* __restrict__ img4, uint8_t* __restrict__ flags, int H, int W, ModelParams mp)
 {
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
     if (x >= W || y >= H) return;
     const size_t p = (size_t)y * W + x;
     const uint32_t c = img4[p];
     uint8_t f = 0;
-    if (y > 0 && color_diff_u32(c, img4[p - W]) < kColorDiff) f |= 1;
-    if (x > 0 && color_diff_u32(c, img4[p - 1]) < kColorDiff) f |= 2;
+    if (y > 0 && (mp.hsi ? hue_diff_u32(c, img4[p - W]) : color_diff_u32(c, img4[p - W])) < mp.sim) f |= 1;
+    if (x > 0 && (mp.hsi ? hue_diff_u32(c, img4[p - 1]) : color_diff_u32(c, img4[p - 1])) < mp.sim) f |= 2;
     flags[p] = f;
 }
 
@@ -190,18 +210,71 @@ void prep_scan_tables(const Launcher& L, const Dims& d, const uint8_t* flags_lef
     L.count(2);
 }
 
+// ---- HSI preprocessing (ADCensus::compute, ADCensus.cpp:350-371) ---------------------------------------
+// bgr2hsi (:1429-1473) is a pure function of the 24-bit pixel with sqrtf / acosf inside; the host evaluates it
+// for all 2^24 inputs once per process with its own libm (tsm_capi.cu) -- the same trick as the exp() tables --
+// so the conversion is a table lookup and bit-identical to the reference.
+__global__ void k_hsi_lookup(const uint32_t* __restrict__ bgr4, const uint32_t* __restrict__ lut, uint32_t* __restrict__ hsi4, size_t n)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) hsi4[i] = lut[bgr4[i] & 0xffffffu];
+}
+
+// computeGaussMedian(src, dst, 3) (:1475-1499): filter2D with the 3x3 kernel [1 2 1; 2 4 2; 1 2 1] / 16
+// (cv::getGaussianKernel(3, -1)), BORDER_CONSTANT 0, rounded half to even; a channel takes the filtered value
+// when it is far from it (hue: circular distance >= 2; S, I: >= 3).
+__global__ void k_gauss_median(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, int H, int W)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= W || y >= H) return;
+    int sum[3] = {0, 0, 0};
+#pragma unroll
+    for (int i = -1; i <= 1; ++i)
+#pragma unroll
+        for (int j = -1; j <= 1; ++j) {
+            const int yy = y + i, xx = x + j;
+            if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
+            const uint32_t v = src[(size_t)yy * W + xx];
+            const int w = (i == 0 ? 2 : 1) * (j == 0 ? 2 : 1);
+            sum[0] += w * (int)(v & 0xffu);
+            sum[1] += w * (int)((v >> 8) & 0xffu);
+            sum[2] += w * (int)((v >> 16) & 0xffu);
+        }
+    const uint32_t s = src[(size_t)y * W + x];
+    uint32_t out = 0;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const int q = sum[c] >> 4, r = sum[c] & 15;
+        const int med = q + ((r > 8 || (r == 8 && (q & 1))) ? 1 : 0);  // round(sum / 16) half to even, <= 255
+        const int own = (int)((s >> (8 * c)) & 0xffu);
+        int diff = abs(own - med);
+        bool take;
+        if (c == 0) { diff = min(diff, 255 - diff); take = diff >= 2; }
+        else take = diff >= 3;
+        out |= (uint32_t)(take ? med : own) << (8 * c);
+    }
+    dst[(size_t)y * W + x] = out;
+}
+
 void prep_view(const Launcher& L, const Dims& d, int view, const uint8_t* img, uint32_t* img4, uint64_t* census,
-               uchar4* arms, uint32_t* desc_h, uint32_t* desc_v, uint8_t* flags)
+               uchar4* arms, uint32_t* desc_h, uint32_t* desc_v, uint8_t* flags, const ModelParams& mp, const uint32_t* hsi_lut)
 {
     const size_t npx = d.npx();
-    k_pack_bgrx<<<(unsigned)((npx + 255) / 256), 256, 0, L.stream>>>(img, img4, npx);
-    dim3 cb(CT_W, CT_H), cg((d.W + CT_W - 1) / CT_W, (d.H + CT_H - 1) / CT_H);
-    k_census<<<cg, cb, 0, L.stream>>>(img4, census, d.H, d.W);
     dim3 b(32, 8), g((d.W + 31) / 32, (d.H + 7) / 8);
-    k_arms<<<g, b, 0, L.stream>>>(img4, arms, d.H, d.W);
+    k_pack_bgrx<<<(unsigned)((npx + 255) / 256), 256, 0, L.stream>>>(img, img4, npx);
+    if (mp.hsi) {
+        uint32_t* tmp = reinterpret_cast<uint32_t*>(arms);  // free until k_arms, same size
+        k_hsi_lookup<<<(unsigned)((npx + 255) / 256), 256, 0, L.stream>>>(img4, hsi_lut, tmp, npx);
+        k_gauss_median<<<g, b, 0, L.stream>>>(tmp, img4, d.H, d.W);
+        L.count(2);
+    }
+    dim3 cb(CT_W, CT_H), cg((d.W + CT_W - 1) / CT_W, (d.H + CT_H - 1) / CT_H);
+    if (mp.hsi) k_census<true><<<cg, cb, 0, L.stream>>>(img4, census, d.H, d.W);
+    else k_census<false><<<cg, cb, 0, L.stream>>>(img4, census, d.H, d.W);
+    k_arms<<<g, b, 0, L.stream>>>(img4, arms, d.H, d.W, mp);
     k_agg_desc<<<g, b, 0, L.stream>>>(arms, desc_h, desc_v, reinterpret_cast<float*>(desc_h + d.desc_h_words()),
                                       reinterpret_cast<float*>(desc_v + d.desc_v_words()), d.H, d.W, d.Wd(), d.Hd());
-    k_flags<<<g, b, 0, L.stream>>>(img4, flags, d.H, d.W);
+    k_flags<<<g, b, 0, L.stream>>>(img4, flags, d.H, d.W, mp);
     L.count(5);
 }
 

@@ -3,6 +3,7 @@
 // (reference source/ADCensus.cpp:330-407) and multiOptimize (:1376-1392).
 #include "tsm_common.cuh"
 #include <algorithm>
+#include <mutex>
 #include <limits.h>
 #include <math.h>
 #include <stdarg.h>
@@ -46,7 +47,8 @@ struct tsm_ctx {
     Buf disp[2], fin, ftmp;
     Buf v_vote, v_lowcnt, v_off, v_mark, v_start, v_sums, v_flat, v_stash;
     Buf e_gray, e_blur, e_mag, e_gx, e_gy, e_map, e_edges, e_hist, e_lut, e_changed;
-    Buf tab_ad, tab_c, agg_ctr;
+    Buf tab_ad, tab_c, agg_ctr, tab_ad_hsi, hsi_lut;
+    bool hsi = false, hsi_ready = false;  // colour model of the current configuration; HSI tables uploaded
     Buf k_in, k_out, k_tab, k_range;  // disparity consumers: staged input map, output, colour table, min/max
     int fin_H = 0, fin_W = 0;        // geometry of the map in `fin` (0 = none yet)
     int disp_cur = 0;  // which of disp[2] holds the working map
@@ -135,8 +137,6 @@ int check_cfg(tsm_ctx* c, const tsm_adcensus_config* cfg, int H, int W)
     if ((long long)cfg->min_disparity * cfg->max_disparity < 0 || cfg->min_disparity >= cfg->max_disparity)
         return fail(c, TSM_E_ARG, "[ADCensus] Set MinMaxDisparity error.");
     if (cfg->offset < 0) return fail(c, TSM_E_ARG, "[ADCensus] Offset must be positive.");  // ADCensus.cpp:325-326
-    if (cfg->color_model != TSM_COLOR_RGB)
-        return fail(c, TSM_E_UNSUPPORTED, "[ADCensus] HSI colour model is not built yet (SURVEY 8(f) row f1)");
     if (cfg->roi_matching || cfg->mask_matching)
         return fail(c, TSM_E_UNSUPPORTED, "[ADCensus] ROI / mask matching modes are not built yet (SURVEY 8(f) row f1)");
     if (cfg->min_disparity != 0)
@@ -149,6 +149,73 @@ int check_cfg(tsm_ctx* c, const tsm_adcensus_config* cfg, int H, int W)
 
 // Host-side LUTs with the host's own expf, in the reference's expression order:
 //   expf(-((float)s / 3.f) / 10.f)  (ADCensus.cpp:435, :518)  and  expf(-(float)n / 30.f).
+// bgr2hsi (ADCensus.cpp:1429-1473) for every 24-bit pixel, evaluated ONCE per process with the host's libm in the
+// reference's expression order (float arithmetic, the hue division in double because CV_PI is a double literal,
+// float -> uchar conversions truncate).  Index = B | G << 8 | R << 16, value = H | S << 8 | I << 16.
+static const std::vector<uint32_t>& hsi_table()
+{
+    static std::vector<uint32_t> tab;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        tab.resize(1u << 24);
+        const double two_pi = 2 * 3.1415926535897932384626433832795;  // 2 * CV_PI
+        for (uint32_t i = 0; i < (1u << 24); ++i) {
+            const volatile float blueValue = (float)(i & 0xff) / 255.f, greenValue = (float)((i >> 8) & 0xff) / 255.f,
+                                 redValue = (float)((i >> 16) & 0xff) / 255.f;
+            const volatile float sum0 = blueValue + greenValue;
+            const volatile float sum = sum0 + redValue;
+            const volatile float iValue = sum / 3.0f;
+            float sValue, hValue;
+            if (sum == 0) sValue = 0;
+            else {
+                const float mn = std::min(std::min((float)blueValue, (float)greenValue), (float)redValue);
+                const volatile float t3 = 3 * mn;
+                const volatile float q = t3 / sum;
+                sValue = 1 - q;
+            }
+            const volatile float rg = redValue - greenValue, rb = redValue - blueValue, gb = greenValue - blueValue;
+            const volatile float a2 = rg * rg, b2 = rb * gb;
+            const volatile float rad = a2 + b2;
+            const float den = sqrtf(rad);
+            const volatile float n0 = 2 * redValue;
+            const volatile float n1 = n0 - greenValue;
+            const volatile float n2 = n1 - blueValue;
+            const float num = n2 / 2.f;
+            if (den == 0.f || den <= num || sValue < 0.05f) hValue = 0;
+            else {
+                const volatile float ratio = num / den;
+                const float theta = acosf(ratio);
+                hValue = blueValue <= greenValue ? (float)(theta / two_pi) : (float)(1 - theta / two_pi);
+            }
+            const volatile float hi = hValue * 255, si = sValue * 255, ii = iValue * 255;
+            const uint32_t H = (unsigned char)hi, S = (unsigned char)si, I = (unsigned char)ii;
+            tab[i] = H | (S << 8) | (I << 16);
+        }
+    });
+    return tab;
+}
+
+int ensure_hsi_tables(tsm_ctx* c)
+{
+    if (c->hsi_ready) return TSM_OK;
+    // exp(-adCost / lambdaAD) over t = 2 * adCost (adCost is a multiple of 0.5, computeHSIADCost :439-452)
+    std::vector<float> tab(kTabAdHsi);
+    const volatile float lambda_ad = 10.f, half = 0.5f;
+    for (int t = 0; t < kTabAdHsi; ++t) {
+        volatile float ad = (float)t * half;
+        tab[t] = expf(-ad / lambda_ad);
+    }
+    const std::vector<uint32_t>& lut = hsi_table();
+    int rc;
+    if ((rc = ensure(c, c->tab_ad_hsi, tab.size() * 4))) return rc;
+    if ((rc = ensure(c, c->hsi_lut, lut.size() * 4))) return rc;
+    CK(c, cudaMemcpyAsync(c->tab_ad_hsi.p, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice, c->stream));
+    CK(c, cudaMemcpyAsync(c->hsi_lut.p, lut.data(), lut.size() * 4, cudaMemcpyHostToDevice, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    c->hsi_ready = true;
+    return TSM_OK;
+}
+
 int ensure_tables(tsm_ctx* c)
 {
     if (c->tables_ready) return TSM_OK;
@@ -181,6 +248,8 @@ int ensure_arena(tsm_ctx* c, const tsm_adcensus_config* cfg, int H, int W)
     if (rc) return rc;
     CK(c, cudaSetDevice(c->device));
     if ((rc = ensure_tables(c))) return rc;
+    c->hsi = cfg->color_model == TSM_COLOR_HSI;
+    if (c->hsi && (rc = ensure_hsi_tables(c))) return rc;
     Dims d;
     d.set(H, W, cfg->max_disparity - cfg->min_disparity + 1);
     c->dm = d;
@@ -276,13 +345,14 @@ int run_stages(tsm_ctx* c, int mask, int arg)
         ScopedStage s(c, "prep");
         for (int k = 0; k < 2; ++k)
             prep_view(L, d, k, (const uint8_t*)c->img[k].p, (uint32_t*)c->img4[k].p, (uint64_t*)c->census[k].p,
-                      (uchar4*)c->arms[k].p, (uint32_t*)c->desc_h[k].p, (uint32_t*)c->desc_v[k].p, (uint8_t*)c->flags[k].p);
+                      (uchar4*)c->arms[k].p, (uint32_t*)c->desc_h[k].p, (uint32_t*)c->desc_v[k].p, (uint8_t*)c->flags[k].p,
+                      model_params(c->hsi), (const uint32_t*)c->hsi_lut.p);
         prep_scan_tables(L, d, (const uint8_t*)c->flags[0].p, (const uint8_t*)c->flags[1].p, (uint32_t*)c->tflags[0].p,
                          (uint32_t*)c->tflags[1].p);
     }
     if (mask & TSM_STAGE_INIT) {
         ScopedStage s(c, "cost_init");
-        cost_init(L, d, vl, vr, (const float*)c->tab_ad.p, (const float*)c->tab_c.p);
+        cost_init(L, d, vl, vr, (const float*)(c->hsi ? c->tab_ad_hsi.p : c->tab_ad.p), (const float*)c->tab_c.p, c->hsi);
     }
     if (mask & TSM_STAGE_AGGREGATE) {
         ScopedStage s(c, "aggregate");
@@ -325,7 +395,7 @@ int run_stages(tsm_ctx* c, int mask, int arg)
     }
     if (mask & TSM_STAGE_INTERP) {
         ScopedStage s(c, "interpolation");
-        proper_interpolation(L, d, (const int32_t*)c->disp[c->disp_cur].p, (int32_t*)c->disp[c->disp_cur ^ 1].p, vl.img4);
+        proper_interpolation(L, d, (const int32_t*)c->disp[c->disp_cur].p, (int32_t*)c->disp[c->disp_cur ^ 1].p, vl.img4, c->hsi);
         c->disp_cur ^= 1;
     }
     if (mask & TSM_STAGE_DISCONT) {
@@ -449,7 +519,7 @@ void tsm_destroy(tsm_ctx* c)
                   &c->desc_h[0], &c->desc_h[1], &c->desc_v[0], &c->desc_v[1], &c->flags[0], &c->flags[1], &c->tflags[0], &c->tflags[1], &c->vtail[0], &c->vtail[1], &c->dense, &c->vol[0], &c->vol[1], &c->wta_[0], &c->wta_[1],
                   &c->disp[0], &c->disp[1], &c->fin, &c->ftmp, &c->v_vote, &c->v_lowcnt, &c->v_off, &c->v_mark, &c->v_start, &c->v_stash,
                   &c->v_sums, &c->v_flat, &c->e_gray, &c->e_blur, &c->e_mag, &c->e_gx, &c->e_gy, &c->e_map, &c->e_edges,
-                  &c->e_hist, &c->e_lut, &c->e_changed, &c->tab_ad, &c->tab_c, &c->agg_ctr, &c->k_in, &c->k_out, &c->k_tab, &c->k_range, &c->r_src, &c->r_map1[0], &c->r_map1[1],
+                  &c->e_hist, &c->e_lut, &c->e_changed, &c->tab_ad, &c->tab_c, &c->agg_ctr, &c->tab_ad_hsi, &c->hsi_lut, &c->k_in, &c->k_out, &c->k_tab, &c->k_range, &c->r_src, &c->r_map1[0], &c->r_map1[1],
                   &c->r_map2[0], &c->r_map2[1], &c->r_fmap[0][0], &c->r_fmap[0][1], &c->r_fmap[1][0], &c->r_fmap[1][1]};
     for (Buf* b : all) release(*b);
     if (c->h_pair) cudaFreeHost(c->h_pair);
@@ -705,6 +775,8 @@ static Buf* tap_buffer(tsm_ctx* c, int id, size_t* bytes)
         case TSM_BUF_CENSUS_RIGHT: *bytes = npx * 48; return &c->census[1];
         case TSM_BUF_IMG_LEFT: *bytes = npx * 3; return &c->img[0];
         case TSM_BUF_IMG_RIGHT: *bytes = npx * 3; return &c->img[1];
+        case TSM_BUF_IMG4_LEFT: *bytes = npx * 4; return &c->img4[0];
+        case TSM_BUF_IMG4_RIGHT: *bytes = npx * 4; return &c->img4[1];
         default: return nullptr;
     }
 }

@@ -11,6 +11,8 @@ Run in the dev container (needs /root/reference and python cv2 4.13.0):
   source/ADCensus.cpp (oracle/_ref/libadcensus_ref.so, serial-scanline semantics) on that
   pair, D = 0..48: integer maps in full, float volumes as SHA-256 digests plus strided
   samples (the full volumes are 11 MB each).
+* ref_0600_crop_160x96_d32_hsi.npz / ref_0600_320x180_d48_hsi.npz -- the same with the HSI colour model
+  (bgr2hsi + computeGaussMedian preprocessing; a 160x96 crop carries the full volumes).
 * ref_synth_96x128_d24.npz -- same for a tiny synthetic pair (synth_v1 seed 7), with the
   full volumes (small enough) so the CUDA kernels can be checked cell by cell on a box
   without /root/reference.
@@ -70,6 +72,15 @@ def main():
     np.savez_compressed(OUT / "pair_0600_320x180.npz", left=Ls, right=Rs)
     st = ref.run(Ls, Rs, 48, serial_scanline=True)
     np.savez_compressed(OUT / "ref_0600_320x180_d48.npz", max_disparity=48, **stage_dict(st, False))
+
+    # HSI colour model (row f1): the preprocessed images the stages see + every stage output, with full volumes on a
+    # crop small enough to commit
+    Lc, Rc = np.ascontiguousarray(Ls[40:136, 96:256]), np.ascontiguousarray(Rs[40:136, 96:256])
+    st = ref.run(Lc, Rc, 32, serial_scanline=True, model="HSI")
+    np.savez_compressed(OUT / "ref_0600_crop_160x96_d32_hsi.npz", left=Lc, right=Rc, max_disparity=32, pre0=st.pre[0], pre1=st.pre[1],
+                        **stage_dict(st, True))
+    st = ref.run(Ls, Rs, 48, serial_scanline=True, model="HSI")
+    np.savez_compressed(OUT / "ref_0600_320x180_d48_hsi.npz", max_disparity=48, pre0=st.pre[0], pre1=st.pre[1], **stage_dict(st, False))
 
     sl, sr = synth_v1(96, 128, 24, seed=7)
     st = ref.run(sl, sr, 24, serial_scanline=True)

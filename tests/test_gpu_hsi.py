@@ -1,0 +1,77 @@
+"""Row f1 (HSI colour model, no ROI / mask): every stage against the unmodified reference run with
+setMatchingStrategy(HSI) -- committed vectors tests/golden/ref_0600_*_hsi.npz (tests/golden/make_golden.py).
+Same bars as the RGB path: everything bit-exact except aggregation (<= 2e-6 relative)."""
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+GOLD = Path(__file__).parent / "golden"
+AGG_RTOL = 2e-6
+
+
+@pytest.fixture(scope="module")
+def crop():
+    return np.load(GOLD / "ref_0600_crop_160x96_d32_hsi.npz")
+
+
+def _runner(z):
+    import tea_stereo_matching_b200 as t
+    from tea_stereo_matching_b200 import _native as N
+
+    return t.StageRunner(z["left"], z["right"], int(z["max_disparity"]), model=t.ColorModel.HSI), N
+
+
+def test_hsi_preprocessing_arms_and_cost_bit_exact(crop):
+    run, N = _runner(crop)
+    run.run(N.STAGE_PREP | N.STAGE_INIT)
+    for v in range(2):
+        assert np.array_equal(run.image(v), crop[f"pre{v}"]), ("bgr2hsi + computeGaussMedian", v)
+        assert np.array_equal(run.arms(v), crop[f"arms{v}"]), ("arms", v)
+        assert np.array_equal(run.volume(v), crop[f"vol_init{v}"]), ("initial cost", v)
+    run.close()
+
+
+def test_hsi_aggregate_scanline_and_refinement_stage_by_stage(crop):
+    run, N = _runner(crop)
+    run.run(N.STAGE_PREP)
+    for v in range(2):
+        run.set_volume(v, crop[f"vol_init{v}"])
+    run.run(N.STAGE_AGGREGATE)
+    for v in range(2):
+        got, want = run.volume(v), crop[f"vol_agg{v}"]
+        assert np.max(np.abs(got - want) / np.maximum(np.abs(want), 1e-6)) <= AGG_RTOL, v
+        run.set_volume(v, want)
+    run.run(N.STAGE_SCANLINE)
+    for v in range(2):
+        assert np.array_equal(run.volume(v), crop[f"vol_scan{v}"]), ("scanline", v)
+        assert np.array_equal(run.wta(v), crop[f"wta{v}"].astype(np.int32)), ("wta", v)
+    run.run(N.STAGE_LRC)
+    assert np.array_equal(run.disp(), crop["lrc"].astype(np.int32))
+    for i in range(5):
+        run.run(N.STAGE_VOTE, i)
+        assert np.array_equal(run.disp(), crop[f"vote{i}"].astype(np.int32)), ("vote", i)
+    run.run(N.STAGE_INTERP)
+    assert np.array_equal(run.disp(), crop["interp"].astype(np.int32))
+    run.run(N.STAGE_DISCONT)
+    assert np.array_equal(run.disp(), crop["discont"].astype(np.int32))
+    run.run(N.STAGE_SUBPIXEL)
+    assert np.array_equal(run.final(), crop["final"])
+    run.close()
+
+
+def test_hsi_default_constructed_matcher_end_to_end(pair_0600):
+    """A default-constructed ADCensus IS the HSI model (ADCensus.cpp:409-420)."""
+    import tea_stereo_matching_b200 as t
+
+    left, right = pair_0600
+    want = np.load(GOLD / "ref_0600_320x180_d48_hsi.npz")["final"]
+    m = t.ADCensus()
+    m.setMinMaxDisparity(0, 48)
+    got = m.compute(left, right)
+    diff = np.abs(got.astype(np.float64) - want)
+    assert (diff > 1).mean() <= 1e-3 and (diff > 0.05).mean() <= 1e-3
+    m.setMatchingStrategy(t.ColorModel.HSI, True, False)
+    with pytest.raises(t.ADCensusError):
+        m.compute(left, right)  # ROI / mask modes are not built
