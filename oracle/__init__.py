@@ -182,6 +182,18 @@ class Ref:
             raise RuntimeError(f"ref_adcensus_compute failed rc={rc}")
         return out, sec.value
 
+    def compute_ex(self, left, right, max_disp: int, model: str = "RGB", roi: bool = False, mask: bool = False, offset: int = 0,
+                   serial: bool = True):
+        """ADCensus::compute with the full matching strategy; serial = one OpenMP thread (deterministic)."""
+        left, right = _check_pair(left, right)
+        H, W, _ = left.shape
+        out = np.empty((H, W), np.float32)
+        rc = self.lib.ref_adcensus_compute_ex(_p(left), _p(right), H, W, 0, max_disp, {"RGB": 0, "HSI": 1}[model], int(roi), int(mask),
+                                              int(offset), int(serial), _p(out))
+        if rc != 0:
+            raise RuntimeError(f"ref_adcensus_compute_ex failed rc={rc}")
+        return out
+
     def ad_census_pairs(self, left, right, y, xl, xr):
         left, right = _check_pair(left, right)
         H, W, _ = left.shape

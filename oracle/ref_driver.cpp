@@ -235,6 +235,37 @@ int ref_adcensus_compute(const uint8_t* left, const uint8_t* right, int H, int W
     }
 }
 
+/* The public entry point with the full matching strategy (model 0 RGB / 1 HSI, roi, mask, offset); serial != 0 runs it
+ * with one OpenMP thread (deterministic scanline).  maxD is what setMinMaxDisparity gets; ROI / mask modes replace it by
+ * W / 2 inside compute (ADCensus.cpp:339-340). */
+int ref_adcensus_compute_ex(const uint8_t* left, const uint8_t* right, int H, int W, int minD, int maxD, int model, int roi,
+                            int mask, int offset, int serial, float* out)
+{
+    const int nthreads = omp_get_max_threads();
+    try {
+        stereo::ADCensus a;
+        a.setMatchingStrategy(model == 1 ? stereo::ColorModel::HSI : stereo::ColorModel::RGB, roi != 0, mask != 0);
+        a.setMinMaxDisparity(minD, maxD);
+        a.setOffset(offset);
+        cv::Mat L(cv::Size(W, H), CV_8UC3), R(cv::Size(W, H), CV_8UC3), D;
+        std::memcpy(L.data, left, (size_t)H * W * 3);
+        std::memcpy(R.data, right, (size_t)H * W * 3);
+        if (serial) omp_set_num_threads(1);
+        a.compute(L, R, D);
+        if (serial) omp_set_num_threads(nthreads);
+        if (out) std::memcpy(out, D.data, (size_t)H * W * sizeof(float));
+        return 0;
+    } catch (const std::string& e) {
+        omp_set_num_threads(nthreads);
+        std::cerr << "[ref] " << e << std::endl;
+        return -1;
+    } catch (const std::exception& e) {
+        omp_set_num_threads(nthreads);
+        std::cerr << "[ref] " << e.what() << std::endl;
+        return -2;
+    }
+}
+
 /* Integer AD sums and census counts for n (y, xL, xR) pairs, straight from the
  * reference's computeRGBADCost / computeRGBCensusCost (ADCensus.cpp:426,454).
  * ad3 = round(ad * 3) is the integer |dB|+|dG|+|dR|. */

@@ -214,10 +214,16 @@ void prep_scan_tables(const Launcher& L, const Dims& d, const uint8_t* flags_lef
 // bgr2hsi (:1429-1473) is a pure function of the 24-bit pixel with sqrtf / acosf inside; the host evaluates it
 // for all 2^24 inputs once per process with its own libm (tsm_capi.cu) -- the same trick as the exp() tables --
 // so the conversion is a table lookup and bit-identical to the reference.
-__global__ void k_hsi_lookup(const uint32_t* __restrict__ bgr4, const uint32_t* __restrict__ lut, uint32_t* __restrict__ hsi4, size_t n)
+// `filter` (ROI mode, bgr2hsi(..., true), :1463-1470): pixels whose hue is >= 60 or <= 10 become (0, 0, 0).
+__global__ void k_hsi_lookup(const uint32_t* __restrict__ bgr4, const uint32_t* __restrict__ lut, uint32_t* __restrict__ hsi4, size_t n,
+                             int filter)
 {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) hsi4[i] = lut[bgr4[i] & 0xffffffu];
+    if (i >= n) return;
+    uint32_t v = lut[bgr4[i] & 0xffffffu];
+    const uint32_t h = v & 0xffu;
+    if (filter && (h >= 60u || h <= 10u)) v = 0u;
+    hsi4[i] = v;
 }
 
 // computeGaussMedian(src, dst, 3) (:1475-1499): filter2D with the 3x3 kernel [1 2 1; 2 4 2; 1 2 1] / 16
@@ -257,14 +263,18 @@ __global__ void k_gauss_median(const uint32_t* __restrict__ src, uint32_t* __res
 }
 
 void prep_view(const Launcher& L, const Dims& d, int view, const uint8_t* img, uint32_t* img4, uint64_t* census,
-               uchar4* arms, uint32_t* desc_h, uint32_t* desc_v, uint8_t* flags, const ModelParams& mp, const uint32_t* hsi_lut)
+               uchar4* arms, uint32_t* desc_h, uint32_t* desc_v, uint8_t* flags, const ModelParams& mp, const uint32_t* hsi_lut,
+               bool roi)
 {
     const size_t npx = d.npx();
     dim3 b(32, 8), g((d.W + 31) / 32, (d.H + 7) / 8);
     k_pack_bgrx<<<(unsigned)((npx + 255) / 256), 256, 0, L.stream>>>(img, img4, npx);
-    if (mp.hsi) {
+    if (mp.hsi && roi) {  // ADCensus.cpp:354-360: hue-filtered HSI, no Gauss-median
+        k_hsi_lookup<<<(unsigned)((npx + 255) / 256), 256, 0, L.stream>>>(img4, hsi_lut, img4, npx, 1);
+        L.count(1);
+    } else if (mp.hsi) {  // :361-370
         uint32_t* tmp = reinterpret_cast<uint32_t*>(arms);  // free until k_arms, same size
-        k_hsi_lookup<<<(unsigned)((npx + 255) / 256), 256, 0, L.stream>>>(img4, hsi_lut, tmp, npx);
+        k_hsi_lookup<<<(unsigned)((npx + 255) / 256), 256, 0, L.stream>>>(img4, hsi_lut, tmp, npx, 0);
         k_gauss_median<<<g, b, 0, L.stream>>>(tmp, img4, d.H, d.W);
         L.count(2);
     }
@@ -276,6 +286,24 @@ void prep_view(const Launcher& L, const Dims& d, int view, const uint8_t* img, u
                                       reinterpret_cast<float*>(desc_v + d.desc_v_words()), d.H, d.W, d.Wd(), d.Hd());
     k_flags<<<g, b, 0, L.stream>>>(img4, flags, d.H, d.W, mp);
     L.count(5);
+}
+
+__global__ void k_roi_finish(float* __restrict__ fin, const uint8_t* __restrict__ bgr, size_t n, float offset)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float d = fin[i];
+    if (d > 0.f) d = __fadd_rn(d, offset);  // disparityOffset: d + offset (int -> float), ADCensus.cpp:1422-1423
+    const bool black = bgr[3 * i] == 0 && bgr[3 * i + 1] == 0 && bgr[3 * i + 2] == 0;
+    if ((black && d > 0.f) || d == 0.f) d = -1.f;  // :397-400
+    fin[i] = d;
+}
+
+void roi_finish(const Launcher& L, const Dims& d, float* fin, const uint8_t* left_bgr, int offset)
+{
+    const size_t n = d.npx();
+    k_roi_finish<<<(unsigned)((n + 255) / 256), 256, 0, L.stream>>>(fin, left_bgr, n, (float)offset);
+    L.count(1);
 }
 
 }  // namespace tsm

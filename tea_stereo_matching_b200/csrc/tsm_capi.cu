@@ -48,6 +48,8 @@ struct tsm_ctx {
     Buf v_vote, v_lowcnt, v_off, v_mark, v_start, v_sums, v_flat, v_stash;
     Buf e_gray, e_blur, e_mag, e_gx, e_gy, e_map, e_edges, e_hist, e_lut, e_changed;
     Buf tab_ad, tab_c, agg_ctr, tab_ad_hsi, hsi_lut;
+    bool roi = false;      // ROI matching mode: maxD = W / 2, HSI hue filter instead of the Gauss-median, offset + final marking
+    int roi_offset = 0;
     bool hsi = false, hsi_ready = false;  // colour model of the current configuration; HSI tables uploaded
     Buf k_in, k_out, k_tab, k_range;  // disparity consumers: staged input map, output, colour table, min/max
     int fin_H = 0, fin_W = 0;        // geometry of the map in `fin` (0 = none yet)
@@ -137,11 +139,14 @@ int check_cfg(tsm_ctx* c, const tsm_adcensus_config* cfg, int H, int W)
     if ((long long)cfg->min_disparity * cfg->max_disparity < 0 || cfg->min_disparity >= cfg->max_disparity)
         return fail(c, TSM_E_ARG, "[ADCensus] Set MinMaxDisparity error.");
     if (cfg->offset < 0) return fail(c, TSM_E_ARG, "[ADCensus] Offset must be positive.");  // ADCensus.cpp:325-326
-    if (cfg->roi_matching || cfg->mask_matching)
-        return fail(c, TSM_E_UNSUPPORTED, "[ADCensus] ROI / mask matching modes are not built yet (SURVEY 8(f) row f1)");
+    if (cfg->mask_matching)
+        return fail(c, TSM_E_UNSUPPORTED, "[ADCensus] mask matching mode is not built yet (SURVEY 8(f) row f1)");
     if (cfg->min_disparity != 0)
         return fail(c, TSM_E_UNSUPPORTED, "[ADCensus] min_disparity != 0 is not built yet");
-    if (cfg->max_disparity + 1 > 512) return fail(c, TSM_E_UNSUPPORTED, "[ADCensus] more than 512 disparity levels");
+    // ROI mode searches the whole half width: maxDisparity = width / 2 at compute time (ADCensus.cpp:339-340)
+    if ((cfg->roi_matching ? W / 2 : cfg->max_disparity) + 1 > 512)
+        return fail(c, TSM_E_UNSUPPORTED, "[ADCensus] more than 512 disparity levels");
+    if (cfg->roi_matching && W / 2 < 1) return fail(c, TSM_E_ARG, "[ADCensus] Image error.");
     if (H <= 0 || W <= 0) return fail(c, TSM_E_ARG, "[ADCensus] Image error.");  // ADCensus.cpp:332-333
     if (cfg->max_disparity > 65535) return fail(c, TSM_E_ARG, "[ADCensus] max_disparity too large");
     return TSM_OK;
@@ -251,7 +256,9 @@ int ensure_arena(tsm_ctx* c, const tsm_adcensus_config* cfg, int H, int W)
     c->hsi = cfg->color_model == TSM_COLOR_HSI;
     if (c->hsi && (rc = ensure_hsi_tables(c))) return rc;
     Dims d;
-    d.set(H, W, cfg->max_disparity - cfg->min_disparity + 1);
+    c->roi = cfg->roi_matching != 0;
+    c->roi_offset = cfg->offset;
+    d.set(H, W, (c->roi ? W / 2 : cfg->max_disparity) - cfg->min_disparity + 1);
     c->dm = d;
     c->cfg = *cfg;
     const size_t npx = d.npx();
@@ -346,7 +353,7 @@ int run_stages(tsm_ctx* c, int mask, int arg)
         for (int k = 0; k < 2; ++k)
             prep_view(L, d, k, (const uint8_t*)c->img[k].p, (uint32_t*)c->img4[k].p, (uint64_t*)c->census[k].p,
                       (uchar4*)c->arms[k].p, (uint32_t*)c->desc_h[k].p, (uint32_t*)c->desc_v[k].p, (uint8_t*)c->flags[k].p,
-                      model_params(c->hsi), (const uint32_t*)c->hsi_lut.p);
+                      model_params(c->hsi), (const uint32_t*)c->hsi_lut.p, c->roi);
         prep_scan_tables(L, d, (const uint8_t*)c->flags[0].p, (const uint8_t*)c->flags[1].p, (uint32_t*)c->tflags[0].p,
                          (uint32_t*)c->tflags[1].p);
     }
@@ -420,6 +427,7 @@ int run_stages(tsm_ctx* c, int mask, int arg)
     if (mask & TSM_STAGE_SUBPIXEL) {
         ScopedStage s(c, "subpixel");
         subpixel(L, d, (const int32_t*)c->disp[c->disp_cur].p, vl.vol, (float*)c->ftmp.p, (float*)c->fin.p);
+        if (c->roi) roi_finish(L, d, (float*)c->fin.p, (const uint8_t*)c->img[0].p, c->roi_offset);
         c->fin_H = d.H;
         c->fin_W = d.W;
     }

@@ -13,6 +13,7 @@ Run in the dev container (needs /root/reference and python cv2 4.13.0):
   samples (the full volumes are 11 MB each).
 * ref_0600_crop_160x96_d32_hsi.npz / ref_0600_320x180_d48_hsi.npz -- the same with the HSI colour model
   (bgr2hsi + computeGaussMedian preprocessing; a 160x96 crop carries the full volumes).
+* ref_0600_crop_160x96_roi.npz -- final maps of the public compute() in ROI matching mode (RGB + offset 5, HSI + offset 3).
 * ref_synth_96x128_d24.npz -- same for a tiny synthetic pair (synth_v1 seed 7), with the
   full volumes (small enough) so the CUDA kernels can be checked cell by cell on a box
   without /root/reference.
@@ -81,6 +82,13 @@ def main():
                         **stage_dict(st, True))
     st = ref.run(Ls, Rs, 48, serial_scanline=True, model="HSI")
     np.savez_compressed(OUT / "ref_0600_320x180_d48_hsi.npz", max_disparity=48, pre0=st.pre[0], pre1=st.pre[1], **stage_dict(st, False))
+
+    # ROI matching mode (row f1): maxD = W / 2, offset, final -1 marking (black left pixels); public compute, one thread
+    Lr, Rr = Lc.copy(), Rc.copy()
+    Lr[20:30, 40:60] = 0
+    np.savez_compressed(OUT / "ref_0600_crop_160x96_roi.npz", left=Lr, right=Rr,
+                        rgb_off5=ref.compute_ex(Lr, Rr, 64, "RGB", roi=True, offset=5),
+                        hsi_off3=ref.compute_ex(Lr, Rr, 64, "HSI", roi=True, offset=3))
 
     sl, sr = synth_v1(96, 128, 24, seed=7)
     st = ref.run(sl, sr, 24, serial_scanline=True)

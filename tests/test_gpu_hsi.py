@@ -72,6 +72,22 @@ def test_hsi_default_constructed_matcher_end_to_end(pair_0600):
     got = m.compute(left, right)
     diff = np.abs(got.astype(np.float64) - want)
     assert (diff > 1).mean() <= 1e-3 and (diff > 0.05).mean() <= 1e-3
-    m.setMatchingStrategy(t.ColorModel.HSI, True, False)
+    m.setMatchingStrategy(t.ColorModel.HSI, False, True)
     with pytest.raises(t.ADCensusError):
-        m.compute(left, right)  # ROI / mask modes are not built
+        m.compute(left, right)  # mask matching is not built
+
+
+def test_roi_matching_mode_rgb_and_hsi():
+    """setMatchingStrategy(model, roiMatching=True): maxD = W / 2, setOffset, final -1 marking (ADCensus.cpp:339-403)."""
+    import tea_stereo_matching_b200 as t
+
+    z = np.load(GOLD / "ref_0600_crop_160x96_roi.npz")
+    for model, off, key in ((t.ColorModel.RGB, 5, "rgb_off5"), (t.ColorModel.HSI, 3, "hsi_off3")):
+        m = t.ADCensus()
+        m.setMatchingStrategy(model, True, False)
+        m.setMinMaxDisparity(0, 64)  # replaced by W / 2 = 80 inside compute
+        m.setOffset(off)
+        got, want = m.compute(z["left"], z["right"]), z[key]
+        assert np.array_equal(got < 0, want < 0), key  # same invalid pixels (incl. the blacked-out block)
+        diff = np.abs(got.astype(np.float64) - want)
+        assert (diff > 1).mean() <= 1e-3 and (diff > 0.05).mean() <= 1e-3, key
