@@ -33,7 +33,7 @@ enum tsm_status {
     TSM_E_ARG = 1,         /* bad argument (NULL, size mismatch, empty image, min>=max, ...) */
     TSM_E_CUDA = 2,        /* CUDA runtime / launch failure, or no device */
     TSM_E_OOM = 3,         /* device or pinned-host allocation failed */
-    TSM_E_UNSUPPORTED = 4, /* valid in the reference but not built yet (mask matching, minD != 0, Dn > 512) */
+    TSM_E_UNSUPPORTED = 4, /* valid in the reference but not built yet (minD != 0, Dn > 512) */
     TSM_E_STATE = 5        /* call sequence error (wait without enqueue, tap before run, ...) */
 };
 
@@ -52,7 +52,8 @@ typedef struct tsm_adcensus_config {
     int32_t color_model;   /* tsm_color_model (the reference default-constructs HSI, ADCensus.cpp:409-420) */
     int32_t roi_matching;  /* != 0: ROI mode -- max_disparity is replaced by W / 2 (ADCensus.cpp:339-340), HSI images are hue-filtered
                               instead of Gauss-median filtered (:354-360), offset is added and black left pixels are marked -1 (:388-403) */
-    int32_t mask_matching; /* != 0 -> TSM_E_UNSUPPORTED */
+    int32_t mask_matching; /* != 0: mask mode -- black pixels (0,0,0) are holes: cost 2 (ADCensus.cpp:551-555), census term dropped
+                              (:459, 481), zero / clipped arms (:625, 673), skipped scanline steps (:824, 862); plus all of the ROI mode */
     int32_t offset;        /* setOffset: added to every positive disparity in ROI mode (disparityOffset, :1415-1427) */
 } tsm_adcensus_config;
 

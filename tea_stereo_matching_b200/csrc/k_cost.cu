@@ -59,7 +59,9 @@ __device__ __forceinline__ int census_count(const Sig& f, const Sig& m)
 // COST_TX = left pixels per CTA: 64, or 32 when the shared tile [COST_TX][Dn] would otherwise leave one CTA per SM
 // HSI: adCost = min(|dH|, 255 - |dH|) * 1 + |dS| * 2.5 + |dI| * 2.5 (computeHSIADCost, :439-452) is exact in fp32,
 // so the table is indexed with 2 * adCost = 2 hd + 5 (ds + di) <= 2804.
-template <int COST_TX, bool HSI>
+// MASK (mask matching): a black centre pixel makes the census cost +inf, i.e. its exp() term 0 (:459, 481, 518); a
+// cell whose OWN view's pixel is black is 2.f (:551-555) -- applied when the tile is flushed, per view.
+template <int COST_TX, bool HSI, bool MASK>
 __global__ void __launch_bounds__(COST_WARPS * 32, TSM_COST_MINB)
 k_cost_init(Dims dm, ViewPtrs vl, ViewPtrs vr, const float* __restrict__ g_tab_ad, const float* __restrict__ g_tab_c)
 {
@@ -150,7 +152,9 @@ k_cost_init(Dims dm, ViewPtrs vl, ViewPtrs vr, const float* __restrict__ g_tab_a
                     ad3 = min((int)__vsadu4(f[j].pix, m.pix), TAB_AD_USED - 1);
                 }
                 const int cen = census_count(f[j], m);
-                float cost = __fsub_rn(__fsub_rn(2.f, tab_ad[ad3]), tab_c[cen]);
+                float ec = tab_c[cen];
+                if (MASK && (f[j].pix == 0u || m.pix == 0u)) ec = 0.f;
+                float cost = __fsub_rn(__fsub_rn(2.f, tab_ad[ad3]), ec);
                 cost = (fok[j] && mok) ? cost : 2.f;
                 if ((unsigned)d < (unsigned)Dn) tj[j][e] = cost;
             }
@@ -166,8 +170,10 @@ k_cost_init(Dims dm, ViewPtrs vl, ViewPtrs vr, const float* __restrict__ g_tab_a
         for (int j = warp; j < npix; j += COST_WARPS) {
             const float4* src = reinterpret_cast<const float4*>(ctile + j * DnP);
             float4* dst = reinterpret_cast<float4*>(vl.vol.main + (row + x0 + j) * Dm);
-            for (int q = lane; q < nq; q += 32) dst[q] = src[q];
-            if (lane < r) vl.vol.tail[(row + x0 + j) * Rp + lane] = ctile[j * DnP + Dm + lane];
+            const bool hole = MASK && vl.img4[row + x0 + j] == 0u;
+            const float4 two = make_float4(2.f, 2.f, 2.f, 2.f);
+            for (int q = lane; q < nq; q += 32) dst[q] = hole ? two : src[q];
+            if (lane < r) vl.vol.tail[(row + x0 + j) * Rp + lane] = hole ? 2.f : ctile[j * DnP + Dm + lane];
         }
     }
     // ---- right view: diagonals of the tile.  Right pixel c gets d in [x0 - c, x0 + npix - 1 - c] (clipped to [0, Dn)),
@@ -184,9 +190,10 @@ k_cost_init(Dims dm, ViewPtrs vl, ViewPtrs vr, const float* __restrict__ g_tab_a
             const float* src = ctile + (c - x0) * DnP;  // + d * stride
             float* const pm = rmain + (size_t)c * Dm;
             float* const pt = rtail + (size_t)c * Rp;
+            const bool hole = MASK && vr.img4[row + c] == 0u;
             for (int d = d0 + lane; d <= d1; d += 32) {
                 float* q = d < Dm ? pm + d : pt + d;
-                *q = src[d * stride];
+                *q = hole ? 2.f : src[d * stride];
             }
         }
     }
@@ -205,7 +212,7 @@ k_cost_init(Dims dm, ViewPtrs vl, ViewPtrs vr, const float* __restrict__ g_tab_a
     }
 }
 
-template <int COST_TX, bool HSI>
+template <int COST_TX, bool HSI, bool MASK>
 static void launch_cost(const Launcher& L, const Dims& d, const ViewPtrs& left, const ViewPtrs& right, const float* d_tab_ad,
                         const float* d_tab_census)
 {
@@ -214,24 +221,27 @@ static void launch_cost(const Launcher& L, const Dims& d, const ViewPtrs& left, 
     const size_t smem = (size_t)(tab_ad_n + TAB_C_PAD) * 4 + 13 * ncol * 4 + (size_t)COST_TX * dnp * 4;
     static size_t smem_set = 0;
     if (smem > smem_set) {
-        cudaFuncSetAttribute(k_cost_init<COST_TX, HSI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(k_cost_init<COST_TX, HSI, MASK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         smem_set = smem;
     }
     dim3 grid((d.W + COST_TX - 1) / COST_TX, d.H);
-    k_cost_init<COST_TX, HSI><<<grid, COST_WARPS * 32, smem, L.stream>>>(d, left, right, d_tab_ad, d_tab_census);
+    k_cost_init<COST_TX, HSI, MASK><<<grid, COST_WARPS * 32, smem, L.stream>>>(d, left, right, d_tab_ad, d_tab_census);
     L.count(1);
 }
 
 void cost_init(const Launcher& L, const Dims& d, const ViewPtrs& left, const ViewPtrs& right, const float* d_tab_ad,
-               const float* d_tab_census, bool hsi)
+               const float* d_tab_census, bool hsi, bool mask)
 {
-    if (hsi) {
-        if (d.Dn > 256) launch_cost<32, true>(L, d, left, right, d_tab_ad, d_tab_census);
-        else launch_cost<64, true>(L, d, left, right, d_tab_ad, d_tab_census);
+    const bool narrow = d.Dn > 256;
+#define TSM_COST_CASE(TX, H, M) launch_cost<TX, H, M>(L, d, left, right, d_tab_ad, d_tab_census)
+    if (mask) {
+        if (hsi) { if (narrow) TSM_COST_CASE(32, true, true); else TSM_COST_CASE(64, true, true); }
+        else { if (narrow) TSM_COST_CASE(32, false, true); else TSM_COST_CASE(64, false, true); }
     } else {
-        if (d.Dn > 256) launch_cost<32, false>(L, d, left, right, d_tab_ad, d_tab_census);
-        else launch_cost<64, false>(L, d, left, right, d_tab_ad, d_tab_census);
+        if (hsi) { if (narrow) TSM_COST_CASE(32, true, false); else TSM_COST_CASE(64, true, false); }
+        else { if (narrow) TSM_COST_CASE(32, false, false); else TSM_COST_CASE(64, false, false); }
     }
+#undef TSM_COST_CASE
 }
 
 }  // namespace tsm

@@ -85,6 +85,7 @@ __device__ __forceinline__ int arm_length(const uint32_t* __restrict__ img4, int
     // Literal walk of computeLimit: ADCensus.cpp:609-658.  RGB: max-channel colour difference; HSI: the
     // intensity tests (the hue and saturation assignments before them are overwritten, :631-645).
     const uint32_t p = img4[(size_t)y * W + x];
+    if (mp.mask && p == 0u) return 0;  // computeLimits, ADCensus.cpp:672-677
     int d = 1;
     int y1 = y + dy, x1 = x + dx;
     uint32_t p2 = p;
@@ -93,6 +94,10 @@ __device__ __forceinline__ int arm_length(const uint32_t* __restrict__ img4, int
         bool color_cond = true, wlimit_cond = true, fcolor_cond = true;
         while (color_cond && wlimit_cond && fcolor_cond && inside) {
             const uint32_t p1 = img4[(size_t)y1 * W + x1];
+            if (mp.mask && p1 == 0u) {  // the arm stops in front of a masked pixel (:624-629)
+                d++;
+                break;
+            }
             int cd, cd2;
             if (mp.hsi) {
                 cd = abs((int)((p >> 16) & 0xffu) - (int)((p1 >> 16) & 0xffu));
@@ -166,6 +171,7 @@ __global__ void k_flags(const uint32_t* __restrict__ img4, uint8_t* __restrict__
     uint8_t f = 0;
     if (y > 0 && (mp.hsi ? hue_diff_u32(c, img4[p - W]) : color_diff_u32(c, img4[p - W])) < mp.sim) f |= 1;
     if (x > 0 && (mp.hsi ? hue_diff_u32(c, img4[p - 1]) : color_diff_u32(c, img4[p - 1])) < mp.sim) f |= 2;
+    if (mp.mask && c == 0u) f |= 4;  // mask matching: a black pixel (ADCensus.cpp:824, 862)
     flags[p] = f;
 }
 
@@ -174,7 +180,8 @@ __global__ void k_flags(const uint32_t* __restrict__ img4, uint8_t* __restrict__
 //   bits 0..15: flag bit `plane` of the OTHER image at (y, c + s*32k), k = 0..K-1, 0 outside the image --
 //               a lane of the scanline warp that handles d = lane + 32k gets all its K similarity
 //               bits from the one word at column x + s*lane;
-//   bit 31    : flag bit `plane` of the OWN image at (y, c).
+//   bit 31    : flag bit `plane` of the OWN image at (y, c);
+//   bits 30/29: mask matching only, see below.
 __global__ void k_scan_table(const uint8_t* __restrict__ fown, const uint8_t* __restrict__ foth, uint32_t* __restrict__ stab,
                              int H, int W, int Wp, int s, int K)
 {
@@ -194,6 +201,13 @@ __global__ void k_scan_table(const uint8_t* __restrict__ fown, const uint8_t* __
         const unsigned f = fown[(size_t)y * W + c];
         tv |= (f & 1u) << 31;
         th |= ((f >> 1) & 1u) << 31;
+        // mask matching: a step whose PREDECESSOR is black is skipped.  (y, c) is the flag pixel of the step = the
+        // later of (pixel, predecessor): bit 30 = black predecessor of a forward step, bit 29 of a backward step.
+        const unsigned own_black = (f >> 2) & 1u;
+        tv |= own_black << 29;
+        th |= own_black << 29;
+        if (y > 0) tv |= ((fown[(size_t)(y - 1) * W + c] >> 2) & 1u) << 30;
+        if (c > 0) th |= ((fown[(size_t)y * W + c - 1] >> 2) & 1u) << 30;
     }
     stab[(size_t)y * Wp + cx] = tv;
     stab[(size_t)H * Wp + (size_t)y * Wp + cx] = th;

@@ -99,8 +99,13 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t a)
 // the pixel changed (m != 0).
 template <int K>
 __device__ __forceinline__ bool scan_step(float (&prev)[K], const float (&cur)[K], unsigned tf, unsigned own, int lane,
-                                          const ScanParams& sp)
+                                          const ScanParams& sp, bool hole = false)
 {
+    if (hole) {  // mask matching: the predecessor is a masked pixel, the step is skipped (ADCensus.cpp:824, 862)
+#pragma unroll
+        for (int k = 0; k < K; ++k) prev[k] = cur[k];
+        return false;
+    }
     unsigned mb = __float_as_uint(prev[0]);
 #pragma unroll
     for (int k = 1; k < K; ++k) mb = min(mb, __float_as_uint(prev[k]));
@@ -261,7 +266,7 @@ __device__ __forceinline__ void scan_dir(float (&prev)[K], const Vol& vol, const
         if (lane == 0 && i + SC_NST < count) issue(st + dep, bar);
         advance_producer();
 
-        const bool changed = scan_step<K>(prev, cur, tw & 0xffffu, ow >> 31, lane, sp);
+        const bool changed = scan_step<K>(prev, cur, tw & 0xffffu, ow >> 31, lane, sp, ((ow >> (dir > 0 ? 30 : 29)) & 1u) != 0);
         if (changed && do_store) store_vec<K>(dst, tdst, prev, lane, has_tail, lastvalid);
         dst += vstep;
         tdst += wstep;

@@ -48,7 +48,8 @@ struct tsm_ctx {
     Buf v_vote, v_lowcnt, v_off, v_mark, v_start, v_sums, v_flat, v_stash;
     Buf e_gray, e_blur, e_mag, e_gx, e_gy, e_map, e_edges, e_hist, e_lut, e_changed;
     Buf tab_ad, tab_c, agg_ctr, tab_ad_hsi, hsi_lut;
-    bool roi = false;      // ROI matching mode: maxD = W / 2, HSI hue filter instead of the Gauss-median, offset + final marking
+    bool mask = false;     // mask matching mode: black pixels are holes (cost 2, zero arms, skipped scanline steps)
+    bool roi = false;      // ROI / mask matching mode: maxD = W / 2, HSI hue filter instead of the Gauss-median, offset + final marking
     int roi_offset = 0;
     bool hsi = false, hsi_ready = false;  // colour model of the current configuration; HSI tables uploaded
     Buf k_in, k_out, k_tab, k_range;  // disparity consumers: staged input map, output, colour table, min/max
@@ -139,14 +140,12 @@ int check_cfg(tsm_ctx* c, const tsm_adcensus_config* cfg, int H, int W)
     if ((long long)cfg->min_disparity * cfg->max_disparity < 0 || cfg->min_disparity >= cfg->max_disparity)
         return fail(c, TSM_E_ARG, "[ADCensus] Set MinMaxDisparity error.");
     if (cfg->offset < 0) return fail(c, TSM_E_ARG, "[ADCensus] Offset must be positive.");  // ADCensus.cpp:325-326
-    if (cfg->mask_matching)
-        return fail(c, TSM_E_UNSUPPORTED, "[ADCensus] mask matching mode is not built yet (SURVEY 8(f) row f1)");
     if (cfg->min_disparity != 0)
         return fail(c, TSM_E_UNSUPPORTED, "[ADCensus] min_disparity != 0 is not built yet");
     // ROI mode searches the whole half width: maxDisparity = width / 2 at compute time (ADCensus.cpp:339-340)
-    if ((cfg->roi_matching ? W / 2 : cfg->max_disparity) + 1 > 512)
+    if (((cfg->roi_matching || cfg->mask_matching) ? W / 2 : cfg->max_disparity) + 1 > 512)
         return fail(c, TSM_E_UNSUPPORTED, "[ADCensus] more than 512 disparity levels");
-    if (cfg->roi_matching && W / 2 < 1) return fail(c, TSM_E_ARG, "[ADCensus] Image error.");
+    if ((cfg->roi_matching || cfg->mask_matching) && W / 2 < 1) return fail(c, TSM_E_ARG, "[ADCensus] Image error.");
     if (H <= 0 || W <= 0) return fail(c, TSM_E_ARG, "[ADCensus] Image error.");  // ADCensus.cpp:332-333
     if (cfg->max_disparity > 65535) return fail(c, TSM_E_ARG, "[ADCensus] max_disparity too large");
     return TSM_OK;
@@ -256,7 +255,8 @@ int ensure_arena(tsm_ctx* c, const tsm_adcensus_config* cfg, int H, int W)
     c->hsi = cfg->color_model == TSM_COLOR_HSI;
     if (c->hsi && (rc = ensure_hsi_tables(c))) return rc;
     Dims d;
-    c->roi = cfg->roi_matching != 0;
+    c->roi = cfg->roi_matching != 0 || cfg->mask_matching != 0;  // both: maxD = W / 2, hue filter, offset, final marking
+    c->mask = cfg->mask_matching != 0;
     c->roi_offset = cfg->offset;
     d.set(H, W, (c->roi ? W / 2 : cfg->max_disparity) - cfg->min_disparity + 1);
     c->dm = d;
@@ -353,13 +353,13 @@ int run_stages(tsm_ctx* c, int mask, int arg)
         for (int k = 0; k < 2; ++k)
             prep_view(L, d, k, (const uint8_t*)c->img[k].p, (uint32_t*)c->img4[k].p, (uint64_t*)c->census[k].p,
                       (uchar4*)c->arms[k].p, (uint32_t*)c->desc_h[k].p, (uint32_t*)c->desc_v[k].p, (uint8_t*)c->flags[k].p,
-                      model_params(c->hsi), (const uint32_t*)c->hsi_lut.p, c->roi);
+                      model_params(c->hsi, c->mask), (const uint32_t*)c->hsi_lut.p, c->roi);
         prep_scan_tables(L, d, (const uint8_t*)c->flags[0].p, (const uint8_t*)c->flags[1].p, (uint32_t*)c->tflags[0].p,
                          (uint32_t*)c->tflags[1].p);
     }
     if (mask & TSM_STAGE_INIT) {
         ScopedStage s(c, "cost_init");
-        cost_init(L, d, vl, vr, (const float*)(c->hsi ? c->tab_ad_hsi.p : c->tab_ad.p), (const float*)c->tab_c.p, c->hsi);
+        cost_init(L, d, vl, vr, (const float*)(c->hsi ? c->tab_ad_hsi.p : c->tab_ad.p), (const float*)c->tab_c.p, c->hsi, c->mask);
     }
     if (mask & TSM_STAGE_AGGREGATE) {
         ScopedStage s(c, "aggregate");

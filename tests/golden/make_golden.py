@@ -90,6 +90,15 @@ def main():
                         rgb_off5=ref.compute_ex(Lr, Rr, 64, "RGB", roi=True, offset=5),
                         hsi_off3=ref.compute_ex(Lr, Rr, 64, "HSI", roi=True, offset=3))
 
+    # mask matching mode: black pixels are holes in BOTH images (a masked foreground, as the mode is meant for)
+    Lm, Rm = Lc.copy(), Rc.copy()
+    Lm[:, :24] = 0; Lm[60:75, 70:100] = 0; Lm[5, 50] = 0
+    Rm[:, :10] = 0; Rm[58:74, 60:88] = 0; Rm[40, 120] = 0
+    np.savez_compressed(OUT / "ref_0600_crop_160x96_mask.npz", left=Lm, right=Rm,
+                        rgb_off2=ref.compute_ex(Lm, Rm, 64, "RGB", mask=True, offset=2),
+                        hsi_off0=ref.compute_ex(Lm, Rm, 64, "HSI", mask=True, offset=0),
+                        rgb_roi_mask=ref.compute_ex(Lm, Rm, 64, "RGB", roi=True, mask=True, offset=1))
+
     sl, sr = synth_v1(96, 128, 24, seed=7)
     st = ref.run(sl, sr, 24, serial_scanline=True)
     np.savez_compressed(OUT / "ref_synth_96x128_d24.npz", left=sl, right=sr, max_disparity=24, **stage_dict(st, True))

@@ -72,9 +72,9 @@ def test_hsi_default_constructed_matcher_end_to_end(pair_0600):
     got = m.compute(left, right)
     diff = np.abs(got.astype(np.float64) - want)
     assert (diff > 1).mean() <= 1e-3 and (diff > 0.05).mean() <= 1e-3
-    m.setMatchingStrategy(t.ColorModel.HSI, False, True)
+    m.setMinMaxDisparity(4, 48)
     with pytest.raises(t.ADCensusError):
-        m.compute(left, right)  # mask matching is not built
+        m.compute(left, right)  # min_disparity != 0 is not built
 
 
 def test_roi_matching_mode_rgb_and_hsi():
@@ -89,5 +89,23 @@ def test_roi_matching_mode_rgb_and_hsi():
         m.setOffset(off)
         got, want = m.compute(z["left"], z["right"]), z[key]
         assert np.array_equal(got < 0, want < 0), key  # same invalid pixels (incl. the blacked-out block)
+        diff = np.abs(got.astype(np.float64) - want)
+        assert (diff > 1).mean() <= 1e-3 and (diff > 0.05).mean() <= 1e-3, key
+
+
+def test_mask_matching_mode_rgb_and_hsi():
+    """setMatchingStrategy(model, roi, maskMatching=True): black pixels are holes (cost 2, zero arms, skipped scanline
+    steps, census term dropped), plus everything of the ROI mode (ADCensus.cpp:339-403, 459, 481, 551, 625, 673, 824, 862)."""
+    import tea_stereo_matching_b200 as t
+
+    z = np.load(GOLD / "ref_0600_crop_160x96_mask.npz")
+    for model, roi, off, key in ((t.ColorModel.RGB, False, 2, "rgb_off2"), (t.ColorModel.HSI, False, 0, "hsi_off0"),
+                                 (t.ColorModel.RGB, True, 1, "rgb_roi_mask")):
+        m = t.ADCensus()
+        m.setMatchingStrategy(model, roi, True)
+        m.setMinMaxDisparity(0, 64)
+        m.setOffset(off)
+        got, want = m.compute(z["left"], z["right"]), z[key]
+        assert np.array_equal(got < 0, want < 0), key
         diff = np.abs(got.astype(np.float64) - want)
         assert (diff > 1).mean() <= 1e-3 and (diff > 0.05).mean() <= 1e-3, key

@@ -189,11 +189,11 @@ def test_unsupported_modes_are_explicit(pair_0600, native_lib):
 
     left, right = pair_0600
     m = t.ADCensus()
-    for model in (t.ColorModel.RGB, t.ColorModel.HSI):  # mask matching: SURVEY 8(f) row f1, not built
-        m.setMatchingStrategy(model, False, True)
-        with pytest.raises(t.ADCensusError) as e:
-            m.compute(left, right)
-        assert e.value.status == N.TSM_E_UNSUPPORTED
+    wide = np.zeros((8, 1100, 3), np.uint8)  # ROI / mask modes search W / 2 + 1 = 551 > 512 levels
+    m.setMatchingStrategy(t.ColorModel.RGB, True, False)
+    with pytest.raises(t.ADCensusError) as e:
+        m.compute(wide, wide)
+    assert e.value.status == N.TSM_E_UNSUPPORTED
     m.setMatchingStrategy(t.ColorModel.RGB, False, False)
     m.setMinMaxDisparity(4, 48)  # min_disparity != 0
     with pytest.raises(t.ADCensusError) as e:
