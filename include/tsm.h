@@ -49,7 +49,7 @@ enum tsm_color_model { TSM_COLOR_RGB = 0, TSM_COLOR_HSI = 1 };
 typedef struct tsm_adcensus_config {
     int32_t min_disparity; /* only 0 is built; others -> TSM_E_UNSUPPORTED */
     int32_t max_disparity; /* Dn = max - min + 1 cost planes (ADCensus.cpp:345) */
-    int32_t color_model;   /* tsm_color_model (the reference default-constructs HSI, ADCensus.cpp:409-420) */
+    int32_t color_model;   /* enum tsm_color_model; the reference default-constructs HSI (ADCensus.cpp:409-420) */
     int32_t roi_matching;  /* != 0: ROI mode -- max_disparity is replaced by W / 2 (ADCensus.cpp:339-340), HSI images are hue-filtered
                               instead of Gauss-median filtered (:354-360), offset is added and black left pixels are marked -1 (:388-403) */
     int32_t mask_matching; /* != 0: mask mode -- black pixels (0,0,0) are holes: cost 2 (ADCensus.cpp:551-555), census term dropped
