@@ -59,3 +59,24 @@ def test_batched_enqueue_matches_single(pair_0600):
             m.enqueue(left, right)
         for k, m in enumerate(ms):
             assert np.array_equal(m.wait(), ref), f"iteration {it}, context {k}"
+
+
+def test_context_reuse_across_geometries_and_models(pair_0600):
+    """One context, arena grown once: a big RGB pair, then smaller pairs / other models must equal fresh contexts."""
+    import tea_stereo_matching_b200 as t
+    from tea_stereo_matching_b200.synth import synth_v1
+
+    left, right = pair_0600
+    big = synth_v1(200, 700, 192, seed=41)
+    jobs = [(big[0], big[1], 192, t.ColorModel.RGB), (left, right, 48, t.ColorModel.RGB), (left, right, 48, t.ColorModel.HSI),
+            (left[10:120, 30:250].copy(), right[10:120, 30:250].copy(), 70, t.ColorModel.RGB), (left, right, 31, t.ColorModel.HSI),
+            (big[0], big[1], 128, t.ColorModel.RGB)]
+    shared = t.ADCensus()
+    for l, r, D, model in jobs:
+        shared.setMatchingStrategy(model)
+        shared.setMinMaxDisparity(0, D)
+        got = shared.compute(l, r)
+        fresh = t.ADCensus()
+        fresh.setMatchingStrategy(model)
+        fresh.setMinMaxDisparity(0, D)
+        assert np.array_equal(got, fresh.compute(l, r)), (l.shape, D, model)
