@@ -191,10 +191,11 @@ k_cost_init(Dims dm, ViewPtrs vl, ViewPtrs vr, const float* __restrict__ g_tab_a
             float* const pm = rmain + (size_t)c * Dm;
             float* const pt = rtail + (size_t)c * Rp;
             const bool hole = MASK && vr.img4[row + c] == 0u;
-            for (int d = d0 + lane; d <= d1; d += 32) {
-                float* q = d < Dm ? pm + d : pt + d;
-                *q = hole ? 2.f : src[d * stride];
-            }
+            // main part and tail part as two plain loops: one pointer select per element cost more address
+            // arithmetic than the copy itself
+            const int dm_last = min(d1, Dm - 1);
+            for (int d = d0 + lane; d <= dm_last; d += 32) pm[d] = hole ? 2.f : src[d * stride];
+            for (int d = max(d0, Dm) + lane; d <= d1; d += 32) pt[d] = hole ? 2.f : src[d * stride];
         }
     }
     // ---- right view, cells whose left pixel c + d lies beyond the image: 2.f (ADCensus.cpp:562-566).  Last tile of the row.
