@@ -4,6 +4,7 @@
 #include "tsm_common.cuh"
 #include <algorithm>
 #include <mutex>
+#include <thread>
 #include <limits.h>
 #include <math.h>
 #include <stdarg.h>
@@ -151,8 +152,6 @@ int check_cfg(tsm_ctx* c, const tsm_adcensus_config* cfg, int H, int W)
     return TSM_OK;
 }
 
-// Host-side LUTs with the host's own expf, in the reference's expression order:
-//   expf(-((float)s / 3.f) / 10.f)  (ADCensus.cpp:435, :518)  and  expf(-(float)n / 30.f).
 // bgr2hsi (ADCensus.cpp:1429-1473) for every 24-bit pixel, evaluated ONCE per process with the host's libm in the
 // reference's expression order (float arithmetic, the hue division in double because CV_PI is a double literal,
 // float -> uchar conversions truncate).  Index = B | G << 8 | R << 16, value = H | S << 8 | I << 16.
@@ -163,7 +162,8 @@ static const std::vector<uint32_t>& hsi_table()
     std::call_once(once, [] {
         tab.resize(1u << 24);
         const double two_pi = 2 * 3.1415926535897932384626433832795;  // 2 * CV_PI
-        for (uint32_t i = 0; i < (1u << 24); ++i) {
+        auto fill = [&](uint32_t lo, uint32_t hi) {
+        for (uint32_t i = lo; i < hi; ++i) {
             const volatile float blueValue = (float)(i & 0xff) / 255.f, greenValue = (float)((i >> 8) & 0xff) / 255.f,
                                  redValue = (float)((i >> 16) & 0xff) / 255.f;
             const volatile float sum0 = blueValue + greenValue;
@@ -195,6 +195,12 @@ static const std::vector<uint32_t>& hsi_table()
             const uint32_t H = (unsigned char)hi, S = (unsigned char)si, I = (unsigned char)ii;
             tab[i] = H | (S << 8) | (I << 16);
         }
+        };
+        const unsigned nt = std::max(1u, std::min(8u, std::thread::hardware_concurrency()));
+        std::vector<std::thread> pool;
+        const uint32_t per = (1u << 24) / nt;
+        for (unsigned t = 0; t < nt; ++t) pool.emplace_back(fill, t * per, t + 1 == nt ? (1u << 24) : (t + 1) * per);
+        for (auto& th : pool) th.join();
     });
     return tab;
 }
@@ -220,6 +226,8 @@ int ensure_hsi_tables(tsm_ctx* c)
     return TSM_OK;
 }
 
+// Host-side LUTs with the host's own expf, in the reference's expression order:
+//   expf(-((float)s / 3.f) / 10.f)  (ADCensus.cpp:435, :518)  and  expf(-(float)n / 30.f).
 int ensure_tables(tsm_ctx* c)
 {
     if (c->tables_ready) return TSM_OK;
