@@ -6,19 +6,24 @@
 // by the cross-window size (:743-749).  The reference adds in fp32 in ascending order;
 // here every (line, d) chain walks its line once, keeps a running fp64 prefix sum P and
 // emits  P[o+b+1] - P[o-a]  with a lag of 33 (= max arm); the last 72 prefixes live in a
-// shared-memory ring.  fp64 prefix differences stay within ~4e-7 relative of the
-// reference's sequential fp32 sums after all 4 iterations (fp32 prefixes do not;
-// SURVEY 0.6).  Each cell is read once and written once per pass, in place.
+// ring in shared memory or in tensor memory.  fp64 prefix differences stay within ~4e-7
+// relative of the reference's sequential fp32 sums after all 4 iterations (fp32 prefixes do
+// not).  Each cell is read once and written once per pass, in place.
 //
-// Thread mapping (k_agg_walk): one thread owns TWO adjacent disparities (d, d+1) of one
+// Thread mapping (walk_line): one thread owns TWO adjacent disparities (d, d+1) of one
 // line: 8-byte global accesses, 16-byte ring entries, and the per-step index arithmetic
 // (ring slots, arm decode, pointers) is paid once per two cells.  Lanes run over d, so a
-// warp reads 256 contiguous bytes per step.  Inputs do not depend on the recurrence:
-// they are loaded AGG_PF steps ahead into a register ring, so every warp keeps AGG_PF
-// 256-byte loads in flight and the only loop-carried dependency is the fp64 prefix add.
-// The main loop is unrolled AGG_PF times and the ring length is a multiple of AGG_PF,
-// so ring slots of the pushes are compile-time offsets and the wrap test runs once per
-// AGG_PF steps.
+// warp reads 256 contiguous bytes per step.  Inputs do not depend on the recurrence: they
+// are loaded in batches of AGG_PF steps into NB register buffers, NB-1 batches ahead of
+// their use, so the only loop-carried dependency is the fp64 prefix add.  A batch is
+// processed in sub-blocks (pushes, ring loads, outputs) so that the ring round trip is
+// paid once per four steps.  The main loop is unrolled NB*AGG_PF times and the ring length
+// is a multiple of AGG_PF, so the ring slots of the pushes are compile-time offsets.
+//
+// Kernels: k_agg_persist (rings in shared AND tensor memory, one persistent CTA per SM, warps
+// pull work items from a global counter; needs Dm % 64 == 0 = every BASELINE configuration),
+// k_agg_walk (shared-memory rings only, any Dm), k_agg_small (lines shorter than 66),
+// k_agg_tail_h (horizontal passes of the tail part: staged row + block scan).
 //
 // Division: the reference divides the fp32 sum by (float)N with an IEEE fp32 divide
 // (ADCensus.cpp:747).  The walk multiplies by the correctly rounded reciprocal stored next to the
