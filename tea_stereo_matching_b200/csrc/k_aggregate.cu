@@ -432,7 +432,8 @@ k_agg_persist(Dims dm, ViewPtrs v0, ViewPtrs v1, int tm_warps, unsigned* ctr)
     extern __shared__ __align__(16) unsigned char ring_raw[];  // [AGG_RING][AGH_SM_THREADS] x double2
     __shared__ uint32_t tm_base;
     const int nlines = VERT ? dm.W : dm.H, len = VERT ? dm.H : dm.W;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // warp index through a lane-0 broadcast: tells the compiler it is warp-uniform (TMEM addresses live in uniform registers)
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
     if (tm_warps > 0) {
         if (warp == 0) {
             asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(

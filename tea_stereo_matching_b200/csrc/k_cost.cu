@@ -94,7 +94,7 @@ k_cost_init(Dims dm, ViewPtrs vl, ViewPtrs vr, const float* __restrict__ g_tab_a
     }
     __syncthreads();
 
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31, warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // lane-0 broadcast: provably warp-uniform for the compiler
     const int nchunk = (Dn + COST_J - 1 + 31) / 32;
     const int DnP = (Dn + 3) & ~3;
     float* ctile = reinterpret_cast<float*>(mw + 13 * ncol);  // [COST_TX][DnP], 16-byte aligned

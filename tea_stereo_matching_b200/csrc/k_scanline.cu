@@ -295,7 +295,9 @@ k_scanline(Dims dm, ViewPtrs v0, ViewPtrs v1, ScanParams sp, int32_t* wta0, int3
     extern __shared__ __align__(128) unsigned char scan_smem[];
     const int view = blockIdx.y;
     const ViewPtrs& v = view ? v1 : v0;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // warp index through a lane-0 broadcast: the compiler then knows it (and the line, the pointers and the stage
+    // addresses derived from it) is warp-uniform and keeps the bulk-copy operands in uniform registers
+    const int lane = threadIdx.x & 31, warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
     const int line = blockIdx.x * SCAN_WARPS + warp;
     const int nlines = VERT ? dm.W : dm.H, len = VERT ? dm.H : dm.W;
     if (line >= nlines) return;
