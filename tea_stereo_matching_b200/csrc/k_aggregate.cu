@@ -663,32 +663,32 @@ static void launch_walk(const Launcher& L, const Dims& d, const ViewPtrs& left, 
     const AggMix& mix = agg_mix();
     if (!VERT && d.tail() > 0 && len >= AGG_LAG + 1 + AGG_U) {
         const size_t smem = (size_t)(d.W + 1) * sizeof(double2);
-        static size_t smem_set = 48 * 1024;
-        if (smem > smem_set) {
+        static PerDevice smem_set;
+        if (smem > 48 * 1024 && smem > smem_set.cur()) {
             cudaFuncSetAttribute(k_agg_tail_h<NORM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            smem_set = smem;
+            smem_set.cur() = smem;
         }
         dim3 grid((unsigned)d.H, 2, (unsigned)((d.tail() + 1) / 2));
         k_agg_tail_h<NORM><<<grid, AGT_BLOCK, smem, L.stream>>>(d, left, right);
         L.count(1);
     }
     if (len >= AGG_LAG + 1 + AGG_U && AGG_NC == 2 && d.Dm >= 64 && d.Dm % 64 == 0 && mix.persist) {
-        static bool attr_set = false;
-        static int n_sm = 0;
-        if (!attr_set) {
+        static PerDevice sm_count;  // doubles as "attribute set on this device"
+        if (!sm_count.cur()) {
             cudaFuncSetAttribute(k_agg_persist<VERT, NORM>, cudaFuncAttributeMaxDynamicSharedMemorySize, AGH_SMEM);
-            int dev = 0;
+            int dev = 0, n = 0;
             cudaGetDevice(&dev);
-            cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-            attr_set = true;
+            cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+            sm_count.cur() = (size_t)n;
         }
+        const int n_sm = (int)sm_count.cur();
         const int tm = mix.tm[VERT], sm = mix.sm[VERT];
         k_agg_persist<VERT, NORM><<<n_sm, 32 * (tm + sm), AGH_SMEM, L.stream>>>(d, left, right, tm, ctr);
     } else if (len >= AGG_LAG + 1 + AGG_U) {
-        static bool attr_set = false;
-        if (!attr_set) {
+        static PerDevice attr_set;
+        if (!attr_set.cur()) {
             cudaFuncSetAttribute(k_agg_walk<VERT, NORM>, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemRing<AGG_BLOCK>::SPAN);
-            attr_set = true;
+            attr_set.cur() = 1;
         }
         const int nb_main = (int)((nl * (d.Dm / AGG_NC) + AGG_BLOCK - 1) / AGG_BLOCK);
         const int nb_tail = VERT ? (int)((nl * ((d.tail() + AGG_NC - 1) / AGG_NC) + AGG_BLOCK - 1) / AGG_BLOCK) : 0;
@@ -696,11 +696,11 @@ static void launch_walk(const Launcher& L, const Dims& d, const ViewPtrs& left, 
         if (grid.x == 0) return;  // Dn < 32, horizontal pass: the tail kernel did all of it
         k_agg_walk<VERT, NORM><<<grid, AGG_BLOCK, SmemRing<AGG_BLOCK>::SPAN, L.stream>>>(d, left, right, 0, nb_main);
     } else {
-        static bool attr_set = false;
+        static PerDevice attr_set;
         const size_t smem = (size_t)AGS_RING * AGS_BLOCK * sizeof(double);
-        if (!attr_set) {
+        if (!attr_set.cur()) {
             cudaFuncSetAttribute(k_agg_small<VERT, NORM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            attr_set = true;
+            attr_set.cur() = 1;
         }
         const int nb_main = (int)((nl * d.Dm + AGS_BLOCK - 1) / AGS_BLOCK);
         const int nb_tail = (int)((nl * d.tail() + AGS_BLOCK - 1) / AGS_BLOCK);

@@ -220,10 +220,10 @@ static void launch_cost(const Launcher& L, const Dims& d, const ViewPtrs& left, 
     constexpr int tab_ad_n = HSI ? kTabAdHsi + 1 : kTabAdRgb;
     const size_t ncol = (size_t)((COST_TX + d.Dn - 1 + 3) & ~3), dnp = (size_t)((d.Dn + 3) & ~3);
     const size_t smem = (size_t)(tab_ad_n + TAB_C_PAD) * 4 + 13 * ncol * 4 + (size_t)COST_TX * dnp * 4;
-    static size_t smem_set = 0;
-    if (smem > smem_set) {
+    static PerDevice smem_set;
+    if (smem > smem_set.cur()) {
         cudaFuncSetAttribute(k_cost_init<COST_TX, HSI, MASK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        smem_set = smem;
+        smem_set.cur() = smem;
     }
     dim3 grid((d.W + COST_TX - 1) / COST_TX, d.H);
     k_cost_init<COST_TX, HSI, MASK><<<grid, COST_WARPS * 32, smem, L.stream>>>(d, left, right, d_tab_ad, d_tab_census);

@@ -715,15 +715,16 @@ cudaError_t discontinuity_adjustment(const Launcher& L, const Dims& d, const int
     k_canny_nms<<<g, b, 0, L.stream>>>(s.gx, s.gy, s.mag, s.map, d.H, d.W, kCannyLow, kCannyHigh);
     L.count(5);
     {
-        static int coop_blocks = 0;
-        if (coop_blocks == 0) {
+        static PerDevice coop;
+        if (coop.cur() == 0) {
             int dev = 0, sms = 0, per_sm = 0;
             cudaGetDevice(&dev);
             cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_canny_hysteresis, HY_T * HY_T, 0);
-            coop_blocks = sms * (per_sm > 0 ? 1 : 0);
-            if (coop_blocks == 0) return cudaErrorLaunchOutOfResources;
+            coop.cur() = (size_t)(sms * (per_sm > 0 ? 1 : 0));
+            if (coop.cur() == 0) return cudaErrorLaunchOutOfResources;
         }
+        const int coop_blocks = (int)coop.cur();
         cudaMemsetAsync(s.changed, 0, 3 * sizeof(int32_t), L.stream);
         uint8_t* map = s.map;
         int H = d.H, W = d.W;

@@ -357,14 +357,11 @@ static void launch_scan(const Launcher& L, const Dims& d, const ViewPtrs& left, 
 {
     const unsigned warp_bytes = ((unsigned)(SC_NST * sp.stage_bytes + SC_NST * 8) + 127u) & ~127u;
     const size_t smem = (size_t)SCAN_WARPS * warp_bytes;
-    static size_t smem_set[2] = {0, 0};
-    if (smem > smem_set[0]) {
+    static PerDevice smem_set;
+    if (smem > smem_set.cur()) {
         cudaFuncSetAttribute(k_scanline<K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        smem_set[0] = smem;
-    }
-    if (smem > smem_set[1]) {
         cudaFuncSetAttribute(k_scanline<K, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        smem_set[1] = smem;
+        smem_set.cur() = smem;
     }
     dim3 gv((d.W + SCAN_WARPS - 1) / SCAN_WARPS, 2), gh((d.H + SCAN_WARPS - 1) / SCAN_WARPS, 2);
     k_scanline<K, true><<<gv, SCAN_WARPS * 32, smem, L.stream>>>(d, left, right, sp, wta0, wta1);

@@ -80,3 +80,25 @@ def test_context_reuse_across_geometries_and_models(pair_0600):
         fresh.setMatchingStrategy(model)
         fresh.setMinMaxDisparity(0, D)
         assert np.array_equal(got, fresh.compute(l, r)), (l.shape, D, model)
+
+
+def test_two_devices_in_one_process(pair_0600):
+    """One process driving two GPUs: function attributes (dynamic shared memory limits) are per device."""
+    import tea_stereo_matching_b200 as t
+    from tea_stereo_matching_b200 import _native as N
+
+    import ctypes as C
+
+    n = C.c_int32(0)
+    N.lib().tsm_device_count(C.byref(n))
+    if n.value < 2:
+        pytest.skip("needs two GPUs")
+    left, right = pair_0600
+    outs = []
+    for dev in (0, 1):
+        for model in (t.ColorModel.RGB, t.ColorModel.HSI):
+            m = t.ADCensus(device=dev)
+            m.setMatchingStrategy(model)
+            m.setMinMaxDisparity(0, 64)
+            outs.append(m.compute(left, right))
+    assert np.array_equal(outs[0], outs[2]) and np.array_equal(outs[1], outs[3])
