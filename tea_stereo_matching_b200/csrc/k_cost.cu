@@ -156,7 +156,11 @@ k_cost_init(Dims dm, ViewPtrs vl, ViewPtrs vr, const float* __restrict__ g_tab_a
                 if (MASK && (f[j].pix == 0u || m.pix == 0u)) ec = 0.f;
                 float cost = __fsub_rn(__fsub_rn(2.f, tab_ad[ad3]), ec);
                 cost = (fok[j] && mok) ? cost : 2.f;
-                if ((unsigned)d < (unsigned)Dn) tj[j][e] = cost;
+                // predicated store (as PTX: the compiler otherwise builds a reconvergence region around each of the four)
+                asm volatile("{ .reg .pred p; setp.lt.u32 p, %2, %3; @p st.shared.f32 [%0], %1; }" ::"r"(
+                                 (uint32_t)__cvta_generic_to_shared(tj[j] + e)),
+                             "f"(cost), "r"((unsigned)d), "r"((unsigned)Dn)
+                             : "memory");
             }
         }
     }
