@@ -246,19 +246,20 @@ void stereo::ADCensus::compute(const std::vector<cv::Mat>& leftImages, const std
 		if (rc == TSM_E_ARG) throw(std::string(tsm_last_error(c)));
 		throw std::runtime_error(tsm_last_error(c));
 	};
-	for (size_t i = 0; i <= n; ++i) {
+	// pair i runs on context i & 1; it is collected right before pair i + 2 needs that context, so two pairs stay in flight
+	for (size_t i = 0; i < n + 2; ++i) {
+		if (i >= 2) {
+			tsm_ctx* c = impl->ctx[i & 1].h;
+			cv::Mat out(leftImages[i - 2].rows, leftImages[i - 2].cols, CV_32FC1);
+			int rc = tsm_adcensus_wait(c, (float*)out.data, out.step);
+			if (rc != TSM_OK) fail(c, rc);
+			disparities[i - 2] = out;
+		}
 		if (i < n) {
 			tsm_ctx* c = impl->ctx[i & 1].h;
 			int rc = tsm_adcensus_enqueue(c, &cfg, leftImages[i].data, leftImages[i].step, rightImages[i].data, rightImages[i].step,
 				leftImages[i].rows, leftImages[i].cols);
 			if (rc != TSM_OK) fail(c, rc);
-		}
-		if (i >= 1) {
-			tsm_ctx* c = impl->ctx[(i - 1) & 1].h;
-			cv::Mat out(leftImages[i - 1].rows, leftImages[i - 1].cols, CV_32FC1);
-			int rc = tsm_adcensus_wait(c, (float*)out.data, out.step);
-			if (rc != TSM_OK) fail(c, rc);
-			disparities[i - 1] = out;
 		}
 	}
 }
