@@ -82,6 +82,14 @@ __device__ __forceinline__ void tma_load_1d(uint32_t dst, const void* src, unsig
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
+// One elected lane of the (converged) warp: unlike `lane == 0` the compiler knows that exactly one thread is
+// active inside, so the uniform-register bulk-copy instructions need no per-thread loop around them.
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred;
+    asm volatile("{ .reg .pred P; elect.sync _|P, 0xffffffff; selp.u32 %0, 1, 0, P; }" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ float lds_f32(uint32_t a)
 {
     float v;
@@ -222,7 +230,7 @@ __device__ __forceinline__ void scan_dir(float (&prev)[K], const Vol& vol, const
     {
         const int npro = count < SC_NST ? count : SC_NST;
         for (int i = 0; i < npro; ++i) {
-            if (lane == 0) issue(pipe.stage0 + islot * stage_bytes, pipe.bar0 + islot * 8u);
+            if (elect_one()) issue(pipe.stage0 + islot * stage_bytes, pipe.bar0 + islot * 8u);
             advance_producer();
             islot = islot + 1 == SC_NST ? 0 : islot + 1;
         }
@@ -263,7 +271,7 @@ __device__ __forceinline__ void scan_dir(float (&prev)[K], const Vol& vol, const
         for (int k = 0; k < K; ++k) dep ^= __float_as_uint(cur[k]);
         dep &= (uint32_t)sp.zero;
         __syncwarp();  // every lane has read the stage
-        if (lane == 0 && i + SC_NST < count) issue(st + dep, bar);
+        if (i + SC_NST < count && elect_one()) issue(st + dep, bar);
         advance_producer();
 
         const bool changed = scan_step<K>(prev, cur, tw & 0xffffu, ow >> 31, lane, sp, ((ow >> (dir > 0 ? 30 : 29)) & 1u) != 0);
