@@ -25,7 +25,7 @@
 //
 // Inputs of the next pixels do not depend on the recurrence, so they are streamed by TMA:
 // lane 0 of every warp issues cp.async.bulk copies (the 128-byte aligned main part of the
-// pixel's cost vector, its tail chunk and a 144-byte window of the scan table) SC_NST steps
+// pixel's cost vector, its tail chunk and a 144-byte window of the scan table) NST steps
 // ahead into a per-warp shared-memory ring; each stage completes on its own mbarrier
 // (expect_tx bytes).  Completion is tracked by the mbarrier, not by register scoreboards,
 // so the loads really stay in flight across the shuffle / REDUX waits of the recurrence
@@ -41,10 +41,16 @@ namespace tsm {
 #define TSM_SCAN_WARPS 4
 #endif
 #ifndef TSM_SC_NST
-#define TSM_SC_NST 8
+#define TSM_SC_NST 0
 #endif
 constexpr int SCAN_WARPS = TSM_SCAN_WARPS;
-constexpr int SC_NST = TSM_SC_NST;    // TMA stages (steps in flight) per warp
+// TMA stages (steps in flight) per warp: 12 while a stage is small (K <= 8 registers = up to 256 disparities,
+// <= 1.2 KB per stage: measured 5.47 -> 5.31 ms against 8 stages at K = 7; 16 stages cost a CTA per SM and lose),
+// 8 for the wide vectors.  -DTSM_SC_NST=n overrides it for experiments.
+template <int K>
+struct ScanCfg {
+    static constexpr int NST = TSM_SC_NST ? TSM_SC_NST : (K <= 8 ? 12 : 8);
+};
 constexpr int SC_WIN = 36;   // scan-table words fetched per step (32 lanes + 16-byte alignment slack)
 
 struct ScanParams {
@@ -192,6 +198,7 @@ __device__ __forceinline__ void scan_dir(float (&prev)[K], const Vol& vol, const
                                          ScanPipe& pipe, int line, int first, int dir, int count, int sgn, int lane,
                                          bool has_tail, bool lastvalid, bool do_store, int32_t* wta_out, const ScanParams& sp)
 {
+    constexpr int SC_NST = ScanCfg<K>::NST;
     const int W = dm.W, Wp = dm.stab_pitch();
     const uint32_t* tab = stab + (size_t)(VERT ? 0 : 1) * dm.H * Wp;
     const unsigned main_bytes = (unsigned)dm.Dm * 4u, tail_bytes = (unsigned)sp.tail_bytes;
@@ -314,6 +321,7 @@ k_scanline(Dims dm, ViewPtrs v0, ViewPtrs v1, ScanParams sp, int32_t* wta0, int3
     const bool has_tail = dm.Rp != 0;
     const bool lastvalid = !has_tail || lane < dm.tail();
 
+    constexpr int SC_NST = ScanCfg<K>::NST;
     ScanPipe pipe;
     const uint32_t warp_bytes = SC_NST * (unsigned)sp.stage_bytes + SC_NST * 8u;
     pipe.stage0 = (uint32_t)__cvta_generic_to_shared(scan_smem) + warp * ((warp_bytes + 127u) & ~127u);
@@ -363,6 +371,7 @@ template <int K>
 static void launch_scan(const Launcher& L, const Dims& d, const ViewPtrs& left, const ViewPtrs& right, const ScanParams& sp,
                         int32_t* wta0, int32_t* wta1)
 {
+    constexpr int SC_NST = ScanCfg<K>::NST;
     const unsigned warp_bytes = ((unsigned)(SC_NST * sp.stage_bytes + SC_NST * 8) + 127u) & ~127u;
     const size_t smem = (size_t)SCAN_WARPS * warp_bytes;
     static PerDevice smem_set;
