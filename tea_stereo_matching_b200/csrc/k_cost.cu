@@ -28,7 +28,10 @@
 
 namespace tsm {
 
-constexpr int COST_WARPS = 8;
+#ifndef TSM_COST_WARPS
+#define TSM_COST_WARPS 8
+#endif
+constexpr int COST_WARPS = TSM_COST_WARPS;
 constexpr int COST_J = 4;       // fixed pixels per warp iteration
 constexpr int TAB_C_N = kTabCensus;
 constexpr int TAB_C_PAD = 194;  // RGB: (766 + 194) * 4 = 3840 bytes, HSI: (2806 + 194) * 4 = 12000: what follows stays 16-byte aligned
