@@ -382,7 +382,7 @@ __device__ __forceinline__ ChainSel select_chain(const Dims& dm, const ViewPtrs&
 // 64-thread CTAs, 73.7 KB of ring each, 3 CTAs = 6 warps per SM.
 template <bool VERT, bool NORM>
 __global__ void __launch_bounds__(AGG_BLOCK)
-k_agg_walk(Dims dm, ViewPtrs v0, ViewPtrs v1, int wsel, int nb_main)
+k_agg_walk(Dims dm, ViewPtrs v0, ViewPtrs v1, int nb_main)
 {
     extern __shared__ __align__(16) unsigned char ring_raw[];  // [AGG_RING][AGG_BLOCK] x double2
     const ViewPtrs& v = blockIdx.y ? v1 : v0;
@@ -584,7 +584,7 @@ k_agg_tail_h(Dims dm, ViewPtrs v0, ViewPtrs v1)
 constexpr int AGS_BLOCK = 128, AGS_RING = 2 * kMaxArm + 2;
 template <bool VERT, bool NORM>
 __global__ void __launch_bounds__(AGS_BLOCK)
-k_agg_small(Dims dm, ViewPtrs v0, ViewPtrs v1, int wsel, int nb_main)
+k_agg_small(Dims dm, ViewPtrs v0, ViewPtrs v1, int nb_main)
 {
     extern __shared__ double sring[];  // [AGS_RING][AGS_BLOCK]
     const ViewPtrs& v = blockIdx.y ? v1 : v0;
@@ -694,7 +694,7 @@ static void launch_walk(const Launcher& L, const Dims& d, const ViewPtrs& left, 
         const int nb_tail = VERT ? (int)((nl * ((d.tail() + AGG_NC - 1) / AGG_NC) + AGG_BLOCK - 1) / AGG_BLOCK) : 0;
         dim3 grid((unsigned)(nb_main + nb_tail), 2);
         if (grid.x == 0) return;  // Dn < 32, horizontal pass: the tail kernel did all of it
-        k_agg_walk<VERT, NORM><<<grid, AGG_BLOCK, SmemRing<AGG_BLOCK>::SPAN, L.stream>>>(d, left, right, 0, nb_main);
+        k_agg_walk<VERT, NORM><<<grid, AGG_BLOCK, SmemRing<AGG_BLOCK>::SPAN, L.stream>>>(d, left, right, nb_main);
     } else {
         static PerDevice attr_set;
         const size_t smem = (size_t)AGS_RING * AGS_BLOCK * sizeof(double);
@@ -705,7 +705,7 @@ static void launch_walk(const Launcher& L, const Dims& d, const ViewPtrs& left, 
         const int nb_main = (int)((nl * d.Dm + AGS_BLOCK - 1) / AGS_BLOCK);
         const int nb_tail = (int)((nl * d.tail() + AGS_BLOCK - 1) / AGS_BLOCK);
         dim3 grid((unsigned)(nb_main + nb_tail), 2);
-        k_agg_small<VERT, NORM><<<grid, AGS_BLOCK, smem, L.stream>>>(d, left, right, 0, nb_main);
+        k_agg_small<VERT, NORM><<<grid, AGS_BLOCK, smem, L.stream>>>(d, left, right, nb_main);
     }
     L.count(1);
 }
