@@ -104,26 +104,44 @@ int tsm_adcensus_enqueue(tsm_ctx* ctx, const tsm_adcensus_config* cfg,
                          const uint8_t* left, size_t lstep, const uint8_t* right, size_t rstep, int H, int W);
 int tsm_adcensus_wait(tsm_ctx* ctx, float* disparity, size_t dstep);
 
+/* Rectify maps are uploaded once and reused from device memory.  Host addresses cannot identify map CONTENT (a
+ * reloaded map may land on the same addresses), so every entry point that takes maps also takes `map_generation`:
+ * an id the caller changes whenever the content behind the pointers changes (the facades bump a process-wide
+ * counter in EpipolarRectify::loadEpipolarRectifyMap, source/EpipolarRectify.cpp:32-44).  The device copy is reused
+ * only while generation, pointers, kind and size are all unchanged; map_generation == 0 uploads on every call. */
+
 /* ---- stereo::EpipolarRectify::rectify(left, right, L, R), source/EpipolarRectify.cpp:87-101 ----
  * One cv::remap(src, dst, map1, map2, INTER_LINEAR) (BORDER_CONSTANT 0) of a CV_8UC3
  * image: src is sH x sW (row stride sstep), dst is H x W (the map size, row stride dstep). */
 int tsm_remap(tsm_ctx* ctx, const uint8_t* src, size_t sstep, int sH, int sW,
-              const void* map1, const void* map2, int map_kind, int H, int W, uint8_t* dst, size_t dstep);
+              const void* map1, const void* map2, int map_kind, unsigned long long map_generation,
+              int H, int W, uint8_t* dst, size_t dstep);
 
 /* ---- stereo::EpipolarRectify::rectify(stereoImage, L, R), source/EpipolarRectify.cpp:68-85 ----
  * Crops the side-by-side frame (H x 2W) into halves [0,W) / [W,2W) and remaps each with its
  * own map pair (map00,map01) / (map10,map11). */
 int tsm_rectify_stereo(tsm_ctx* ctx, const uint8_t* stereo, size_t sstep, int H, int W,
                        const void* map00, const void* map01, const void* map10, const void* map11, int map_kind,
-                       uint8_t* left, size_t lstep, uint8_t* right, size_t rstep);
+                       unsigned long long map_generation, uint8_t* left, size_t lstep, uint8_t* right, size_t rstep);
 
 /* Fused rectify -> ADCensus (BASELINE config C4): the rectified pair never leaves
- * the device.  Maps are cached on the device keyed by their host pointers + size;
- * call tsm_invalidate_maps() if the host map contents change in place. */
+ * the device.  tsm_invalidate_maps() drops the device copies of the maps. */
 int tsm_rectify_adcensus(tsm_ctx* ctx, const tsm_adcensus_config* cfg,
                          const uint8_t* stereo, size_t sstep, int H, int W,
                          const void* map00, const void* map01, const void* map10, const void* map11, int map_kind,
-                         float* disparity, size_t dstep);
+                         unsigned long long map_generation, float* disparity, size_t dstep);
+/* Asynchronous form for batches: enqueue, then tsm_adcensus_wait() on the same ctx. */
+int tsm_rectify_adcensus_enqueue(tsm_ctx* ctx, const tsm_adcensus_config* cfg,
+                                 const uint8_t* stereo, size_t sstep, int H, int W,
+                                 const void* map00, const void* map01, const void* map10, const void* map11, int map_kind,
+                                 unsigned long long map_generation);
+/* The same on a device-resident side-by-side frame (row stride sstep bytes) and a packed device output, enqueued
+ * on the ctx stream without host synchronisation (the maps stay host pointers: they are uploaded once per
+ * generation).  This is the HBM-resident form bench.py times for config C4. */
+int tsm_rectify_adcensus_device(tsm_ctx* ctx, const tsm_adcensus_config* cfg,
+                                const uint8_t* d_stereo, size_t sstep, int H, int W,
+                                const void* map00, const void* map01, const void* map10, const void* map11, int map_kind,
+                                unsigned long long map_generation, float* d_disparity);
 void tsm_invalidate_maps(tsm_ctx* ctx);
 
 /* ---- stereo::EpipolarRectifyMap::compute, source/stereo_utils.cpp:157-169 ----

@@ -141,6 +141,9 @@ class Port:
     def threads(self) -> int:
         return int(self.lib.orc_omp_max_threads())
 
+    def set_threads(self, n: int) -> None:
+        self.lib.orc_omp_set_num_threads(int(n))
+
 
 class Ref:
     """ctypes view of oracle/_ref/libadcensus_ref.so (the unmodified reference)."""
@@ -210,6 +213,10 @@ class Ref:
     @property
     def threads(self) -> int:
         return int(self.lib.ref_omp_max_threads())
+
+    def set_threads(self, n: int) -> None:
+        """OpenMP threads of the following runs (torchrun exports OMP_NUM_THREADS=1 to its workers)."""
+        self.lib.ref_omp_set_num_threads(int(n))
 
 
 def have_ref() -> bool:

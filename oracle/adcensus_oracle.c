@@ -605,3 +605,4 @@ int orc_adcensus(const uint8_t* left, const uint8_t* right, int H, int W, int ma
 }
 
 int orc_omp_max_threads(void) { return omp_get_max_threads(); }
+void orc_omp_set_num_threads(int n) { if (n > 0) omp_set_num_threads(n); }

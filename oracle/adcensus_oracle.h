@@ -95,6 +95,7 @@ typedef struct OrcTaps {
 /* a1/a15: the whole path, ADCensus::compute (ADCensus.cpp:330-407) with RGB, D = 0..maxD. */
 int orc_adcensus(const uint8_t* left, const uint8_t* right, int H, int W, int maxD, OrcTaps* taps);
 int orc_omp_max_threads(void);
+void orc_omp_set_num_threads(int n);
 
 #ifdef __cplusplus
 }

@@ -286,5 +286,7 @@ int ref_ad_census_pairs(const uint8_t* left, const uint8_t* right, int H, int W,
 }
 
 int ref_omp_max_threads(void) { return omp_get_max_threads(); }
+/* Launchers such as torchrun export OMP_NUM_THREADS=1; a timing run sets the thread count it reports explicitly. */
+void ref_omp_set_num_threads(int n) { if (n > 0) omp_set_num_threads(n); }
 
 }  // extern "C"

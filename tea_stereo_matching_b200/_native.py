@@ -31,6 +31,7 @@ EXPORTS = [
     "tsm_version", "tsm_status_string", "tsm_last_error", "tsm_create", "tsm_create_on_stream", "tsm_destroy",
     "tsm_device_count", "tsm_synchronize", "tsm_adcensus_compute", "tsm_adcensus_compute_device",
     "tsm_adcensus_enqueue", "tsm_adcensus_wait", "tsm_remap", "tsm_rectify_stereo", "tsm_rectify_adcensus",
+    "tsm_rectify_adcensus_device", "tsm_rectify_adcensus_enqueue",
     "tsm_invalidate_maps", "tsm_stage_begin", "tsm_stage_run", "tsm_volume_pitch", "tsm_buffer_bytes", "tsm_tap",
     "tsm_poke", "tsm_set_profiling", "tsm_get_stage_times", "tsm_launch_count", "tsm_selftest",
     "tsm_init_undistort_rectify_map", "tsm_reproject_to_depth", "tsm_reproject_to_3d", "tsm_reproject_to_3d_q", "tsm_apply_colormap", "tsm_jet_colormap",
@@ -95,9 +96,12 @@ def lib() -> C.CDLL:
     L.tsm_adcensus_compute_device.argtypes = [vp, cfgp, vp, vp, i32, i32, vp]
     L.tsm_adcensus_enqueue.argtypes = [vp, cfgp, u8p, sz, u8p, sz, i32, i32]
     L.tsm_adcensus_wait.argtypes = [vp, vp, sz]
-    L.tsm_remap.argtypes = [vp, u8p, sz, i32, i32, vp, vp, i32, i32, i32, u8p, sz]
-    L.tsm_rectify_stereo.argtypes = [vp, u8p, sz, i32, i32, vp, vp, vp, vp, i32, u8p, sz, u8p, sz]
-    L.tsm_rectify_adcensus.argtypes = [vp, cfgp, u8p, sz, i32, i32, vp, vp, vp, vp, i32, vp, sz]
+    u64 = C.c_ulonglong
+    L.tsm_remap.argtypes = [vp, u8p, sz, i32, i32, vp, vp, i32, u64, i32, i32, u8p, sz]
+    L.tsm_rectify_stereo.argtypes = [vp, u8p, sz, i32, i32, vp, vp, vp, vp, i32, u64, u8p, sz, u8p, sz]
+    L.tsm_rectify_adcensus.argtypes = [vp, cfgp, u8p, sz, i32, i32, vp, vp, vp, vp, i32, u64, vp, sz]
+    L.tsm_rectify_adcensus_enqueue.argtypes = [vp, cfgp, u8p, sz, i32, i32, vp, vp, vp, vp, i32, u64]
+    L.tsm_rectify_adcensus_device.argtypes = [vp, cfgp, vp, sz, i32, i32, vp, vp, vp, vp, i32, u64, vp]
     L.tsm_invalidate_maps.argtypes = [vp]
     L.tsm_invalidate_maps.restype = None
     L.tsm_stage_begin.argtypes = [vp, cfgp, u8p, sz, u8p, sz, i32, i32]

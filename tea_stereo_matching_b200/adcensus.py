@@ -84,13 +84,18 @@ class Context:
         self.check(self._lib.tsm_set_profiling(self.handle, int(on)))
 
     def stage_times(self) -> dict:
-        n = C.c_int(32)
-        names = (C.c_char_p * 32)()
-        ms = (C.c_float * 32)()
+        """Device time per stage of the last profiled compute, ms.  Keys with a '/' ("aggregate/h_norm") are single
+        launches inside the stage named before the slash (summed over repeats; `<key>#n` counts them)."""
+        n = C.c_int(96)
+        names = (C.c_char_p * 96)()
+        ms = (C.c_float * 96)()
         self.check(self._lib.tsm_get_stage_times(self.handle, C.byref(n), names, ms))
         out: dict = {}
         for i in range(n.value):
-            out[names[i].decode()] = out.get(names[i].decode(), 0.0) + float(ms[i])
+            k = names[i].decode()
+            out[k] = out.get(k, 0.0) + float(ms[i])
+            if "/" in k:
+                out[k + "#n"] = out.get(k + "#n", 0) + 1
         return out
 
     def __del__(self):
@@ -156,8 +161,76 @@ class ADCensus:
         H, W = self._pending_shape
         if out is None:
             out = np.empty((H, W), np.float32)
+        elif (not isinstance(out, np.ndarray) or out.dtype != np.float32 or out.shape != (H, W) or out.strides[1] != 4
+              or out.strides[0] < 4 * W or not out.flags.writeable):
+            # the C side copies H rows of W floats at out.strides[0]: anything else would overrun the buffer
+            raise ADCensusError(f"[ADCensus] disparity buffer error (need a writeable float32 array of shape ({H}, {W}) with contiguous rows).")
         ctx = self.context
         ctx.check(ctx._lib.tsm_adcensus_wait(ctx.handle, _ptr(out), out.strides[0]))
+        return out
+
+    IN_FLIGHT = 3  # pairs in flight per device of computeBatch (measured best, profiles/README.md)
+
+    def computeBatch(self, leftImages, rightImages, devices=None) -> list:
+        """ADCensus::compute(vector, vector, vector&) of the C++ facade (cpp/stereo.h; the reference's batched signature
+        style, include/stereo.h:381): pair i runs on devices[i % N], one worker thread per device, IN_FLIGHT contexts each.
+        devices=None: this object's device; devices=-1: every visible device.  Sharding never changes a pair's bits."""
+        import threading
+
+        if len(leftImages) != len(rightImages):
+            raise ADCensusError("[ADCensus] Image error.")
+        pairs = [self._check_pair(l, r) for l, r in zip(leftImages, rightImages)]
+        n = len(pairs)
+        if n == 0:
+            return []
+        if devices is None:
+            devices = [self._device]
+        elif devices == -1:
+            cnt = C.c_int32(0)
+            if N.lib().tsm_device_count(C.byref(cnt)) != N.TSM_OK or cnt.value < 1:
+                raise ADCensusError(N.lib().tsm_last_error(None).decode(), N.TSM_E_CUDA)
+            devices = list(range(min(cnt.value, n)))
+        devices = list(devices)
+        pool = self.__dict__.setdefault("_batch_pool", {})
+        out: list = [None] * n
+        errors: list = []
+
+        def worker(w: int) -> None:
+            ms = pool.get(devices[w])
+            if ms is None:
+                ms = pool[devices[w]] = [ADCensus(device=devices[w]) for _ in range(self.IN_FLIGHT)]
+            for m in ms:
+                m._min, m._max, m._model, m._roi, m._mask, m._offset = (self._min, self._max, self._model, self._roi,
+                                                                        self._mask, self._offset)
+            mine = list(range(w, n, len(devices)))
+            K = len(ms)
+            slot: list = [None] * K
+            try:
+                for j in range(len(mine) + K):
+                    k = j % K
+                    if slot[k] is not None:
+                        i, slot[k] = slot[k], None
+                        out[i] = ms[k].wait()
+                    if j < len(mine):
+                        ms[k].enqueue(*pairs[mine[j]])
+                        slot[k] = mine[j]
+            except Exception as e:  # leave no context with an un-waited pair, then report
+                for k in range(K):
+                    if slot[k] is not None:
+                        try:
+                            ms[k].wait()
+                        except Exception:
+                            pass
+                errors.append(e)
+
+        if len(devices) == 1:
+            worker(0)
+        else:
+            ths = [threading.Thread(target=worker, args=(w,)) for w in range(len(devices))]
+            [t.start() for t in ths]
+            [t.join() for t in ths]
+        if errors:
+            raise errors[0]
         return out
 
     def compute_device(self, d_left: int, d_right: int, H: int, W: int, d_out: int) -> None:

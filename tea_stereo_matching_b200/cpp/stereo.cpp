@@ -14,8 +14,15 @@
 #include <cstdio>
 #include <cstdlib>
 #include <stdexcept>
+#include <atomic>
+#include <exception>
+#include <mutex>
+#include <thread>
 
 namespace {
+
+// Process-wide id of rectify-map CONTENT (tsm.h: map_generation): every loadEpipolarRectifyMap takes a new one.
+std::atomic<unsigned long long> g_map_generation{1};
 
 bool log_enabled() { static const bool on = std::getenv("TSM_LOG") != nullptr; return on; }
 void log_info(const std::string& m) { if (log_enabled()) std::fprintf(stderr, "[INFO] %s\n", m.c_str()); }
@@ -30,6 +37,10 @@ int default_device()
 struct Ctx {
 	tsm_ctx* h = nullptr;
 	int device = -1;
+	Ctx() = default;
+	Ctx(const Ctx&) = delete;
+	Ctx& operator=(const Ctx&) = delete;
+	Ctx(Ctx&& o) noexcept : h(o.h), device(o.device) { o.h = nullptr; o.device = -1; }
 	void ensure(int dev)
 	{
 		if (h && device == dev) return;
@@ -82,6 +93,7 @@ public:
 	cv::Size m_imgsz;
 	cv::Mat c00, c01, c10, c11;  // continuous copies handed to the C-ABI
 	int kind = -1;
+	unsigned long long gen = 0;  // identifies the content of c00..c11 to the device-side map cache
 	Ctx ctx;
 };
 
@@ -108,7 +120,7 @@ void stereo::EpipolarRectify::loadEpipolarRectifyMap(const EpipolarRectifyMap& r
 	impl->kind = map_kind_of(impl->c00, impl->c01);
 	if (impl->kind < 0 || map_kind_of(impl->c10, impl->c11) != impl->kind)
 		throw std::runtime_error("[EpipolarRectify] unsupported map types (need CV_16SC2+CV_16UC1 or CV_32FC1 x2)");
-	if (impl->ctx.h) tsm_invalidate_maps(impl->ctx.h);
+	impl->gen = g_map_generation.fetch_add(1);
 	log_info("Loaded stereo epipolar rectify params!");
 }
 
@@ -130,7 +142,7 @@ void stereo::EpipolarRectify::rectify(const cv::Mat& stereoImage, cv::Mat& recti
 		impl->ctx.ensure(default_device());
 		cv::Mat l(H, W, CV_8UC3), r(H, W, CV_8UC3);
 		int rc = tsm_rectify_stereo(impl->ctx.h, stereoImage.data, stereoImage.step, H, W, impl->c00.data, impl->c01.data,
-			impl->c10.data, impl->c11.data, impl->kind, l.data, l.step, r.data, r.step);
+			impl->c10.data, impl->c11.data, impl->kind, impl->gen, l.data, l.step, r.data, r.step);
 		if (rc != TSM_OK) throw std::runtime_error(tsm_last_error(impl->ctx.h));
 		rectifyLeftImage = l; rectifiedRightImage = r;
 		return;
@@ -152,7 +164,7 @@ void stereo::EpipolarRectify::rectify(const cv::Mat& leftImage, const cv::Mat& r
 	for (int k = 0; k < 2; ++k) {
 		out[k].create(m1[k]->rows, m1[k]->cols, CV_8UC3);
 		int rc = tsm_remap(impl->ctx.h, src[k]->data, src[k]->step, src[k]->rows, src[k]->cols, m1[k]->data, m2[k]->data,
-			impl->kind, m1[k]->rows, m1[k]->cols, out[k].data, out[k].step);
+			impl->kind, impl->gen, m1[k]->rows, m1[k]->cols, out[k].data, out[k].step);
 		if (rc != TSM_OK) throw std::runtime_error(tsm_last_error(impl->ctx.h));
 	}
 	rectifyLeftImage = out[0]; rectifiedRightImage = out[1];
@@ -171,8 +183,10 @@ public:
 	ColorModel m_colorModel = ColorModel::HSI;
 	bool m_roiMatching = false, m_maskMatching = false;
 	int m_offset = 0;
-	int device = default_device();
-	Ctx ctx[2];
+	int device = default_device();  // -1: the batched compute shards over every visible device
+	Ctx ctx[1];                     // single-pair compute / fused rectify
+	static constexpr size_t kInFlight = 3;  // pairs in flight per device of the batched compute (measured best: profiles/README.md)
+	std::vector<Ctx> batch;         // [device][kInFlight] contexts of the batched compute
 	tsm_adcensus_config config() const
 	{
 		tsm_adcensus_config c;
@@ -208,7 +222,11 @@ void stereo::ADCensus::setOffset(const int& offset)
 	impl->m_offset = offset;
 }
 
-void stereo::ADCensus::setDevice(const int& device) { impl->device = device; }
+void stereo::ADCensus::setDevice(const int& device)
+{
+	if (device < -1) throw(std::string("[ADCensus] Device error."));
+	impl->device = device;
+}
 
 static void check_pair(const cv::Mat& l, const cv::Mat& r)
 {
@@ -222,7 +240,7 @@ void stereo::ADCensus::compute(const cv::Mat& leftImage, const cv::Mat& rightIma
 	check_pair(leftImage, rightImage);
 	log_info("Computing disparity...");
 	auto start = std::chrono::steady_clock::now();
-	impl->ctx[0].ensure(impl->device);
+	impl->ctx[0].ensure(impl->device < 0 ? default_device() : impl->device);
 	cv::Mat out(leftImage.rows, leftImage.cols, CV_32FC1);
 	const tsm_adcensus_config cfg = impl->config();
 	int rc = tsm_adcensus_compute(impl->ctx[0].h, &cfg, leftImage.data, leftImage.step, rightImage.data, rightImage.step,
@@ -234,34 +252,91 @@ void stereo::ADCensus::compute(const cv::Mat& leftImage, const cv::Mat& rightIma
 	log_info("Disparity map computed. Timing: " + std::to_string(tt.count() / 1000.0) + " ms.");
 }
 
+// Batched form: stereo pairs are independent, so pair i goes to device i % N (the frame
+// sharding bench.py measures), one worker thread per device, kInFlight contexts (= streams, arenas) per device so
+// that the copies and the small refinement kernels of one pair overlap with the bandwidth kernels of another.
+// setDevice(d >= 0): that one device; setDevice(-1): every visible device.  Results do not depend on the sharding:
+// every pair runs the same kernels on its own context.
 void stereo::ADCensus::compute(const std::vector<cv::Mat>& leftImages, const std::vector<cv::Mat>& rightImages, std::vector<cv::Mat>& disparities)
 {
 	if (leftImages.size() != rightImages.size()) throw(std::string("[ADCensus] Image error."));
 	const size_t n = leftImages.size();
 	for (size_t i = 0; i < n; ++i) check_pair(leftImages[i], rightImages[i]);
 	disparities.assign(n, cv::Mat());
+	if (n == 0) return;
 	const tsm_adcensus_config cfg = impl->config();
-	for (int k = 0; k < 2; ++k) impl->ctx[k].ensure(impl->device);
-	auto fail = [&](tsm_ctx* c, int rc) {
-		if (rc == TSM_E_ARG) throw(std::string(tsm_last_error(c)));
-		throw std::runtime_error(tsm_last_error(c));
-	};
-	// pair i runs on context i & 1; it is collected right before pair i + 2 needs that context, so two pairs stay in flight
-	for (size_t i = 0; i < n + 2; ++i) {
-		if (i >= 2) {
-			tsm_ctx* c = impl->ctx[i & 1].h;
-			cv::Mat out(leftImages[i - 2].rows, leftImages[i - 2].cols, CV_32FC1);
-			int rc = tsm_adcensus_wait(c, (float*)out.data, out.step);
-			if (rc != TSM_OK) fail(c, rc);
-			disparities[i - 2] = out;
-		}
-		if (i < n) {
-			tsm_ctx* c = impl->ctx[i & 1].h;
-			int rc = tsm_adcensus_enqueue(c, &cfg, leftImages[i].data, leftImages[i].step, rightImages[i].data, rightImages[i].step,
-				leftImages[i].rows, leftImages[i].cols);
-			if (rc != TSM_OK) fail(c, rc);
-		}
+	std::vector<int> devices;
+	if (impl->device >= 0) devices.push_back(impl->device);
+	else {
+		int count = 0;
+		if (tsm_device_count(&count) != TSM_OK or count < 1) throw std::runtime_error(tsm_last_error(nullptr));
+		for (int d = 0; d < count and (size_t)d < n; ++d) devices.push_back(d);
 	}
+	const size_t nd = devices.size();
+	if (impl->batch.size() != nd * ADCensusImpl::kInFlight) {
+		impl->batch.clear();
+		impl->batch.resize(nd * ADCensusImpl::kInFlight);
+	}
+	std::mutex err_mtx;
+	std::exception_ptr err;
+	std::string err_str;  // the reference throws std::string for argument errors
+	auto worker = [&](size_t w) {
+		Ctx* ctx = &impl->batch[w * ADCensusImpl::kInFlight];
+		constexpr size_t K = ADCensusImpl::kInFlight;
+		std::vector<size_t> mine;
+		for (size_t i = w; i < n; i += nd) mine.push_back(i);
+		bool pending[K] = {};
+		size_t slot_pair[K] = {};
+		auto drain = [&] {  // error path: leave no context with an un-waited pair
+			for (size_t k = 0; k < K; ++k)
+				if (pending[k]) {
+					cv::Mat scratch(leftImages[slot_pair[k]].rows, leftImages[slot_pair[k]].cols, CV_32FC1);
+					tsm_adcensus_wait(ctx[k].h, (float*)scratch.data, scratch.step);
+					pending[k] = false;
+				}
+		};
+		try {
+			for (size_t k = 0; k < K; ++k) ctx[k].ensure(devices[w]);
+			for (size_t j = 0; j < mine.size() + K; ++j) {
+				const size_t k = j % K;
+				if (pending[k]) {
+					const size_t i = slot_pair[k];
+					cv::Mat out(leftImages[i].rows, leftImages[i].cols, CV_32FC1);
+					pending[k] = false;
+					int rc = tsm_adcensus_wait(ctx[k].h, (float*)out.data, out.step);
+					if (rc != TSM_OK) throw std::make_pair(rc, std::string(tsm_last_error(ctx[k].h)));
+					disparities[i] = out;
+				}
+				if (j < mine.size()) {
+					const size_t i = mine[j];
+					int rc = tsm_adcensus_enqueue(ctx[k].h, &cfg, leftImages[i].data, leftImages[i].step, rightImages[i].data,
+						rightImages[i].step, leftImages[i].rows, leftImages[i].cols);
+					if (rc != TSM_OK) throw std::make_pair(rc, std::string(tsm_last_error(ctx[k].h)));
+					pending[k] = true;
+					slot_pair[k] = i;
+				}
+			}
+		} catch (const std::pair<int, std::string>& e) {
+			drain();
+			std::lock_guard<std::mutex> g(err_mtx);
+			if (!err and err_str.empty()) {
+				if (e.first == TSM_E_ARG) err_str = e.second;
+				else err = std::make_exception_ptr(std::runtime_error(e.second));
+			}
+		} catch (...) {
+			drain();
+			std::lock_guard<std::mutex> g(err_mtx);
+			if (!err and err_str.empty()) err = std::current_exception();
+		}
+	};
+	if (nd == 1) worker(0);
+	else {
+		std::vector<std::thread> pool;
+		for (size_t w = 0; w < nd; ++w) pool.emplace_back(worker, w);
+		for (auto& t : pool) t.join();
+	}
+	if (!err_str.empty()) throw(std::string(err_str));
+	if (err) std::rethrow_exception(err);
 }
 
 void stereo::ADCensus::compute(EpipolarRectify& rectify, const cv::Mat& stereoImage, cv::Mat& disparity)
@@ -272,11 +347,11 @@ void stereo::ADCensus::compute(EpipolarRectify& rectify, const cv::Mat& stereoIm
 	const int W = r.m_imgsz.width, H = r.m_imgsz.height;
 	if (stereoImage.cols < 2 * W or stereoImage.rows < H or r.c00.rows != H or r.c00.cols != W)
 		throw(std::string("[ADCensus] Image error."));
-	impl->ctx[0].ensure(impl->device);
+	impl->ctx[0].ensure(impl->device < 0 ? default_device() : impl->device);
 	cv::Mat out(H, W, CV_32FC1);
 	const tsm_adcensus_config cfg = impl->config();
 	int rc = tsm_rectify_adcensus(impl->ctx[0].h, &cfg, stereoImage.data, stereoImage.step, H, W, r.c00.data, r.c01.data, r.c10.data,
-		r.c11.data, r.kind, (float*)out.data, out.step);
+		r.c11.data, r.kind, r.gen, (float*)out.data, out.step);
 	if (rc == TSM_E_ARG) throw(std::string(tsm_last_error(impl->ctx[0].h)));
 	if (rc != TSM_OK) throw std::runtime_error(tsm_last_error(impl->ctx[0].h));
 	disparity = out;

@@ -725,11 +725,19 @@ void aggregate(const Launcher& L, const Dims& d, const ViewPtrs& left, const Vie
     unsigned* ctr = work_counters;
     for (int it = 0; it < kIterations; ++it, ctr += 4) {
         if (hf) {
+            L.begin("aggregate/h");
             launch_walk<false, false>(L, d, left, right, ctr);
+            L.end();
+            L.begin("aggregate/v_norm");
             launch_walk<true, true>(L, d, left, right, ctr + 2);
+            L.end();
         } else {
+            L.begin("aggregate/v");
             launch_walk<true, false>(L, d, left, right, ctr);
+            L.end();
+            L.begin("aggregate/h_norm");
             launch_walk<false, true>(L, d, left, right, ctr + 2);
+            L.end();
         }
         hf = !hf;
     }

@@ -156,12 +156,18 @@ void reproject_xyz_q(const Launcher& L, const float* disp, float* xyz, int H, in
     L.count(1);
 }
 
+__global__ void k_range_init(int* range)
+{
+    range[0] = 0x7f800000;  // +inf as the running minimum
+    range[1] = -1;          // below every non-negative float pattern as the running maximum
+}
+
 void apply_colormap(const Launcher& L, const float* disp, uint8_t* dst, size_t n, bool auto_range, float minv, float maxv,
                     const uint8_t* d_table, int* d_range)
 {
     if (auto_range) {
-        const int init[2] = {0x7f800000, -1};
-        cudaMemcpyAsync(d_range, init, sizeof init, cudaMemcpyHostToDevice, L.stream);
+        k_range_init<<<1, 1, 0, L.stream>>>(d_range);
+        L.count(1);
         const unsigned blocks = (unsigned)std::min<size_t>((n + 255) / 256, 148 * 8);
         k_minmax<<<blocks, 256, 0, L.stream>>>(disp, n, d_range);
         L.count(1);

@@ -381,8 +381,12 @@ static void launch_scan(const Launcher& L, const Dims& d, const ViewPtrs& left, 
         smem_set.cur() = smem;
     }
     dim3 gv((d.W + SCAN_WARPS - 1) / SCAN_WARPS, 2), gh((d.H + SCAN_WARPS - 1) / SCAN_WARPS, 2);
+    L.begin("scanline/vertical");
     k_scanline<K, true><<<gv, SCAN_WARPS * 32, smem, L.stream>>>(d, left, right, sp, wta0, wta1);
+    L.end();
+    L.begin("scanline/horizontal");
     k_scanline<K, false><<<gh, SCAN_WARPS * 32, smem, L.stream>>>(d, left, right, sp, wta0, wta1);
+    L.end();
     L.count(2);
 }
 

@@ -67,8 +67,14 @@ struct tsm_ctx {
 
     // rectify
     Buf r_src, r_map1[2], r_map2[2], r_fmap[2][2];
-    const void* map_key[4] = {nullptr, nullptr, nullptr, nullptr};
-    int map_kind = -1, map_H = 0, map_W = 0;
+    // device copies of rectify maps, one slot per map pair; valid while the caller's generation id is unchanged
+    struct MapSlot {
+        unsigned long long gen = 0;  // 0 = empty
+        const void* m1 = nullptr;
+        const void* m2 = nullptr;
+        int kind = -1, H = 0, W = 0;
+    } map_slot[2];
+    int remap_victim = 0;
     uint8_t* h_stereo = nullptr;
     size_t h_stereo_bytes = 0;
 
@@ -76,6 +82,7 @@ struct tsm_ctx {
     bool profiling = false;
     std::vector<StageTimer> timers;
     size_t timers_used = 0;
+    size_t sub_open = (size_t)-1;  // timer of the launch-level interval that is open (Launcher::begin / end)
 };
 
 namespace {
@@ -326,22 +333,15 @@ ViewPtrs view_ptrs(tsm_ctx* c, int k)
     return v;
 }
 
+size_t timer_open(tsm_ctx* c, const char* name);
+
 struct ScopedStage {
     tsm_ctx* c;
     size_t idx = (size_t)-1;
     ScopedStage(tsm_ctx* ctx, const char* name) : c(ctx)
     {
         if (!c->profiling) return;
-        if (c->timers_used == c->timers.size()) {
-            StageTimer t;
-            t.name = name;
-            cudaEventCreate(&t.beg);
-            cudaEventCreate(&t.end);
-            c->timers.push_back(t);
-        }
-        idx = c->timers_used++;
-        c->timers[idx].name = name;
-        cudaEventRecord(c->timers[idx].beg, c->stream);
+        idx = timer_open(c, name);
     }
     ~ScopedStage()
     {
@@ -349,13 +349,47 @@ struct ScopedStage {
     }
 };
 
+size_t timer_open(tsm_ctx* c, const char* name)
+{
+    if (c->timers_used == c->timers.size()) {
+        StageTimer t;
+        t.name = name;
+        cudaEventCreate(&t.beg);
+        cudaEventCreate(&t.end);
+        c->timers.push_back(t);
+    }
+    const size_t idx = c->timers_used++;
+    c->timers[idx].name = name;
+    cudaEventRecord(c->timers[idx].beg, c->stream);
+    return idx;
+}
+
+// Launcher hook: one event pair around a single launch (or a few) inside a stage
+void prof_mark(void* self, const char* name, int begin)
+{
+    tsm_ctx* c = (tsm_ctx*)self;
+    if (!c->profiling) return;
+    if (begin) c->sub_open = timer_open(c, name);
+    else if (c->sub_open != (size_t)-1) {
+        cudaEventRecord(c->timers[c->sub_open].end, c->stream);
+        c->sub_open = (size_t)-1;
+    }
+}
+
+Launcher make_launcher(tsm_ctx* c)
+{
+    Launcher L{c->stream, &c->launches};
+    if (c->profiling) { L.prof = c; L.mark = prof_mark; }
+    return L;
+}
+
 // Runs the stages in `mask` on the current arena, in pipeline order.
 int run_stages(tsm_ctx* c, int mask, int arg)
 {
     const Dims& d = c->dm;
-    Launcher L{c->stream, &c->launches};
+    Launcher L = make_launcher(c);
     ViewPtrs vl = view_ptrs(c, 0), vr = view_ptrs(c, 1);
-    if (c->profiling && mask == TSM_STAGE_ALL) c->timers_used = 0;
+    if (c->profiling && mask == TSM_STAGE_ALL && arg != -2) c->timers_used = 0;  // -2: the caller already recorded a stage
     if (mask & TSM_STAGE_PREP) {
         ScopedStage s(c, "prep");
         for (int k = 0; k < 2; ++k)
@@ -561,6 +595,7 @@ int tsm_adcensus_compute_device(tsm_ctx* c, const tsm_adcensus_config* cfg, cons
 {
     if (!c) return TSM_E_ARG;
     if (!d_left || !d_right || !d_disparity) return fail(c, TSM_E_ARG, "[ADCensus] Image error.");
+    if (c->pending) return fail(c, TSM_E_STATE, "tsm_adcensus_compute_device: a pair is enqueued on this context and not waited for");
     int rc = ensure_arena(c, cfg, H, W);
     if (rc) return rc;
     const size_t img_bytes = (size_t)H * W * 3;
@@ -636,8 +671,22 @@ static int upload_maps(tsm_ctx* c, int slot, const void* m1, const void* m2, int
     return TSM_OK;
 }
 
+// Device copy of one map pair in `slot`.  The copy is reused only while the caller vouches, through a non-zero
+// generation id, that the CONTENT behind (m1, m2) is unchanged: host addresses alone say nothing (a reloaded map can
+// land on the same address).  generation 0 = upload every call.
+static int ensure_map_slot(tsm_ctx* c, int slot, unsigned long long gen, const void* m1, const void* m2, int kind, int H, int W)
+{
+    tsm_ctx::MapSlot& s = c->map_slot[slot];
+    if (gen != 0 && s.gen == gen && s.m1 == m1 && s.m2 == m2 && s.kind == kind && s.H == H && s.W == W) return TSM_OK;
+    s.gen = 0;
+    int rc = upload_maps(c, slot, m1, m2, kind, H, W);
+    if (rc) return rc;
+    s.gen = gen; s.m1 = m1; s.m2 = m2; s.kind = kind; s.H = H; s.W = W;
+    return TSM_OK;
+}
+
 int tsm_remap(tsm_ctx* c, const uint8_t* src, size_t sstep, int sH, int sW, const void* map1, const void* map2, int map_kind,
-              int H, int W, uint8_t* dst, size_t dstep)
+              unsigned long long map_generation, int H, int W, uint8_t* dst, size_t dstep)
 {
     if (!c) return TSM_E_ARG;
     if (!map1 || !map2) return fail(c, TSM_E_ARG, "Stereo epipolar rectify params is empty, please load it first.");
@@ -645,14 +694,20 @@ int tsm_remap(tsm_ctx* c, const uint8_t* src, size_t sstep, int sH, int sW, cons
     if (!dst || H <= 0 || W <= 0 || dstep < (size_t)W * 3) return fail(c, TSM_E_ARG, "[EpipolarRectify] destination error.");
     CK(c, cudaSetDevice(c->device));
     int rc;
-    tsm_invalidate_maps(c);
-    if ((rc = upload_maps(c, 0, map1, map2, map_kind, H, W))) return rc;
+    // a slot that already holds this pair, else the other slot than the one used last
+    int slot = 0;
+    for (int k = 0; k < 2; ++k)
+        if (map_generation != 0 && c->map_slot[k].gen == map_generation && c->map_slot[k].m1 == map1 && c->map_slot[k].m2 == map2) slot = k;
+    if (!(map_generation != 0 && c->map_slot[slot].gen == map_generation && c->map_slot[slot].m1 == map1)) {
+        slot = c->map_slot[0].gen == 0 ? 0 : (c->map_slot[1].gen == 0 ? 1 : (c->remap_victim ^= 1));
+    }
+    if ((rc = ensure_map_slot(c, slot, map_generation, map1, map2, map_kind, H, W))) return rc;
     if ((rc = ensure(c, c->r_src, sstep * sH + (size_t)W * 3 * H))) return rc;
     uint8_t* d_src = (uint8_t*)c->r_src.p;
     uint8_t* d_dst = d_src + sstep * sH;
     CK(c, cudaMemcpyAsync(d_src, src, sstep * sH, cudaMemcpyHostToDevice, c->stream));
     Launcher L{c->stream, &c->launches};
-    remap_bilinear(L, d_src, sstep, sH, sW, (const int16_t*)c->r_map1[0].p, (const uint16_t*)c->r_map2[0].p, H, W, d_dst,
+    remap_bilinear(L, d_src, sstep, sH, sW, (const int16_t*)c->r_map1[slot].p, (const uint16_t*)c->r_map2[slot].p, H, W, d_dst,
                    (size_t)W * 3);
     CK(c, cudaGetLastError());
     CK(c, cudaMemcpy2DAsync(dst, dstep, d_dst, (size_t)W * 3, (size_t)W * 3, H, cudaMemcpyDeviceToHost, c->stream));
@@ -663,40 +718,28 @@ int tsm_remap(tsm_ctx* c, const uint8_t* src, size_t sstep, int sH, int sW, cons
 void tsm_invalidate_maps(tsm_ctx* c)
 {
     if (!c) return;
-    for (auto& k : c->map_key) k = nullptr;
-    c->map_kind = -1;
+    for (auto& s : c->map_slot) s.gen = 0;
 }
 
-static int ensure_map_cache(tsm_ctx* c, const void* m00, const void* m01, const void* m10, const void* m11, int kind, int H, int W)
+static int ensure_map_cache(tsm_ctx* c, const void* m00, const void* m01, const void* m10, const void* m11, int kind,
+                            unsigned long long gen, int H, int W)
 {
     if (!m00 || !m01 || !m10 || !m11)
         return fail(c, TSM_E_ARG, "Stereo epipolar rectify params is empty, please load it first.");
-    if (c->map_key[0] == m00 && c->map_key[1] == m01 && c->map_key[2] == m10 && c->map_key[3] == m11 && c->map_kind == kind &&
-        c->map_H == H && c->map_W == W)
-        return TSM_OK;
     int rc;
-    if ((rc = upload_maps(c, 0, m00, m01, kind, H, W))) return rc;
-    if ((rc = upload_maps(c, 1, m10, m11, kind, H, W))) return rc;
-    c->map_key[0] = m00; c->map_key[1] = m01; c->map_key[2] = m10; c->map_key[3] = m11;
-    c->map_kind = kind; c->map_H = H; c->map_W = W;
+    if ((rc = ensure_map_slot(c, 0, gen, m00, m01, kind, H, W))) return rc;
+    if ((rc = ensure_map_slot(c, 1, gen, m10, m11, kind, H, W))) return rc;
     return TSM_OK;
 }
 
-// Uploads the side-by-side frame and remaps both halves into d_left / d_right (packed BGR).
-static int rectify_to_device(tsm_ctx* c, const uint8_t* stereo, size_t sstep, int H, int W, const void* m00, const void* m01,
-                             const void* m10, const void* m11, int kind, uint8_t* d_left, uint8_t* d_right)
+// Remaps both halves of a device-resident side-by-side frame into d_left / d_right (packed BGR).
+static int rectify_on_device(tsm_ctx* c, const uint8_t* d_src, size_t row, int H, int W, const void* m00, const void* m01,
+                             const void* m10, const void* m11, int kind, unsigned long long gen, uint8_t* d_left, uint8_t* d_right)
 {
-    if (!stereo || H <= 0 || W <= 0 || sstep < (size_t)W * 6) return fail(c, TSM_E_ARG, "Stereo image is empty.");
-    CK(c, cudaSetDevice(c->device));
     int rc;
-    if ((rc = ensure_map_cache(c, m00, m01, m10, m11, kind, H, W))) return rc;
-    const size_t row = (size_t)W * 6;
-    if ((rc = ensure_pinned(c, (void**)&c->h_stereo, &c->h_stereo_bytes, row * H))) return rc;
-    for (int y = 0; y < H; ++y) memcpy(c->h_stereo + (size_t)y * row, stereo + (size_t)y * sstep, row);
-    if ((rc = ensure(c, c->r_src, row * H + (size_t)W * 3 * H))) return rc;
-    uint8_t* d_src = (uint8_t*)c->r_src.p;
-    CK(c, cudaMemcpyAsync(d_src, c->h_stereo, row * H, cudaMemcpyHostToDevice, c->stream));
+    if ((rc = ensure_map_cache(c, m00, m01, m10, m11, kind, gen, H, W))) return rc;
     Launcher L{c->stream, &c->launches};
+    ScopedStage s(c, "rectify");
     // halves [0,W) and [W,2W) of the frame (EpipolarRectify.cpp:81-82): same rows, column offset 3*W bytes
     remap_bilinear(L, d_src, row, H, W, (const int16_t*)c->r_map1[0].p, (const uint16_t*)c->r_map2[0].p, H, W, d_left, (size_t)W * 3);
     remap_bilinear(L, d_src + (size_t)W * 3, row, H, W, (const int16_t*)c->r_map1[1].p, (const uint16_t*)c->r_map2[1].p, H, W,
@@ -705,19 +748,37 @@ static int rectify_to_device(tsm_ctx* c, const uint8_t* stereo, size_t sstep, in
     return TSM_OK;
 }
 
+// Uploads the side-by-side frame and remaps both halves into d_left / d_right (packed BGR).
+static int rectify_to_device(tsm_ctx* c, const uint8_t* stereo, size_t sstep, int H, int W, const void* m00, const void* m01,
+                             const void* m10, const void* m11, int kind, unsigned long long gen, uint8_t* d_left, uint8_t* d_right)
+{
+    if (!stereo || H <= 0 || W <= 0 || sstep < (size_t)W * 6) return fail(c, TSM_E_ARG, "Stereo image is empty.");
+    int rc;
+    const size_t row = (size_t)W * 6;
+    if ((rc = ensure_pinned(c, (void**)&c->h_stereo, &c->h_stereo_bytes, row * H))) return rc;
+    for (int y = 0; y < H; ++y) memcpy(c->h_stereo + (size_t)y * row, stereo + (size_t)y * sstep, row);
+    if ((rc = ensure(c, c->r_src, row * H + (size_t)W * 3 * H))) return rc;
+    uint8_t* d_src = (uint8_t*)c->r_src.p;
+    CK(c, cudaMemcpyAsync(d_src, c->h_stereo, row * H, cudaMemcpyHostToDevice, c->stream));
+    return rectify_on_device(c, d_src, row, H, W, m00, m01, m10, m11, kind, gen, d_left, d_right);
+}
+
 int tsm_rectify_stereo(tsm_ctx* c, const uint8_t* stereo, size_t sstep, int H, int W, const void* map00, const void* map01,
-                       const void* map10, const void* map11, int map_kind, uint8_t* left, size_t lstep, uint8_t* right,
-                       size_t rstep)
+                       const void* map10, const void* map11, int map_kind, unsigned long long map_generation, uint8_t* left,
+                       size_t lstep, uint8_t* right, size_t rstep)
 {
     if (!c) return TSM_E_ARG;
     if (!left || !right || lstep < (size_t)W * 3 || rstep < (size_t)W * 3)
         return fail(c, TSM_E_ARG, "[EpipolarRectify] destination error.");
+    if (H <= 0 || W <= 0) return fail(c, TSM_E_ARG, "Stereo image is empty.");
+    if (c->pending) return fail(c, TSM_E_STATE, "tsm_rectify_stereo: a pair is enqueued on this context and not waited for");
+    CK(c, cudaSetDevice(c->device));  // before anything that may allocate
     int rc;
     const size_t img_bytes = (size_t)H * W * 3;
     if ((rc = ensure(c, c->img[0], img_bytes))) return rc;
     if ((rc = ensure(c, c->img[1], img_bytes))) return rc;
-    if ((rc = rectify_to_device(c, stereo, sstep, H, W, map00, map01, map10, map11, map_kind, (uint8_t*)c->img[0].p,
-                                (uint8_t*)c->img[1].p)))
+    if ((rc = rectify_to_device(c, stereo, sstep, H, W, map00, map01, map10, map11, map_kind, map_generation,
+                                (uint8_t*)c->img[0].p, (uint8_t*)c->img[1].p)))
         return rc;
     CK(c, cudaMemcpy2DAsync(left, lstep, c->img[0].p, (size_t)W * 3, (size_t)W * 3, H, cudaMemcpyDeviceToHost, c->stream));
     CK(c, cudaMemcpy2DAsync(right, rstep, c->img[1].p, (size_t)W * 3, (size_t)W * 3, H, cudaMemcpyDeviceToHost, c->stream));
@@ -725,23 +786,54 @@ int tsm_rectify_stereo(tsm_ctx* c, const uint8_t* stereo, size_t sstep, int H, i
     return TSM_OK;
 }
 
-int tsm_rectify_adcensus(tsm_ctx* c, const tsm_adcensus_config* cfg, const uint8_t* stereo, size_t sstep, int H, int W,
-                         const void* map00, const void* map01, const void* map10, const void* map11, int map_kind,
-                         float* disparity, size_t dstep)
+int tsm_rectify_adcensus_enqueue(tsm_ctx* c, const tsm_adcensus_config* cfg, const uint8_t* stereo, size_t sstep, int H, int W,
+                                 const void* map00, const void* map01, const void* map10, const void* map11, int map_kind,
+                                 unsigned long long map_generation)
 {
     if (!c) return TSM_E_ARG;
-    if (!disparity || dstep < (size_t)W * 4) return fail(c, TSM_E_ARG, "[ADCensus] disparity buffer error.");
+    if (c->pending) return fail(c, TSM_E_STATE, "tsm_rectify_adcensus: previous pair not waited for");
     int rc = ensure_arena(c, cfg, H, W);
     if (rc) return rc;
-    if ((rc = rectify_to_device(c, stereo, sstep, H, W, map00, map01, map10, map11, map_kind, (uint8_t*)c->img[0].p,
-                                (uint8_t*)c->img[1].p)))
+    if (c->profiling) c->timers_used = 0;
+    if ((rc = rectify_to_device(c, stereo, sstep, H, W, map00, map01, map10, map11, map_kind, map_generation,
+                                (uint8_t*)c->img[0].p, (uint8_t*)c->img[1].p)))
         return rc;
     c->have_pair = true;
-    if ((rc = run_stages(c, TSM_STAGE_ALL, -1))) return rc;
+    if ((rc = run_stages(c, TSM_STAGE_ALL, -2))) return rc;
     if ((rc = ensure_pinned(c, (void**)&c->h_out, &c->h_out_bytes, (size_t)H * W * 4))) return rc;
     CK(c, cudaMemcpyAsync(c->h_out, c->fin.p, (size_t)H * W * 4, cudaMemcpyDeviceToHost, c->stream));
     c->pending = true;
+    return TSM_OK;
+}
+
+int tsm_rectify_adcensus(tsm_ctx* c, const tsm_adcensus_config* cfg, const uint8_t* stereo, size_t sstep, int H, int W,
+                         const void* map00, const void* map01, const void* map10, const void* map11, int map_kind,
+                         unsigned long long map_generation, float* disparity, size_t dstep)
+{
+    if (!c) return TSM_E_ARG;
+    if (!disparity || dstep < (size_t)W * 4) return fail(c, TSM_E_ARG, "[ADCensus] disparity buffer error.");
+    int rc = tsm_rectify_adcensus_enqueue(c, cfg, stereo, sstep, H, W, map00, map01, map10, map11, map_kind, map_generation);
+    if (rc) return rc;
     return tsm_adcensus_wait(c, disparity, dstep);
+}
+
+int tsm_rectify_adcensus_device(tsm_ctx* c, const tsm_adcensus_config* cfg, const uint8_t* d_stereo, size_t sstep, int H, int W,
+                                const void* map00, const void* map01, const void* map10, const void* map11, int map_kind,
+                                unsigned long long map_generation, float* d_disparity)
+{
+    if (!c) return TSM_E_ARG;
+    if (!d_stereo || !d_disparity || H <= 0 || W <= 0 || sstep < (size_t)W * 6) return fail(c, TSM_E_ARG, "Stereo image is empty.");
+    if (c->pending) return fail(c, TSM_E_STATE, "tsm_rectify_adcensus_device: previous pair not waited for");
+    int rc = ensure_arena(c, cfg, H, W);
+    if (rc) return rc;
+    if (c->profiling) c->timers_used = 0;
+    if ((rc = rectify_on_device(c, d_stereo, sstep, H, W, map00, map01, map10, map11, map_kind, map_generation,
+                                (uint8_t*)c->img[0].p, (uint8_t*)c->img[1].p)))
+        return rc;
+    c->have_pair = true;
+    if ((rc = run_stages(c, TSM_STAGE_ALL, -2))) return rc;
+    CK(c, cudaMemcpyAsync(d_disparity, c->fin.p, (size_t)H * W * 4, cudaMemcpyDeviceToDevice, c->stream));
+    return TSM_OK;
 }
 
 // --------------------------------------------------------------------- taps

@@ -95,6 +95,13 @@ def _map_kind(m1: np.ndarray, m2: np.ndarray) -> int:
     raise ADCensusError("[EpipolarRectify] unsupported map types (need CV_16SC2+CV_16UC1 or CV_32FC1 x2)")
 
 
+# Process-wide id of the map CONTENT handed to the C-ABI (tsm.h: map_generation): every loadEpipolarRectifyMap takes a
+# new one, so a device-side copy is never reused for different maps that happen to live at the same host addresses.
+import itertools
+
+_map_generation = itertools.count(1)
+
+
 class EpipolarRectify:
     def __init__(self, rectifyMap: EpipolarRectifyMap | None = None, imgsz: tuple[int, int] | None = None,
                  device: int = 0, context: Context | None = None):
@@ -119,9 +126,8 @@ class EpipolarRectify:
         if _map_kind(m.map10, m.map11) != self._kind:
             raise ADCensusError("[EpipolarRectify] left and right maps must have the same type")
         self._map = m
+        self._gen = next(_map_generation)
         self._imgsz = (int(imgsz[0]), int(imgsz[1]))
-        if self._ctx is not None:
-            self._ctx._lib.tsm_invalidate_maps(self._ctx.handle)
 
     # rectify(left, right) -> (rectLeft, rectRight)         EpipolarRectify.cpp:87-101
     # rectify(stereo)      -> (rectLeft, rectRight)         EpipolarRectify.cpp:68-85
@@ -153,7 +159,7 @@ class EpipolarRectify:
         right = np.empty((H, W, 3), np.uint8)
         ctx, m = self.context, self._map
         ctx.check(ctx._lib.tsm_rectify_stereo(ctx.handle, _ptr(stereo), stereo.strides[0], H, W, _ptr(m.map00), _ptr(m.map01),
-                                               _ptr(m.map10), _ptr(m.map11), self._kind, _ptr(left), left.strides[0],
+                                               _ptr(m.map10), _ptr(m.map11), self._kind, self._gen, _ptr(left), left.strides[0],
                                                _ptr(right), right.strides[0]))
         return left, right
 
@@ -172,8 +178,29 @@ class EpipolarRectify:
         ctx, m = matcher.context, self._map
         ctx.check(ctx._lib.tsm_rectify_adcensus(ctx.handle, C.byref(matcher._config()), _ptr(stereo), stereo.strides[0], H, W,
                                                  _ptr(m.map00), _ptr(m.map01), _ptr(m.map10), _ptr(m.map11), self._kind,
-                                                 _ptr(out), out.strides[0]))
+                                                 self._gen, _ptr(out), out.strides[0]))
         return out
+
+    def rectify_adcensus_enqueue(self, stereoImage, matcher) -> None:
+        """Asynchronous rectify_adcensus: collect the map with matcher.wait()."""
+        if self._map.empty():
+            raise RuntimeError("stereo params is empty, please load it first")
+        stereo = _as_bgr(stereoImage, "stereo")
+        W, H = self._imgsz
+        ctx, m = matcher.context, self._map
+        ctx.check(ctx._lib.tsm_rectify_adcensus_enqueue(ctx.handle, C.byref(matcher._config()), _ptr(stereo), stereo.strides[0], H, W,
+                                                         _ptr(m.map00), _ptr(m.map01), _ptr(m.map10), _ptr(m.map11), self._kind,
+                                                         self._gen))
+        matcher._pending_shape = matcher.last_shape = (H, W)
+
+    def rectify_adcensus_device(self, d_stereo: int, sstep: int, matcher, d_out: int) -> None:
+        """Device-resident form of rectify_adcensus: raw device pointers, async on the matcher's stream."""
+        W, H = self._imgsz
+        ctx, m = matcher.context, self._map
+        ctx.check(ctx._lib.tsm_rectify_adcensus_device(ctx.handle, C.byref(matcher._config()), C.c_void_p(d_stereo), sstep, H, W,
+                                                        _ptr(m.map00), _ptr(m.map01), _ptr(m.map10), _ptr(m.map11), self._kind,
+                                                        self._gen, C.c_void_p(d_out)))
+        matcher.last_shape = (H, W)
 
     def _remap(self, src: np.ndarray, which: int) -> np.ndarray:
         m1, m2 = (self._map.map00, self._map.map01) if which == 0 else (self._map.map10, self._map.map11)
@@ -181,7 +208,7 @@ class EpipolarRectify:
         dst = np.empty((H, W, 3), np.uint8)
         ctx = self.context
         ctx.check(ctx._lib.tsm_remap(ctx.handle, _ptr(src), src.strides[0], src.shape[0], src.shape[1], _ptr(m1), _ptr(m2),
-                                      self._kind, H, W, _ptr(dst), dst.strides[0]))
+                                      self._kind, self._gen, H, W, _ptr(dst), dst.strides[0]))
         return dst
 
 

@@ -62,7 +62,7 @@ int main(int argc, char** argv)
         } catch (const std::exception& e) { std::fprintf(stderr, "exception: %s\n", e.what()); return 4; }
         return 0;
     }
-    if (argc < 4) { std::fprintf(stderr, "usage: %s api | run in out | batch in out n\n", argv[0]); return 2; }
+    if (argc < 4) { std::fprintf(stderr, "usage: %s api | run in out | batch in out n | batchall in out n\n", argv[0]); return 2; }
     std::ifstream f(argv[2], std::ios::binary);
     int32_t hdr[3];
     f.read((char*)hdr, sizeof hdr);
@@ -75,8 +75,9 @@ int main(int argc, char** argv)
         adcensus.setMatchingStrategy(stereo::ColorModel::RGB, false, false);
         adcensus.setMinMaxDisparity(0, D);
         std::ofstream o(argv[3], std::ios::binary);
-        if (!std::strcmp(argv[1], "batch")) {
+        if (!std::strcmp(argv[1], "batch") || !std::strcmp(argv[1], "batchall")) {
             const int n = argc > 4 ? std::atoi(argv[4]) : 3;
+            if (!std::strcmp(argv[1], "batchall")) adcensus.setDevice(-1);  // shard the pairs over every visible device
             std::vector<cv::Mat> ls(n, left), rs(n, right), ds;
             adcensus.compute(ls, rs, ds);
             for (auto& d : ds) o.write((const char*)d.data, (std::streamsize)H * W * 4);

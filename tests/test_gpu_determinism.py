@@ -102,3 +102,33 @@ def test_two_devices_in_one_process(pair_0600):
             m.setMinMaxDisparity(0, 64)
             outs.append(m.compute(left, right))
     assert np.array_equal(outs[0], outs[2]) and np.array_equal(outs[1], outs[3])
+
+
+def test_batch_sharded_over_devices_equals_one_device(pair_0600):
+    """every frame of a batch sharded over N GPUs equals the 1-GPU bits (thread per device, three
+    pairs in flight each).  With one visible device the same code path runs with N = 1 worker."""
+    import ctypes as C
+
+    import tea_stereo_matching_b200 as t
+    from tea_stereo_matching_b200 import _native as N
+    from tea_stereo_matching_b200.synth import synth_v1
+
+    left, right = pair_0600
+    pairs = [(left, right)] + [synth_v1(180, 320, 48, seed=70 + i) for i in range(6)]
+    m = t.ADCensus(device=0)
+    m.setMatchingStrategy(t.ColorModel.RGB)
+    m.setMinMaxDisparity(0, 48)
+    single = [m.compute(l, r) for l, r in pairs]
+    one = m.computeBatch([p[0] for p in pairs], [p[1] for p in pairs])
+    assert all(np.array_equal(a, b) for a, b in zip(single, one))
+    n = C.c_int32(0)
+    N.lib().tsm_device_count(C.byref(n))
+    allgpu = m.computeBatch([p[0] for p in pairs], [p[1] for p in pairs], devices=-1)
+    assert all(np.array_equal(a, b) for a, b in zip(single, allgpu)), f"{n.value} devices"
+    # an error in the middle of a batch leaves the contexts usable (no un-waited pair)
+    bad = [p[0] for p in pairs]
+    bad[3] = bad[3][:, :-1]
+    with pytest.raises(t.ADCensusError):
+        m.computeBatch(bad, [p[1] for p in pairs])
+    again = m.computeBatch([p[0] for p in pairs], [p[1] for p in pairs])
+    assert all(np.array_equal(a, b) for a, b in zip(single, again))
