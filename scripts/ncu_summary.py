@@ -55,6 +55,16 @@ for r in data:
                 pass
             line.append(f"{short}={v}{units[idx[k]] if short in ('time','dram_rd','dram_wr') else ''}")
     print("   " + "  ".join(line))
+    # every stall reason, cycles per issued instruction (sorted)
+    st = []
+    for h, i in idx.items():
+        m = re.match(r"smsp__average_warps_issue_stalled_(\w+)_per_issue_active\.ratio", h)
+        if m:
+            try:
+                st.append((float(r[i]), m.group(1)))
+            except ValueError:
+                pass
+    print("   stalls/issue: " + "  ".join(f"{n}={v:.3f}" for v, n in sorted(st, reverse=True) if v >= 0.01))
 
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(src)))

@@ -510,6 +510,328 @@ k_agg_persist(Dims dm, ViewPtrs v0, ViewPtrs v1, int tm_warps, unsigned* ctr)
     }
 }
 
+
+// ---- kernel 4: TWO consecutive same-direction passes in one walk (V.norm -> V, H.norm -> H) ----
+// The pass order of costAggregate is H, V.n | V, H.n | H, V.n | V, H.n (ADCensus.cpp:774-783; .n = the pass that ends
+// an iteration and divides by the window size): three adjacent pairs walk the same lines with the same arms, so one
+// walk can apply both -- the volume makes 5 round trips through HBM instead of 8.  Per chain that takes two prefix
+// rings: pass A (normalising) emits c(o1) = (PA[o1+b+1] - PA[o1-a]) / N(o1) with a lag of 33 behind the input
+// position t; pass B pushes c(o1) into its own prefix PB and emits out(o2) = PB[o2+b+1] - PB[o2-a] another 33
+// (+ one batch of 4: B works on the previous batch's c so that the two ring round trips overlap) behind.
+//
+// Ring storage decides how many chains an SM can keep in flight, and the walk needs warps in flight to cover the HBM
+// latency.  Two fp64 rings per chain leave room for 5 warps.  The rings here hold 48-bit WRAP-AROUND FIXED-POINT
+// prefixes instead: only differences of prefixes at most 67 positions apart are ever used, and those are < 2^14
+// (normalising pass: a window of <= 67 first-pass sums <= 134) resp. < 2^8 (plain pass: <= 67 averaged costs <= 2),
+// so 48 bits mod 2^48 carry them exactly at a resolution of 2^-34 resp. 2^-40 -- the resolution an fp64 prefix has at
+// the far end of a 1920-pixel line, and uniform along the line.  A slot is 12 bytes per chain pair (two low words +
+// the two 16-bit high halves in one word): pass A's ring is 216 of the 256 tensor-memory columns a warp can call its
+// own when eight warps share the four lane quarters, pass B's ring 27 KB of shared memory per warp -- 8 warps per SM
+// with both rings, all running the same code.  scripts/emulate_agg_fixed.py checks the arithmetic against the oracle.
+//
+// The walk is branch-free over garbage: it starts 3 positions in front of the line (so that pass A's descriptor
+// groups are 16-byte aligned), runs 70 positions past its end, loads outside [0, len) are predicated off, stores
+// outside [0, len) likewise, and whatever the prefixes collect before position 0 is a common offset that cancels in
+// every difference (the arithmetic is modular, so it cancels exactly).  Descriptors read before / behind a line are
+// the neighbouring lines' or zero padding: any of them keeps the ring offsets inside the ring.
+#ifndef TSM_AGF_NBUF
+#define TSM_AGF_NBUF 3
+#endif
+#ifndef TSM_AGF_PD
+#define TSM_AGF_PD 10
+#endif
+constexpr int AGF_WARPS = 8, AGF_THREADS = 32 * AGF_WARPS;
+constexpr int AGF_NB = TSM_AGF_NBUF;             // register buffers of AGG_PF input positions each
+constexpr int AGF_PD = TSM_AGF_PD;               // batches the L2 prefetch runs ahead of the register loads (0 = off)
+constexpr int AGF_SPAN3 = 3 * AGG_RING;          // ring positions are kept in units of 3 = TMEM columns per slot
+constexpr int AGF_SMEM = AGG_RING * 3 * 1024;    // pass B rings: [slot][256 x 8 B low words | 256 x 4 B high halves]
+constexpr int AGF_LEAD = 3;                      // positions walked in front of the line
+constexpr int AGF_LAG_A = AGG_LAG;               // o1 = t - 33
+constexpr int AGF_LAG_B = 2 * AGG_LAG + AGG_PF;  // o2 = t - 70
+constexpr int AGF_SA = 34, AGF_SB = 40;          // fixed-point scales of the two passes
+static_assert(AGG_PF == 4 && AGG_NC == 2 && AGG_RING % 4 == 0, "fused walk geometry");
+static_assert((AGF_LEAD + AGF_LAG_A) % 4 == 0, "pass A descriptor groups are aligned");
+static_assert(AGF_SPAN3 + 1 <= 256, "a warp's tensor-memory share");
+
+// low 48 bits = round(v * 2^S) mod 2^48; the bits above are junk that the rings drop
+template <int S>
+__device__ __forceinline__ uint64_t fix48(float v)
+{
+    constexpr double magic = 1.5 * (double)(1ull << (52 - S));
+    // float -> double by re-biasing the exponent with two integer instructions instead of a conversion (F2F runs on the
+    // quarter-rate XU pipe and every one of them occupies a scoreboard slot the loads need).  Exact for positive normal
+    // numbers; +0 and denormals (< 2^-126) become a value below 2^-126, which the addition of `magic` rounds away just as
+    // it would round the true value; anything else only occurs in discarded positions.
+    const uint32_t b = __float_as_uint(v);
+    const double w = __hiloint2double((int)((b >> 3) + 0x38000000u), (int)(b << 29));
+    return (uint64_t)__double_as_longlong(__dadd_rn(w, magic));
+}
+// (hi - lo) mod 2^48 of two ring entries, times 2^-S, rounded once to fp32 -- for both chains of the pair
+template <int S>
+__device__ __forceinline__ void diff48(const uint32_t* h, const uint32_t* l, float& r0, float& r1)
+{
+    constexpr uint32_t EXP = (uint32_t)(1023 + 52 - S) << 20;
+    constexpr double base = (double)(1ull << (52 - S));
+    uint32_t d0lo, d0hi, d1lo, d1hi;
+    asm("sub.cc.u32 %0, %2, %3;\n\tsubc.u32 %1, %4, %5;" : "=r"(d0lo), "=r"(d0hi) : "r"(h[0]), "r"(l[0]), "r"(h[2]), "r"(l[2]));
+    asm("sub.cc.u32 %0, %2, %3;\n\tsubc.u32 %1, %4, %5;"
+        : "=r"(d1lo), "=r"(d1hi)
+        : "r"(h[1]), "r"(l[1]), "r"(h[2] >> 16), "r"(l[2] >> 16));
+    d0hi = __byte_perm(d0hi, EXP, 0x7610);  // (d & 0xffff) | EXP in one instruction
+    d1hi = __byte_perm(d1hi, EXP, 0x7610);
+    r0 = __double2float_rn(__dsub_rn(__hiloint2double((int)d0hi, (int)d0lo), base));
+    r1 = __double2float_rn(__dsub_rn(__hiloint2double((int)d1hi, (int)d1lo), base));
+}
+
+__device__ __forceinline__ void ld_stream_if(float2& v, const char* p, int pos, int len)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.lt.u32 p, %3, %4;\n\t@p ld.global.L1::no_allocate.v2.f32 {%0, %1}, [%2];\n\t}"
+                 : "+f"(v.x), "+f"(v.y)
+                 : "l"(p), "r"(pos), "r"(len));
+}
+__device__ __forceinline__ void prefetch_l2_if(const char* p, int pos, int len)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.lt.u32 p, %1, %2;\n\t@p prefetch.global.L2 [%0];\n\t}" ::"l"(p), "r"(pos), "r"(len));
+}
+__device__ __forceinline__ void st_stream_if(char* p, float a, float b, int pos, int len)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.lt.u32 p, %3, %4;\n\t@p st.global.L1::no_allocate.v2.f32 [%0], {%1, %2};\n\t}" ::"l"(p),
+                 "f"(a), "f"(b), "r"(pos), "r"(len)
+                 : "memory");
+}
+
+// One thread walks its two chains along one line through both passes.  tm = tensor-memory address of the warp's
+// pass-A ring (lane quarter << 16 | first column), sl / sh = shared-memory addresses of the thread's pass-B ring
+// (low-word pairs, high halves; a slot is 3 KB further).
+__device__ __forceinline__ void walk_fused(const uint32_t tm, const uint32_t sl, const uint32_t sh, float* cell, const uint32_t cstride,
+                                           const uint32_t* fdesc_line, const float* rcp_line, const int len)
+{
+    auto step_addr = [&](const char* base, int u) {
+        const char* a;
+        asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(a) : "r"(cstride), "r"((uint32_t)u), "l"(base));
+        return a;
+    };
+    // position of the first step: t = -AGF_LEAD
+    const char* in_ptr = reinterpret_cast<const char*>(cell) - (size_t)AGF_LEAD * cstride;
+    char* out_ptr = reinterpret_cast<char*>(cell) - (size_t)(AGF_LEAD + AGF_LAG_B) * cstride;
+    const uint32_t* da_ptr = fdesc_line - (AGF_LEAD + AGF_LAG_A);   // pass A: positions t - 33, 16-byte aligned groups
+    const float* ry_ptr = rcp_line - (AGF_LEAD + AGF_LAG_A);
+    const uint32_t* db_ptr = fdesc_line - (AGF_LEAD + AGF_LAG_B - 1);  // pass B: the group holding positions t - 69 .. t - 66 of u = 0;
+                                                                       // its first three words + the last word of the group before
+    int t_load = -AGF_LEAD;            // position of the next batch to be loaded
+    int o_out = -(AGF_LEAD + AGF_LAG_B);  // output position of pass B for u = 0 of the batch being processed
+
+    // Inputs AND side data (descriptors of both passes, reciprocals) of a batch are loaded together, AGF_NB - 1 batches
+    // ahead of their use: a warp has six scoreboard slots and a slot completes when ALL loads charged to it have landed,
+    // so loads are grouped by the time they are needed (side data fetched one batch ahead shared slots with younger
+    // volume loads and stalled on them: 25 % of the samples in the first ncu capture).
+    float2 vin[AGF_NB][AGG_PF];
+    uint32_t fa[AGF_NB][AGG_PF], fb[AGF_NB][AGG_PF];
+    float yv[AGF_NB][AGG_PF];
+    uint32_t fb_carry = 0;
+#pragma unroll
+    for (int b = 0; b < AGF_NB; ++b)
+#pragma unroll
+        for (int u = 0; u < AGG_PF; ++u) vin[b][u] = make_float2(0.f, 0.f);
+    // All global loads of a warp end up on one or two of its six scoreboard slots (ptxas), so waiting for the oldest
+    // batch also waits for the youngest: register prefetching deeper than one batch buys nothing.  The DRAM latency is
+    // covered by an L2 prefetch (no destination register, no scoreboard) AGF_PD batches ahead instead; the register
+    // loads then hit L2 one or two batches ahead of their use.
+    const char* pf_ptr = in_ptr + (size_t)(AGF_PD * AGG_PF) * cstride;
+    auto load_batch = [&](int buf) {
+        if (AGF_PD > 0) {
+#pragma unroll
+            for (int u = 0; u < AGG_PF; ++u) prefetch_l2_if(step_addr(pf_ptr, u), t_load + AGF_PD * AGG_PF + u, len);
+            pf_ptr = step_addr(pf_ptr, AGG_PF);
+            asm volatile("" : "+l"(pf_ptr));
+        }
+#pragma unroll
+        for (int u = 0; u < AGG_PF; ++u) ld_stream_if(vin[buf][u], step_addr(in_ptr, u), t_load + u, len);
+        in_ptr = step_addr(in_ptr, AGG_PF);
+        asm volatile("" : "+l"(in_ptr));
+        t_load += AGG_PF;
+        const uint4 qa = *reinterpret_cast<const uint4*>(da_ptr);
+        const float4 qy = *reinterpret_cast<const float4*>(ry_ptr);
+        const uint4 qb = *reinterpret_cast<const uint4*>(db_ptr);
+        fa[buf][0] = qa.x; fa[buf][1] = qa.y; fa[buf][2] = qa.z; fa[buf][3] = qa.w;
+        yv[buf][0] = qy.x; yv[buf][1] = qy.y; yv[buf][2] = qy.z; yv[buf][3] = qy.w;
+        fb[buf][0] = fb_carry; fb[buf][1] = qb.x; fb[buf][2] = qb.y; fb[buf][3] = qb.z;
+        fb_carry = qb.w;
+        da_ptr += AGG_PF; ry_ptr += AGG_PF; db_ptr += AGG_PF;
+    };
+
+    uint64_t PA0 = 0, PA1 = 0, PB0 = 0, PB1 = 0;
+    uint32_t topA = 0, topB = AGF_SPAN3 - 3 * AGG_PF;  // ring position (x3) of the newest batch of each pass; B trails A by one batch
+
+    // pass A pushes of one batch: prefixes of the inputs in `buf`, packed for tensor memory (no memory traffic here)
+    auto push_a = [&](int buf, uint32_t (&wa)[3 * AGG_PF]) {
+#pragma unroll
+        for (int u = 0; u < AGG_PF; ++u) {
+            PA0 += fix48<AGF_SA>(vin[buf][u].x);
+            PA1 += fix48<AGF_SA>(vin[buf][u].y);
+            wa[3 * u + 0] = (uint32_t)PA0;
+            wa[3 * u + 1] = (uint32_t)PA1;
+            wa[3 * u + 2] = __byte_perm((uint32_t)(PA0 >> 32), (uint32_t)(PA1 >> 32), 0x5410);
+        }
+    };
+    auto store_a = [&](uint32_t top, const uint32_t (&wa)[3 * AGG_PF]) {
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(tm + top), "r"(wa[0]),
+                     "r"(wa[1]), "r"(wa[2]), "r"(wa[3]), "r"(wa[4]), "r"(wa[5]), "r"(wa[6]), "r"(wa[7])
+                     : "memory");
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(tm + top + 8), "r"(wa[8]), "r"(wa[9]),
+                     "r"(wa[10]), "r"(wa[11])
+                     : "memory");
+    };
+
+    // One loop body = batch k of pass A and batch k - 1 of pass B, software-pipelined so that no ring round trip is
+    // exposed: the pushes of batch k are already in tensor memory (previous body); the ring loads of both passes are
+    // issued first, the prefixes of batch k + 1 are computed while they fly and stored once they have landed (the
+    // stores reuse the oldest slots, which this batch still reads), the outputs follow, and pass A's outputs go into
+    // pass B's ring at the end, to be read by the next body.
+    auto run_batch = [&](int b) {
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        // ---- ring loads of both passes ----
+        uint32_t ha[AGG_PF][4], la[AGG_PF][4], hb[AGG_PF][3], lb[AGG_PF][3];
+#pragma unroll
+        for (int u = 0; u < AGG_PF; ++u) {
+            const uint32_t f = fa[b][u], top = topA + 3 * u;
+            const uint32_t s1 = top - (f & 0xffu), s0 = top - __byte_perm(f, 0, 0x4441);  // P[o + b + 1], P[o - a]
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                         : "=r"(ha[u][0]), "=r"(ha[u][1]), "=r"(ha[u][2]), "=r"(ha[u][3])
+                         : "r"(tm + min(s1, s1 + AGF_SPAN3))
+                         : "memory");
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                         : "=r"(la[u][0]), "=r"(la[u][1]), "=r"(la[u][2]), "=r"(la[u][3])
+                         : "r"(tm + min(s0, s0 + AGF_SPAN3))
+                         : "memory");
+        }
+#pragma unroll
+        for (int u = 0; u < AGG_PF; ++u) {
+            const uint32_t f = fb[b][u], top = topB + 3 * u;
+            uint32_t s1 = top - (f & 0xffu), s0 = top - __byte_perm(f, 0, 0x4441);
+            s1 = min(s1, s1 + AGF_SPAN3) << 10;
+            s0 = min(s0, s0 + AGF_SPAN3) << 10;
+            asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(hb[u][0]), "=r"(hb[u][1]) : "r"(sl + s1) : "memory");
+            asm volatile("ld.shared.b32 %0, [%1];" : "=r"(hb[u][2]) : "r"(sh + s1) : "memory");
+            asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(lb[u][0]), "=r"(lb[u][1]) : "r"(sl + s0) : "memory");
+            asm volatile("ld.shared.b32 %0, [%1];" : "=r"(lb[u][2]) : "r"(sh + s0) : "memory");
+        }
+        // ---- prefixes of the next batch of pass A while the ring loads are in flight ----
+        uint32_t wa[3 * AGG_PF];
+        push_a((b + 1) % AGF_NB, wa);
+        uint32_t nextA = topA + 3 * AGG_PF;
+        if (nextA == AGF_SPAN3) nextA = 0;
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int u = 0; u < AGG_PF; ++u)
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {  // keep every use of the loaded words behind the (volatile) wait::ld
+                asm volatile("" : "+r"(ha[u][i]));
+                asm volatile("" : "+r"(la[u][i]));
+            }
+        store_a(nextA, wa);
+        // ---- pass B outputs ----
+#pragma unroll
+        for (int u = 0; u < AGG_PF; ++u) {
+            float r0, r1;
+            diff48<AGF_SB>(hb[u], lb[u], r0, r1);
+            st_stream_if(const_cast<char*>(step_addr(out_ptr, u)), r0, r1, o_out + u, len);
+        }
+        // ---- pass A outputs c = window sum / N, pushed into pass B's ring for the next body ----
+        const uint32_t slB = sl + (topA << 10), shB = sh + (topA << 10);  // pass B's ring position of this batch = pass A's label
+#pragma unroll
+        for (int u = 0; u < AGG_PF; ++u) {
+            float r0, r1;
+            diff48<AGF_SA>(ha[u], la[u], r0, r1);
+            const float nf = __fsub_rn(__uint_as_float(0x4B000000u | (fa[b][u] >> 16)), 8388608.f);  // (float)N, N < 2^16
+            PB0 += fix48<AGF_SB>(div_exact_rn(r0, nf, yv[b][u]));
+            PB1 += fix48<AGF_SB>(div_exact_rn(r1, nf, yv[b][u]));
+            asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(slB + u * 3072), "r"((uint32_t)PB0), "r"((uint32_t)PB1) : "memory");
+            asm volatile("st.shared.b32 [%0], %1;" ::"r"(shB + u * 3072),
+                         "r"(__byte_perm((uint32_t)(PB0 >> 32), (uint32_t)(PB1 >> 32), 0x5410))
+                         : "memory");
+        }
+        out_ptr = const_cast<char*>(step_addr(out_ptr, AGG_PF));
+        asm volatile("" : "+l"(out_ptr));
+        o_out += AGG_PF;
+        topB = topA;
+        topA = nextA;
+        load_batch(b);  // this buffer's inputs were consumed by the previous body, its side data by this one
+    };
+
+    // batches: positions -3 .. len + 69 (the last output of pass B is position len - 1 = t - 70)
+    const int nbatch = (len + AGF_LAG_B - 1 + AGF_LEAD) / AGG_PF + 1;
+    if (AGF_PD > 0) {
+#pragma unroll 1
+        for (int j = 0; j < AGF_PD * AGG_PF; ++j) prefetch_l2_if(step_addr(in_ptr, j), j - AGF_LEAD, len);
+    }
+#pragma unroll
+    for (int b = 0; b < AGF_NB; ++b) load_batch(b);
+    {
+        uint32_t wa[3 * AGG_PF];
+        push_a(0, wa);
+        store_a(topA, wa);
+    }
+    int done = 0;
+    for (; done + AGF_NB <= nbatch; done += AGF_NB) {
+#pragma unroll
+        for (int b = 0; b < AGF_NB; ++b) run_batch(b);
+    }
+    {
+        int rem = nbatch - done;
+#pragma unroll
+        for (int b = 0; b < AGF_NB; ++b) {
+            if (rem > 0) {
+                run_batch(b);
+                --rem;
+            }
+        }
+    }
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+
+template <bool VERT>
+__global__ void __launch_bounds__(AGF_THREADS, 1)
+k_agg_fused(Dims dm, ViewPtrs v0, ViewPtrs v1, unsigned* ctr)
+{
+    extern __shared__ __align__(16) unsigned char ring_raw[];
+    __shared__ uint32_t tm_base;
+    const int nlines = VERT ? dm.W : dm.H, len = VERT ? dm.H : dm.W;
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(
+                         (uint32_t)__cvta_generic_to_shared(&tm_base))
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    // eight warps share the four lane quarters of tensor memory: warp w owns lanes 32 (w & 3) .. + 31, columns 256 (w >> 2) .. + 255
+    const uint32_t tm = tm_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(warp >> 2) * 256u;
+    const uint32_t smem = (uint32_t)__cvta_generic_to_shared(ring_raw);
+    const uint32_t sl = smem + threadIdx.x * 8, sh = smem + 2048 + threadIdx.x * 4;
+    const unsigned ngroups = dm.Dm / 64, per_view = (unsigned)nlines * ngroups, n_items = 2 * per_view;
+    const size_t line_step = VERT ? (size_t)dm.Dm : (size_t)dm.W * dm.Dm;  // floats between lines
+    const uint32_t cstride = (VERT ? (uint32_t)dm.W * (uint32_t)dm.Dm : (uint32_t)dm.Dm) * 4u;
+    const int desc_pitch = VERT ? dm.Hd() : dm.Wd();
+    unsigned item = next_item(ctr, lane);
+    while (item < n_items) {
+        const unsigned nxt = next_item(ctr, lane);  // its latency hides behind the walk
+        const ViewPtrs& v = item >= per_view ? v1 : v0;
+        const unsigned r = item >= per_view ? item - per_view : item;
+        const unsigned line = r / ngroups, grp = r - line * ngroups;
+        float* cell = v.vol.main + line * line_step + 64 * grp + 2 * lane;
+        const uint32_t* fdesc_line = (VERT ? v.fdesc_v : v.fdesc_h) + (size_t)line * desc_pitch;
+        const float* rcp_line = (VERT ? v.rcp_v : v.rcp_h) + (size_t)line * desc_pitch;
+        walk_fused(tm, sl, sh, cell, cstride, fdesc_line, rcp_line, len);
+        item = nxt;
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tm_base) : "memory");
+}
+
 // ---- kernel 3: horizontal pass over the tail part ----
 // In the tail part [H][W][Rp] a horizontal chain steps Rp floats at a time and neighbouring chains of a
 // warp would be whole image rows apart (one 32-byte sector per lane and step: measured +0.6 ms per pass
@@ -517,66 +839,107 @@ k_agg_persist(Dims dm, ViewPtrs v0, ViewPtrs v1, int tm_warps, unsigned* ctr)
 // stages the row in shared memory with coalesced loads, turns it into fp64 prefix sums with a block
 // scan, and every output is the same  P[x+b+1] - P[x-a]  as in the walk.
 constexpr int AGT_BLOCK = 256;
-template <bool NORM>
-__global__ void __launch_bounds__(AGT_BLOCK)
-k_agg_tail_h(Dims dm, ViewPtrs v0, ViewPtrs v1)
+
+// In-place inclusive scan of A[1 .. n] (fp64 pairs) by one CTA: warp w owns the contiguous range [w*R, (w+1)*R) and walks it
+// 32 elements at a time (consecutive lanes = consecutive 16-byte slots: conflict-free) with a running carry; the warp
+// totals are exchanged through shared memory once and added in a second sweep.  Ends with a barrier.
+__device__ __forceinline__ void tail_scan(double2* A, double2* warp_tot, int n)
 {
-    extern __shared__ __align__(16) unsigned char tail_raw[];
-    double2* P = reinterpret_cast<double2*>(tail_raw);  // [W + 1]
-    __shared__ double2 warp_tot[AGT_BLOCK / 32];
-    const ViewPtrs& v = blockIdx.y ? v1 : v0;
-    const int y = blockIdx.x, W = dm.W, Rp = dm.Rp, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    float* row = v.vol.tail + (size_t)y * W * Rp + 2 * blockIdx.z;
-    for (int x = tid; x < W; x += AGT_BLOCK) {
-        const float2 c = *reinterpret_cast<const float2*>(row + (size_t)x * Rp);
-        P[x + 1] = make_double2((double)c.x, (double)c.y);
-    }
-    if (tid == 0) P[0] = make_double2(0.0, 0.0);
-    __syncthreads();
-    // inclusive scan: warp w owns the contiguous range [w*R, (w+1)*R) and walks it 32 elements at a time
-    // (consecutive lanes = consecutive 16-byte slots: conflict-free) with a running carry; the warp totals are
-    // exchanged through shared memory once and added in a second sweep.
-    const int R = (((W + AGT_BLOCK / 32 - 1) / (AGT_BLOCK / 32)) + 31) & ~31;
-    const int xb = warp * R, xe = min(W, xb + R);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int R = (((n + AGT_BLOCK / 32 - 1) / (AGT_BLOCK / 32)) + 31) & ~31;
+    const int xb = warp * R, xe = min(n, xb + R);
     double c0 = 0.0, c1 = 0.0;
     for (int x = xb + lane; x - lane < xe; x += 32) {
         double i0 = 0.0, i1 = 0.0;
-        if (x < xe) { const double2 p = P[x + 1]; i0 = p.x; i1 = p.y; }
+        if (x < xe) { const double2 p = A[x + 1]; i0 = p.x; i1 = p.y; }
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const double t0 = __shfl_up_sync(0xffffffffu, i0, o), t1 = __shfl_up_sync(0xffffffffu, i1, o);
             if (lane >= o) { i0 += t0; i1 += t1; }
         }
         i0 += c0; i1 += c1;
-        if (x < xe) P[x + 1] = make_double2(i0, i1);
+        if (x < xe) A[x + 1] = make_double2(i0, i1);
         c0 = __shfl_sync(0xffffffffu, i0, 31);
         c1 = __shfl_sync(0xffffffffu, i1, 31);
     }
+    __syncthreads();  // (also protects warp_tot against the previous scan's readers)
     if (lane == 0) warp_tot[warp] = make_double2(c0, c1);
     __syncthreads();
     double o0 = 0.0, o1 = 0.0;
     for (int w = 0; w < warp; ++w) { o0 += warp_tot[w].x; o1 += warp_tot[w].y; }
     if (warp > 0) {
         for (int x = xb + lane; x < xe; x += 32) {
-            double2 p = P[x + 1];
+            double2 p = A[x + 1];
             p.x += o0; p.y += o1;
-            P[x + 1] = p;
+            A[x + 1] = p;
         }
     }
     __syncthreads();
-    const uint32_t* desc = v.desc_h + (size_t)y * dm.Wd();
-    for (int x = tid; x < W; x += AGT_BLOCK) {
+}
+
+// MODE 0: one plain pass, 1: one normalising pass, 2: a normalising pass followed by a plain pass (the tail part's share
+// of a fused launch).  One CTA per (line, view, disparity pair); the line is staged in shared memory.
+template <bool VERT, int MODE>
+__global__ void __launch_bounds__(AGT_BLOCK)
+k_agg_tail(Dims dm, ViewPtrs v0, ViewPtrs v1)
+{
+    extern __shared__ __align__(16) unsigned char tail_raw[];
+    const int len = VERT ? dm.H : dm.W;
+    double2* P = reinterpret_cast<double2*>(tail_raw);  // [len + 1]
+    double2* Q = P + (len + 1);                         // [len + 1], MODE 2 only
+    __shared__ double2 warp_tot[AGT_BLOCK / 32];
+    const ViewPtrs& v = blockIdx.y ? v1 : v0;
+    const int line = blockIdx.x, Rp = dm.Rp, tid = threadIdx.x;
+    const size_t estride = VERT ? (size_t)dm.W * Rp : (size_t)Rp;  // floats between consecutive positions of the line
+    float* first = v.vol.tail + (VERT ? (size_t)line * Rp : (size_t)line * dm.W * Rp) + 2 * blockIdx.z;
+    for (int x = tid; x < len; x += AGT_BLOCK) {
+        const float2 c = *reinterpret_cast<const float2*>(first + (size_t)x * estride);
+        P[x + 1] = make_double2((double)c.x, (double)c.y);
+    }
+    if (tid == 0) { P[0] = make_double2(0.0, 0.0); if (MODE == 2) Q[0] = make_double2(0.0, 0.0); }
+    __syncthreads();
+    tail_scan(P, warp_tot, len);
+    const uint32_t* desc = VERT ? v.desc_v + (size_t)line * dm.Hd() : v.desc_h + (size_t)line * dm.Wd();
+    for (int x = tid; x < len; x += AGT_BLOCK) {
         const uint32_t w = desc[x];
         const int a = w & 0xff, b = (w >> 8) & 0xff;
         const double2 hi = P[x + b + 1], lo = P[x - a];
         float r0 = __double2float_rn(hi.x - lo.x), r1 = __double2float_rn(hi.y - lo.y);
-        if (NORM) {
+        if (MODE != 0) {
             const RcpN rn = rcp_prepare((float)(w >> 16));
             r0 = div_exact(r0, rn);
             r1 = div_exact(r1, rn);
         }
-        *reinterpret_cast<float2*>(row + (size_t)x * Rp) = make_float2(r0, r1);
+        if (MODE == 2) Q[x + 1] = make_double2((double)r0, (double)r1);
+        else *reinterpret_cast<float2*>(first + (size_t)x * estride) = make_float2(r0, r1);
     }
+    if (MODE == 2) {
+        __syncthreads();
+        tail_scan(Q, warp_tot, len);
+        for (int x = tid; x < len; x += AGT_BLOCK) {
+            const uint32_t w = desc[x];
+            const int a = w & 0xff, b = (w >> 8) & 0xff;
+            const double2 hi = Q[x + b + 1], lo = Q[x - a];
+            *reinterpret_cast<float2*>(first + (size_t)x * estride) =
+                make_float2(__double2float_rn(hi.x - lo.x), __double2float_rn(hi.y - lo.y));
+        }
+    }
+}
+
+template <bool VERT, int MODE>
+static void launch_tail(const Launcher& L, const Dims& d, const ViewPtrs& left, const ViewPtrs& right)
+{
+    if (d.tail() <= 0) return;
+    const int len = VERT ? d.H : d.W, nlines = VERT ? d.W : d.H;
+    const size_t smem = (size_t)(len + 1) * sizeof(double2) * (MODE == 2 ? 2 : 1);
+    static PerDevice smem_set;
+    if (smem > 48 * 1024 && smem > smem_set.cur()) {
+        cudaFuncSetAttribute(k_agg_tail<VERT, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        smem_set.cur() = smem;
+    }
+    dim3 grid((unsigned)nlines, 2, (unsigned)((d.tail() + 1) / 2));
+    k_agg_tail<VERT, MODE><<<grid, AGT_BLOCK, smem, L.stream>>>(d, left, right);
+    L.count(1);
 }
 
 // Generic guarded variant for lines shorter than AGG_LAG + 1 + AGG_PF (tiny images): one
@@ -661,17 +1024,7 @@ static void launch_walk(const Launcher& L, const Dims& d, const ViewPtrs& left, 
     const int len = VERT ? d.H : d.W;
     const long long nl = VERT ? d.W : d.H;
     const AggMix& mix = agg_mix();
-    if (!VERT && d.tail() > 0 && len >= AGG_LAG + 1 + AGG_U) {
-        const size_t smem = (size_t)(d.W + 1) * sizeof(double2);
-        static PerDevice smem_set;
-        if (smem > 48 * 1024 && smem > smem_set.cur()) {
-            cudaFuncSetAttribute(k_agg_tail_h<NORM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            smem_set.cur() = smem;
-        }
-        dim3 grid((unsigned)d.H, 2, (unsigned)((d.tail() + 1) / 2));
-        k_agg_tail_h<NORM><<<grid, AGT_BLOCK, smem, L.stream>>>(d, left, right);
-        L.count(1);
-    }
+    if (!VERT && len >= AGG_LAG + 1 + AGG_U) launch_tail<false, NORM ? 1 : 0>(L, d, left, right);
     if (len >= AGG_LAG + 1 + AGG_U && AGG_NC == 2 && d.Dm >= 64 && d.Dm % 64 == 0 && mix.persist) {
         static PerDevice sm_count;  // doubles as "attribute set on this device"
         if (!sm_count.cur()) {
@@ -717,10 +1070,59 @@ size_t aggregate_overread_floats(const Dims& d)
     return (size_t)(AGG_U + 1) * d.W * (size_t)(d.Dm > d.Rp ? d.Dm : d.Rp);
 }
 
+template <bool VERT>
+static void launch_fused(const Launcher& L, const Dims& d, const ViewPtrs& left, const ViewPtrs& right, unsigned* ctr)
+{
+    static PerDevice sm_count;  // doubles as "attribute set on this device"
+    if (!sm_count.cur()) {
+        cudaFuncSetAttribute(k_agg_fused<VERT>, cudaFuncAttributeMaxDynamicSharedMemorySize, AGF_SMEM);
+        int dev = 0, n = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        sm_count.cur() = (size_t)n;
+    }
+    launch_tail<VERT, 2>(L, d, left, right);  // the tail part's share: staged lines, both passes in shared memory
+    k_agg_fused<VERT><<<(int)sm_count.cur(), AGF_THREADS, AGF_SMEM, L.stream>>>(d, left, right, ctr);
+    L.count(1);
+}
+
+// TSM_AGG_FUSE=0 keeps the eight single-pass launches (A/B measurements); default: H | V.n+V | H.n+H | V.n+V | H.n
+static bool agg_fuse_enabled()
+{
+    static const bool on = [] {
+        const char* e = getenv("TSM_AGG_FUSE");
+        return !(e && e[0] == '0');
+    }();
+    return on;
+}
+
 void aggregate(const Launcher& L, const Dims& d, const ViewPtrs& left, const ViewPtrs& right, unsigned* work_counters)
 {
-    // two work counters (main items, tail items) per pass of the persistent kernel
+    // two work counters (main items, tail items) per pass of the persistent kernels
     cudaMemsetAsync(work_counters, 0, kAggCounterBytes, L.stream);
+    if (agg_fuse_enabled() && AGG_NC == 2 && d.Dm >= 64 && d.Dm % 64 == 0 && d.W >= AGG_LAG + 1 + AGG_U && agg_mix().persist) {
+        unsigned* ctr = work_counters;
+        L.begin("aggregate/h");
+        launch_walk<false, false>(L, d, left, right, ctr);
+        L.end();
+        for (int k = 0; k < kIterations - 1; ++k) {  // iterations alternate H,V | V,H: the pass ending one and the pass starting the next share a direction
+            ctr += 2;
+            if (k % 2 == 0) {
+                L.begin("aggregate/v_norm+v");
+                launch_fused<true>(L, d, left, right, ctr);
+            } else {
+                L.begin("aggregate/h_norm+h");
+                launch_fused<false>(L, d, left, right, ctr);
+            }
+            L.end();
+        }
+        static_assert(kIterations % 2 == 0, "the last pass is a horizontal normalising one");
+        ctr += 2;
+        L.begin("aggregate/h_norm");
+        launch_walk<false, true>(L, d, left, right, ctr);
+        L.end();
+        return;
+    }
     bool hf = true;
     unsigned* ctr = work_counters;
     for (int it = 0; it < kIterations; ++it, ctr += 4) {

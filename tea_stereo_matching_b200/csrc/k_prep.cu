@@ -139,7 +139,8 @@ __global__ void k_arms(const uint32_t* __restrict__ img4, uchar4* __restrict__ a
 // The pass that ENDS an iteration divides by N (:743-749): a vertical pass ends a
 // horizontal-first iteration (N_hf), a horizontal pass a vertical-first one (N_vf).
 __global__ void k_agg_desc(const uchar4* __restrict__ arms, uint32_t* __restrict__ desc_h, uint32_t* __restrict__ desc_v,
-                           float* __restrict__ rcp_h, float* __restrict__ rcp_v, int H, int W, int Wd, int Hd)
+                           float* __restrict__ rcp_h, float* __restrict__ rcp_v, uint32_t* __restrict__ fdesc_h,
+                           uint32_t* __restrict__ fdesc_v, int H, int W, int Wd, int Hd)
 {
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
     if (x >= W || y >= H) return;
@@ -156,6 +157,9 @@ __global__ void k_agg_desc(const uchar4* __restrict__ arms, uint32_t* __restrict
     }
     desc_h[(size_t)y * Wd + x] = (uint32_t)a.z | ((uint32_t)a.w << 8) | ((uint32_t)nv << 16);
     desc_v[(size_t)x * Hd + y] = (uint32_t)a.x | ((uint32_t)a.y << 8) | ((uint32_t)nh << 16);
+    // fused walk (k_agg_fused): distances from the newest prefix to P[o + b + 1] and P[o - a] in ring units of 3
+    fdesc_h[(size_t)y * Wd + x] = 3u * (uint32_t)(kMaxArm - a.w) | (3u * (uint32_t)(kMaxArm + 1 + a.z)) << 8 | ((uint32_t)nv << 16);
+    fdesc_v[(size_t)x * Hd + y] = 3u * (uint32_t)(kMaxArm - a.y) | (3u * (uint32_t)(kMaxArm + 1 + a.x)) << 8 | ((uint32_t)nh << 16);
     // correctly rounded reciprocals of the divisors: the normalising passes divide with one residual correction
     rcp_h[(size_t)y * Wd + x] = __frcp_rn((float)nv);
     rcp_v[(size_t)x * Hd + y] = __frcp_rn((float)nh);
@@ -277,8 +281,8 @@ __global__ void k_gauss_median(const uint32_t* __restrict__ src, uint32_t* __res
 }
 
 void prep_view(const Launcher& L, const Dims& d, int view, const uint8_t* img, uint32_t* img4, uint64_t* census,
-               uchar4* arms, uint32_t* desc_h, uint32_t* desc_v, uint8_t* flags, const ModelParams& mp, const uint32_t* hsi_lut,
-               bool roi)
+               uchar4* arms, uint32_t* desc_h, uint32_t* desc_v, uint32_t* fdesc_h, uint32_t* fdesc_v, uint8_t* flags,
+               const ModelParams& mp, const uint32_t* hsi_lut, bool roi)
 {
     const size_t npx = d.npx();
     dim3 b(32, 8), g((d.W + 31) / 32, (d.H + 7) / 8);
@@ -297,7 +301,8 @@ void prep_view(const Launcher& L, const Dims& d, int view, const uint8_t* img, u
     else k_census<false><<<cg, cb, 0, L.stream>>>(img4, census, d.H, d.W);
     k_arms<<<g, b, 0, L.stream>>>(img4, arms, d.H, d.W, mp);
     k_agg_desc<<<g, b, 0, L.stream>>>(arms, desc_h, desc_v, reinterpret_cast<float*>(desc_h + d.desc_h_words()),
-                                      reinterpret_cast<float*>(desc_v + d.desc_v_words()), d.H, d.W, d.Wd(), d.Hd());
+                                      reinterpret_cast<float*>(desc_v + d.desc_v_words()), fdesc_h + kFdescFront,
+                                      fdesc_v + kFdescFront, d.H, d.W, d.Wd(), d.Hd());
     k_flags<<<g, b, 0, L.stream>>>(img4, flags, d.H, d.W, mp);
     L.count(5);
 }

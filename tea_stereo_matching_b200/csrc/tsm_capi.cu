@@ -42,7 +42,7 @@ struct tsm_ctx {
     bool have_pair = false;
 
     // device buffers
-    Buf img[2], img4[2], census[2], arms[2], desc_h[2], desc_v[2], flags[2], tflags[2], vol[2], vtail[2], wta_[2];
+    Buf img[2], img4[2], census[2], arms[2], desc_h[2], desc_v[2], fdesc_h[2], fdesc_v[2], flags[2], tflags[2], vol[2], vtail[2], wta_[2];
     Buf dense;  // [H][W][Dn] staging for volume taps / pokes
     bool stage_mode = false;  // tsm_stage_run: keep every tap-able buffer complete
     Buf disp[2], fin, ftmp;
@@ -284,6 +284,8 @@ int ensure_arena(tsm_ctx* c, const tsm_adcensus_config* cfg, int H, int W)
         if ((rc = ensure(c, c->arms[k], npx * 4))) return rc;
         if ((rc = ensure(c, c->desc_h[k], d.desc_h_words() * 8, true))) return rc;
         if ((rc = ensure(c, c->desc_v[k], d.desc_v_words() * 8, true))) return rc;
+        if ((rc = ensure(c, c->fdesc_h[k], d.fdesc_h_words() * 4, true))) return rc;
+        if ((rc = ensure(c, c->fdesc_v[k], d.fdesc_v_words() * 4, true))) return rc;
         if ((rc = ensure(c, c->flags[k], npx))) return rc;
         if ((rc = ensure(c, c->tflags[k], ((size_t)2 * H * d.stab_pitch() + 64) * 4, true))) return rc;
         if ((rc = ensure(c, c->vol[k], (npx * d.Dm + aggregate_overread_floats(d)) * 4 + 256, true))) return rc;
@@ -326,6 +328,8 @@ ViewPtrs view_ptrs(tsm_ctx* c, int k)
     v.desc_v = (const uint32_t*)c->desc_v[k].p;
     v.rcp_h = (const float*)(v.desc_h + c->dm.desc_h_words());
     v.rcp_v = (const float*)(v.desc_v + c->dm.desc_v_words());
+    v.fdesc_h = (const uint32_t*)c->fdesc_h[k].p + kFdescFront;
+    v.fdesc_v = (const uint32_t*)c->fdesc_v[k].p + kFdescFront;
     v.flags = (const uint8_t*)c->flags[k].p;
     v.stab = (const uint32_t*)c->tflags[k].p;
     v.vol.main = (float*)c->vol[k].p;
@@ -394,7 +398,8 @@ int run_stages(tsm_ctx* c, int mask, int arg)
         ScopedStage s(c, "prep");
         for (int k = 0; k < 2; ++k)
             prep_view(L, d, k, (const uint8_t*)c->img[k].p, (uint32_t*)c->img4[k].p, (uint64_t*)c->census[k].p,
-                      (uchar4*)c->arms[k].p, (uint32_t*)c->desc_h[k].p, (uint32_t*)c->desc_v[k].p, (uint8_t*)c->flags[k].p,
+                      (uchar4*)c->arms[k].p, (uint32_t*)c->desc_h[k].p, (uint32_t*)c->desc_v[k].p, (uint32_t*)c->fdesc_h[k].p,
+                      (uint32_t*)c->fdesc_v[k].p, (uint8_t*)c->flags[k].p,
                       model_params(c->hsi, c->mask), (const uint32_t*)c->hsi_lut.p, c->roi);
         prep_scan_tables(L, d, (const uint8_t*)c->flags[0].p, (const uint8_t*)c->flags[1].p, (uint32_t*)c->tflags[0].p,
                          (uint32_t*)c->tflags[1].p);
@@ -566,7 +571,7 @@ void tsm_destroy(tsm_ctx* c)
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     Buf* all[] = {&c->img[0], &c->img[1], &c->img4[0], &c->img4[1], &c->census[0], &c->census[1], &c->arms[0], &c->arms[1],
-                  &c->desc_h[0], &c->desc_h[1], &c->desc_v[0], &c->desc_v[1], &c->flags[0], &c->flags[1], &c->tflags[0], &c->tflags[1], &c->vtail[0], &c->vtail[1], &c->dense, &c->vol[0], &c->vol[1], &c->wta_[0], &c->wta_[1],
+                  &c->desc_h[0], &c->desc_h[1], &c->desc_v[0], &c->desc_v[1], &c->fdesc_h[0], &c->fdesc_h[1], &c->fdesc_v[0], &c->fdesc_v[1], &c->flags[0], &c->flags[1], &c->tflags[0], &c->tflags[1], &c->vtail[0], &c->vtail[1], &c->dense, &c->vol[0], &c->vol[1], &c->wta_[0], &c->wta_[1],
                   &c->disp[0], &c->disp[1], &c->fin, &c->ftmp, &c->v_vote, &c->v_lowcnt, &c->v_off, &c->v_mark, &c->v_start, &c->v_stash,
                   &c->v_sums, &c->v_flat, &c->e_gray, &c->e_blur, &c->e_mag, &c->e_gx, &c->e_gy, &c->e_map, &c->e_edges,
                   &c->e_hist, &c->e_lut, &c->e_changed, &c->tab_ad, &c->tab_c, &c->agg_ctr, &c->tab_ad_hsi, &c->hsi_lut, &c->k_in, &c->k_out, &c->k_tab, &c->k_range, &c->r_src, &c->r_map1[0], &c->r_map1[1],
