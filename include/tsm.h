@@ -33,7 +33,9 @@ enum tsm_status {
     TSM_E_ARG = 1,         /* bad argument (NULL, size mismatch, empty image, min>=max, ...) */
     TSM_E_CUDA = 2,        /* CUDA runtime / launch failure, or no device */
     TSM_E_OOM = 3,         /* device or pinned-host allocation failed */
-    TSM_E_UNSUPPORTED = 4, /* valid in the reference but not built yet (minD != 0, Dn > 512) */
+    TSM_E_UNSUPPORTED = 4, /* accepted by the reference's setters but outside what is built: more than 768 cost planes (ROI / mask
+                              matching on images wider than 1535 px), negative disparities, max < 2 * min (the reference's own
+                              WTA range is empty there, ADCensus.cpp:1398) */
     TSM_E_STATE = 5        /* call sequence error (wait without enqueue, tap before run, ...) */
 };
 
@@ -47,7 +49,7 @@ enum tsm_color_model { TSM_COLOR_RGB = 0, TSM_COLOR_HSI = 1 };
  * Tunables (lambda, tau, L, pi, voting, Canny) are the RGB constants of
  * ADCensusParams::setADCensusParams, source/stereo_utils.cpp:271-326. */
 typedef struct tsm_adcensus_config {
-    int32_t min_disparity; /* only 0 is built; others -> TSM_E_UNSUPPORTED */
+    int32_t min_disparity; /* >= 0; with min > 0 the reference's plane-index / disparity mix is reproduced as it is (tsm_common.cuh, Dims) */
     int32_t max_disparity; /* Dn = max - min + 1 cost planes (ADCensus.cpp:345) */
     int32_t color_model;   /* enum tsm_color_model; the reference default-constructs HSI (ADCensus.cpp:409-420) */
     int32_t roi_matching;  /* != 0: ROI mode -- max_disparity is replaced by W / 2 (ADCensus.cpp:339-340), HSI images are hue-filtered

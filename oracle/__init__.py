@@ -155,15 +155,17 @@ class Ref:
             raise FileNotFoundError(f"{path} missing and {REFERENCE_ROOT} not available to build it")
         self.lib = C.CDLL(str(path))
 
-    def run(self, left, right, max_disp: int, serial_scanline: bool = True, volumes: bool = True, model: str = "RGB") -> Stages:
-        """Staged run with taps; volumes are transposed to [H][W][Dn] for comparison.  model "HSI" runs the
-        reference's HSI preprocessing first (bgr2hsi + computeGaussMedian); st.pre = the two preprocessed images."""
+    def run(self, left, right, max_disp: int, serial_scanline: bool = True, volumes: bool = True, model: str = "RGB",
+            min_disp: int = 0) -> Stages:
+        """Staged run with taps; volumes are transposed to [H][W][Dn] for comparison (Dn = max_disp - min_disp + 1 planes).
+        model "HSI" runs the reference's HSI preprocessing first (bgr2hsi + computeGaussMedian); st.pre = the two
+        preprocessed images."""
         left, right = _check_pair(left, right)
         H, W, _ = left.shape
-        Dn = max_disp + 1
+        Dn = max_disp - min_disp + 1
         st, t = _alloc_stages(H, W, Dn, volumes, (Dn, H, W))
         pre = [np.empty((H, W, 3), np.uint8), np.empty((H, W, 3), np.uint8)]
-        rc = self.lib.ref_adcensus_staged_model(_p(left), _p(right), H, W, 0, max_disp, int(serial_scanline),
+        rc = self.lib.ref_adcensus_staged_model(_p(left), _p(right), H, W, min_disp, max_disp, int(serial_scanline),
                                                 {"RGB": 0, "HSI": 1}[model], _p(pre[0]), _p(pre[1]), C.byref(t))
         st.pre = pre
         if rc != 0:

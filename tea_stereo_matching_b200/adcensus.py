@@ -262,12 +262,13 @@ class ADCensus:
 class StageRunner:
     """Parity harness over tsm_stage_begin / tsm_stage_run / tsm_tap / tsm_poke (tests only)."""
 
-    def __init__(self, left, right, max_disparity: int, device: int = 0, model: "ColorModel | None" = None):
+    def __init__(self, left, right, max_disparity: int, device: int = 0, model: "ColorModel | None" = None,
+                 min_disparity: int = 0):
         self.ctx = Context(device)
         self.left, self.right = _as_bgr(left), _as_bgr(right)
         self.H, self.W, _ = self.left.shape
-        self.Dn = max_disparity + 1
-        self.cfg = N.Config(0, max_disparity, int(ColorModel.RGB if model is None else model), 0, 0, 0)
+        self.Dn = max_disparity - min_disparity + 1  # cost planes (ADCensus.cpp:345)
+        self.cfg = N.Config(min_disparity, max_disparity, int(ColorModel.RGB if model is None else model), 0, 0, 0)
         L = self.ctx._lib
         self.ctx.check(L.tsm_stage_begin(self.ctx.handle, C.byref(self.cfg), _ptr(self.left), self.left.strides[0],
                                          _ptr(self.right), self.right.strides[0], self.H, self.W))

@@ -237,6 +237,74 @@ static void launch_cost(const Launcher& L, const Dims& d, const ViewPtrs& left, 
     L.count(1);
 }
 
+// ---- general form (slow path) ----------------------------------------------------------------------------
+// costInitialize for minD != 0 (ADCensus.cpp:556-561): plane p of the left volume holds the cost of the pixel pair
+// (xL, xR) = (x - minD, x - p), plane p of the right volume that of (x + p, x + minD) -- the matched pair is p - minD
+// apart (negative for p < minD), not p, and the right volume is no longer a shear of the left one inside the image.
+// One warp per pixel of one view, lanes over the planes; signatures come straight from global memory (L2-resident).
+template <bool HSI, bool MASK>
+__global__ void __launch_bounds__(256)
+k_cost_init_general(Dims dm, ViewPtrs vl, ViewPtrs vr, const float* __restrict__ tab_ad, const float* __restrict__ tab_c)
+{
+    const int H = dm.H, W = dm.W, Dn = dm.Dn, m = dm.minD;
+    const int lane = threadIdx.x & 31, x = blockIdx.x * 8 + (threadIdx.x >> 5), y = blockIdx.y, view = blockIdx.z;
+    if (x >= W) return;
+    const size_t npx = (size_t)H * W, row = (size_t)y * W;
+    const int hw = kCensusW / 2;
+    const bool yout = (y - kCensusH / 2 < 0) || (y + kCensusH / 2 >= H);
+    constexpr int TAB_AD_USED = HSI ? kTabAdHsi : kTabAdRgb;
+    const ViewPtrs& own = view ? vr : vl;
+    const bool hole = MASK && own.img4[row + x] == 0u;  // a black pixel of the own view costs 2 (:551-555)
+    auto load = [&](const ViewPtrs& v, int c, Sig& s) {
+        const bool ok = !yout && c - hw >= 0 && c + hw < W;
+        s.pix = ok ? v.img4[row + c] : kInvalidPix;
+#pragma unroll
+        for (int p = 0; p < 6; ++p) {
+            const uint64_t w = ok ? v.census[(size_t)p * npx + row + c] : 0ull;
+            s.w[2 * p] = (uint32_t)w;
+            s.w[2 * p + 1] = (uint32_t)(w >> 32);
+        }
+    };
+    // the pixel of the pair that does not depend on the plane: left view -> xL = x - minD, right view -> xR = x + minD
+    Sig f;
+    load(view ? vr : vl, view ? x + m : x - m, f);
+    for (int p0 = 0; p0 < Dn; p0 += 32) {
+        const int p = p0 + lane;
+        if (p >= Dn) break;
+        Sig g;
+        load(view ? vl : vr, view ? x + p : x - p, g);  // left view: xR = x - p; right view: xL = x + p
+        float cost = 2.f;
+        if (!hole && f.pix != kInvalidPix && g.pix != kInvalidPix) {
+            int ad3;
+            if (HSI) {
+                const uint32_t dv = __vabsdiffu4(f.pix, g.pix);
+                const int hd = dv & 0xffu;
+                ad3 = min(2 * min(hd, 255 - hd) + 5 * (int)(((dv >> 8) & 0xffu) + ((dv >> 16) & 0xffu)), TAB_AD_USED - 1);
+            } else {
+                ad3 = min((int)__vsadu4(f.pix, g.pix), TAB_AD_USED - 1);
+            }
+            float ec = tab_c[census_count(f, g)];
+            if (MASK && (f.pix == 0u || g.pix == 0u)) ec = 0.f;
+            cost = __fsub_rn(__fsub_rn(2.f, tab_ad[ad3]), ec);
+        }
+        *cell_ptr(own.vol, dm, row + x, p) = cost;
+    }
+}
+
+void cost_init_general(const Launcher& L, const Dims& d, const ViewPtrs& left, const ViewPtrs& right, const float* d_tab_ad,
+                       const float* d_tab_census, bool hsi, bool mask)
+{
+    dim3 grid((d.W + 7) / 8, d.H, 2);
+    if (hsi) {
+        if (mask) k_cost_init_general<true, true><<<grid, 256, 0, L.stream>>>(d, left, right, d_tab_ad, d_tab_census);
+        else k_cost_init_general<true, false><<<grid, 256, 0, L.stream>>>(d, left, right, d_tab_ad, d_tab_census);
+    } else {
+        if (mask) k_cost_init_general<false, true><<<grid, 256, 0, L.stream>>>(d, left, right, d_tab_ad, d_tab_census);
+        else k_cost_init_general<false, false><<<grid, 256, 0, L.stream>>>(d, left, right, d_tab_ad, d_tab_census);
+    }
+    L.count(1);
+}
+
 void cost_init(const Launcher& L, const Dims& d, const ViewPtrs& left, const ViewPtrs& right, const float* d_tab_ad,
                const float* d_tab_census, bool hsi, bool mask)
 {

@@ -13,7 +13,8 @@ namespace cg = cooperative_groups;
 namespace tsm {
 
 // =========================================================================== a9
-// cost2disparity (ADCensus.cpp:1394-1413): first strict minimum over d = 0..Dn-1.
+// cost2disparity (ADCensus.cpp:1394-1413): first strict minimum over the PLANES minD .. maxD - minD = minD .. Dn - 1; the plane
+// index is what the reference reports as the disparity.
 __global__ void __launch_bounds__(256) k_wta(Vol vol, Dims dm, int32_t* __restrict__ disp)
 {
     const size_t npx = dm.npx();
@@ -24,6 +25,7 @@ __global__ void __launch_bounds__(256) k_wta(Vol vol, Dims dm, int32_t* __restri
     float best = FLT_MAX;
     int bd = INT_MAX;
     for (int d = lane; d < Dn; d += 32) {
+        if (d < dm.minD) continue;
         const float v = *cell_ptr(vol, dm, p, d);
         if (best > v) { best = v; bd = d; }
     }
@@ -69,8 +71,9 @@ void volume_scatter(const Launcher& L, const Dims& d, const float* dense, const 
 }
 
 // ========================================================================== a10
-// outlierElimination (ADCensus.cpp:1013-1044), dispTolerance = 0, minD = 0.
-__global__ void k_lrc(const int32_t* __restrict__ dl, const int32_t* __restrict__ dr, int32_t* __restrict__ out, int H, int W, int maxD)
+// outlierElimination (ADCensus.cpp:1013-1044), dispTolerance = 0; the markers stay -1 / -2 whatever minD is (:415-416).
+__global__ void k_lrc(const int32_t* __restrict__ dl, const int32_t* __restrict__ dr, int32_t* __restrict__ out, int H, int W, int minD,
+                      int maxD)
 {
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
     if (x >= W) return;
@@ -79,7 +82,7 @@ __global__ void k_lrc(const int32_t* __restrict__ dl, const int32_t* __restrict_
     if (x - disp < 0 || rrow[x - disp] != disp) {
         bool occlusion = true;
         const int dmax = min(maxD, x);
-        for (int d = 0; d <= dmax; ++d)
+        for (int d = minD; d <= dmax; ++d)
             if (rrow[x - d] == d) { occlusion = false; break; }
         disp = occlusion ? kOcclusion : kMismatch;
     }
@@ -89,7 +92,7 @@ __global__ void k_lrc(const int32_t* __restrict__ dl, const int32_t* __restrict_
 void lrc(const Launcher& L, const Dims& d, const int32_t* dl, const int32_t* dr, int32_t* out)
 {
     dim3 g((d.W + 127) / 128, d.H);
-    k_lrc<<<g, 128, 0, L.stream>>>(dl, dr, out, d.H, d.W, d.Dn - 1);
+    k_lrc<<<g, 128, 0, L.stream>>>(dl, dr, out, d.H, d.W, d.minD, d.minD + d.Dn - 1);
     L.count(1);
 }
 
@@ -113,7 +116,7 @@ void lrc(const Launcher& L, const Dims& d, const int32_t* dl, const int32_t* dr,
 // Lanes always run along x so the disparity reads are coalesced.
 template <bool HF, typename F>
 __device__ __forceinline__ void for_each_region(const int32_t* __restrict__ disp, const uchar4* __restrict__ arms, int W,
-                                                size_t p, int lane, F f)
+                                                size_t p, int lane, int minD, F f)
 {
     const uchar4 a = arms[p];
     if (HF) {
@@ -124,7 +127,7 @@ __device__ __forceinline__ void for_each_region(const int32_t* __restrict__ disp
                 const int i = i0 + lane;
                 const bool in = i <= (int)ac.w;
                 const int v = in ? disp[c + i] : -1;
-                f(in && v >= 0, v);
+                f(in && v >= minD, v - minD);  // valid: disp >= minD; histogram bin disp - minD (:1127-1131)
             }
         }
     } else {
@@ -144,7 +147,7 @@ __device__ __forceinline__ void for_each_region(const int32_t* __restrict__ disp
             for (int i = -mup; i <= mdown; ++i) {
                 const bool in = oin && i >= -up && i <= down;
                 const int v = in ? disp[c + (ptrdiff_t)i * W] : -1;
-                f(in && v >= 0, v);
+                f(in && v >= minD, v - minD);  // valid: disp >= minD; histogram bin disp - minD (:1127-1131)
             }
         }
     }
@@ -180,7 +183,7 @@ __device__ __forceinline__ void hist_add(int* hist, bool valid, int v, int lane)
 }
 
 // First arg-max over d ascending + the ratio test of ADCensus.cpp:1138-1152.
-__device__ __forceinline__ int vote_decide(const int* hist, int Dn, int nv, int dp, int lane)
+__device__ __forceinline__ int vote_decide(const int* hist, int Dn, int nv, int dp, int lane, int minD)
 {
     int best = 0, bd = INT_MAX;
     for (int d = lane; d < Dn; d += 32) {
@@ -194,7 +197,7 @@ __device__ __forceinline__ int vote_decide(const int* hist, int Dn, int nv, int 
         if (oh > best || (oh == best && od < bd)) { best = oh; bd = od; }
     }
     const float ratio = __fdiv_rn((float)best, (float)nv);  // hist[d] / (float)vote, :1144
-    return (best > 0 && ratio > kVotingRatio) ? bd : dp;
+    return (best > 0 && ratio > kVotingRatio) ? bd + minD : dp;
 }
 
 // Pass A: ONE traversal of the cross region per outlier builds its histogram and its vote count.
@@ -205,7 +208,8 @@ __device__ __forceinline__ int vote_decide(const int* hist, int Dn, int nv, int 
 template <bool HF>
 __global__ void __launch_bounds__(VOTE_TILE)
 k_vote_pass_a(const int32_t* __restrict__ disp, const uchar4* __restrict__ arms, int32_t* __restrict__ vote,
-              int32_t* __restrict__ lowcnt, uint16_t* __restrict__ stash, int32_t* __restrict__ out, size_t npx, int W, int Dn)
+              int32_t* __restrict__ lowcnt, uint16_t* __restrict__ stash, int32_t* __restrict__ out, size_t npx, int W, int Dn,
+              int minD)
 {
     extern __shared__ int hist_all[];  // [VOTE_WARPS][Dn]
     __shared__ int list[VOTE_TILE];
@@ -216,7 +220,7 @@ k_vote_pass_a(const int32_t* __restrict__ disp, const uchar4* __restrict__ arms,
     bool outlier = false;
     if (pt < npx) {
         const int dp = disp[pt];
-        outlier = dp < 0;
+        outlier = dp < minD;
         if (!outlier) { vote[pt] = 0; lowcnt[pt] = 0; out[pt] = dp; }
     }
     const int n = tile_compact(outlier, threadIdx.x, list, &count);
@@ -228,14 +232,14 @@ k_vote_pass_a(const int32_t* __restrict__ disp, const uchar4* __restrict__ arms,
         for (int d = lane; d < Dn; d += 32) hist[d] = 0;
         __syncwarp();
         int cnt = 0;
-        for_each_region<HF>(disp, arms, W, p, lane, [&](bool valid, int v) {
+        for_each_region<HF>(disp, arms, W, p, lane, minD, [&](bool valid, int v) {
             cnt += __popc(__ballot_sync(0xffffffffu, valid));
             hist_add(hist, valid, v, lane);
         });
         __syncwarp();
         int res = dp;
         if (cnt > kVotingThresh) {
-            res = vote_decide(hist, Dn, cnt, dp, lane);
+            res = vote_decide(hist, Dn, cnt, dp, lane, minD);
         } else if (cnt > 0) {
             // park the votes (order is irrelevant for a histogram): bin d contributes hist[d] copies of d
             uint16_t* dst = stash + p * kVotingThresh;
@@ -263,11 +267,11 @@ k_vote_pass_a(const int32_t* __restrict__ disp, const uchar4* __restrict__ arms,
 }
 
 __global__ void k_vote_mark(const int32_t* __restrict__ disp, const int32_t* __restrict__ vote, const int32_t* __restrict__ off,
-                            int32_t* __restrict__ mark, size_t npx)
+                            int32_t* __restrict__ mark, size_t npx, int minD)
 {
     const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= npx) return;
-    mark[p] = (disp[p] < 0 && vote[p] > kVotingThresh) ? off[p] : 0;
+    mark[p] = (disp[p] < minD && vote[p] > kVotingThresh) ? off[p] : 0;
 }
 
 // parked votes -> CSR payload in raster order of their pixels
@@ -288,7 +292,7 @@ template <bool HF>
 __global__ void __launch_bounds__(VOTE_TILE)
 k_vote_pass_b(const int32_t* __restrict__ disp, const uchar4* __restrict__ arms, const int32_t* __restrict__ vote,
               const int32_t* __restrict__ off, const int32_t* __restrict__ start, const uint16_t* __restrict__ flat,
-              int32_t* __restrict__ out, size_t npx, int W, int Dn)
+              int32_t* __restrict__ out, size_t npx, int W, int Dn, int minD)
 {
     extern __shared__ int hist_all[];  // [VOTE_WARPS][Dn]
     __shared__ int list[VOTE_TILE];
@@ -297,7 +301,7 @@ k_vote_pass_b(const int32_t* __restrict__ disp, const uchar4* __restrict__ arms,
     __syncthreads();
     const size_t p0 = (size_t)blockIdx.x * VOTE_TILE, pt = p0 + threadIdx.x;
     bool redo = false;
-    if (pt < npx) redo = disp[pt] < 0 && vote[pt] > kVotingThresh && start[pt] < off[pt];
+    if (pt < npx) redo = disp[pt] < minD && vote[pt] > kVotingThresh && start[pt] < off[pt];
     const int n = tile_compact(redo, threadIdx.x, list, &count);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int* hist = hist_all + warp * Dn;
@@ -305,14 +309,14 @@ k_vote_pass_b(const int32_t* __restrict__ disp, const uchar4* __restrict__ arms,
         const size_t p = p0 + list[i];
         for (int d = lane; d < Dn; d += 32) hist[d] = 0;
         __syncwarp();
-        for_each_region<HF>(disp, arms, W, p, lane, [&](bool valid, int v) { hist_add(hist, valid, v, lane); });
+        for_each_region<HF>(disp, arms, W, p, lane, minD, [&](bool valid, int v) { hist_add(hist, valid, v, lane); });
         for (int j0 = start[p]; j0 < off[p]; j0 += 32) {  // the leak
             const int j = j0 + lane;
             const bool in = j < off[p];
             hist_add(hist, in, in ? (int)flat[j] : 0, lane);
         }
         __syncwarp();
-        const int res = vote_decide(hist, Dn, vote[p], disp[p], lane);
+        const int res = vote_decide(hist, Dn, vote[p], disp[p], lane, minD);
         if (lane == 0) out[p] = res;
         __syncwarp();
     }
@@ -425,15 +429,15 @@ static void region_voting_t(const Launcher& L, const Dims& d, const int32_t* dis
     const size_t npx = d.npx();
     const unsigned wblocks = (unsigned)((npx + VOTE_TILE - 1) / VOTE_TILE);
     const size_t smem = (size_t)VOTE_WARPS * d.Dn * sizeof(int);
-    k_vote_pass_a<HF><<<wblocks, VOTE_TILE, smem, L.stream>>>(disp_in, arms, s.vote, s.lowcnt, s.stash, disp_out, npx, d.W, d.Dn);
+    k_vote_pass_a<HF><<<wblocks, VOTE_TILE, smem, L.stream>>>(disp_in, arms, s.vote, s.lowcnt, s.stash, disp_out, npx, d.W, d.Dn, d.minD);
     L.count(1);
     exclusive_scan<OpSum>(L, s.lowcnt, s.off, s.blocksums, npx);
-    k_vote_mark<<<(unsigned)((npx + 255) / 256), 256, 0, L.stream>>>(disp_in, s.vote, s.off, s.mark, npx);
+    k_vote_mark<<<(unsigned)((npx + 255) / 256), 256, 0, L.stream>>>(disp_in, s.vote, s.off, s.mark, npx, d.minD);
     L.count(1);
     exclusive_scan<OpMax>(L, s.mark, s.start, s.blocksums, npx);
     k_vote_copy<<<(unsigned)((npx + 255) / 256), 256, 0, L.stream>>>(s.lowcnt, s.off, s.stash, s.flat, npx);
     k_vote_pass_b<HF><<<wblocks, VOTE_TILE, smem, L.stream>>>(
-        disp_in, arms, s.vote, s.off, s.start, s.flat, disp_out, npx, d.W, d.Dn);
+        disp_in, arms, s.vote, s.off, s.start, s.flat, disp_out, npx, d.W, d.Dn, d.minD);
     L.count(2);
 }
 
@@ -450,13 +454,13 @@ __constant__ int c_dirW[16] = {0, 2, 2, 2, 0, -2, -2, -2, 1, 2, 2, 1, -1, -2, -2
 __constant__ int c_dirH[16] = {2, 2, 0, -2, -2, -2, 0, 2, 2, 1, -1, -2, -2, -1, 1, 2};
 
 __global__ void k_interpolate(const int32_t* __restrict__ disp, int32_t* __restrict__ out, const uint32_t* __restrict__ img4, int H, int W,
-                              int hsi)
+                              int hsi, int minD)
 {
     const int w = blockIdx.x * blockDim.x + threadIdx.x, h = blockIdx.y * blockDim.y + threadIdx.y;
     if (w >= W || h >= H) return;
     const size_t p = (size_t)h * W + w;
     const int own = disp[p];
-    if (own >= 0) { out[p] = own; return; }
+    if (own >= minD) { out[p] = own; return; }
     const uint32_t pc = img4[p];
     // occlusion: min over the 16 entries, each initialised to the pixel's own value (:1180, :1211-1216),
     // so a single direction without a hit keeps the pixel at -1
@@ -475,7 +479,7 @@ __global__ void k_interpolate(const int32_t* __restrict__ disp, int32_t* __restr
             inside = hD >= 0 && hD < H && wD >= 0 && wD < W;
             if (inside) {
                 const int v = disp[(size_t)hD * W + wD];
-                if (v >= 0) {
+                if (v >= minD) {
                     nd = v;
                     const uint32_t qc = img4[(size_t)hD * W + wD];
                     nf = hsi ? hue_diff_u32(pc, qc) : color_diff_u32(pc, qc);
@@ -487,14 +491,14 @@ __global__ void k_interpolate(const int32_t* __restrict__ disp, int32_t* __restr
         if (k == 0) { md = nd; mf = nf; }
         else if (mf < 0 || (mf > nf && nf > 0)) { md = nd; mf = nf; }
     }
-    out[p] = (own == kOcclusion) ? occ_min : md;
+    out[p] = (own == minD - 1) ? occ_min : md;  // the occlusion test is minD - 1 (:1209) although the marker written by the LRC is always -1
 }
 
 void proper_interpolation(const Launcher& L, const Dims& d, const int32_t* disp_in, int32_t* disp_out, const uint32_t* img4_left,
                           bool hsi)
 {
     dim3 b(32, 8), g((d.W + 31) / 32, (d.H + 7) / 8);
-    k_interpolate<<<g, b, 0, L.stream>>>(disp_in, disp_out, img4_left, d.H, d.W, hsi ? 1 : 0);
+    k_interpolate<<<g, b, 0, L.stream>>>(disp_in, disp_out, img4_left, d.H, d.W, hsi ? 1 : 0, d.minD);
     L.count(1);
 }
 
@@ -687,14 +691,15 @@ __global__ void k_discont_adjust(const int32_t* __restrict__ disp, int32_t* __re
             if (e(h - 1, w - 1) || e(h, w - 1) || e(h + 1, w - 1))
                 if (e(h - 1, w + 1) || e(h, w + 1) || e(h + 1, w + 1)) dir = 6;
         }
-        if (dir != -1 && d >= 0) {
+        const int m = dm.minD;  // valid: disp >= minD; the volume is read at plane disp - minD (:1310-1322)
+        if (dir != -1 && d >= m) {
             dir = (dir + 4) % 8;
-            float cost = *cell_ptr(vol, dm, p, d);
+            float cost = *cell_ptr(vol, dm, p, d - m);
             const size_t p1 = (size_t)(h + c_adjH[dir]) * W + (w + c_adjW[dir]);
             const size_t p2 = (size_t)(h + c_adjH[dir + 1]) * W + (w + c_adjW[dir + 1]);
             const int d1 = disp[p1], d2 = disp[p2];
-            const float c1 = d1 >= 0 ? *cell_ptr(vol, dm, p1, d1) : -1.f;
-            const float c2 = d2 >= 0 ? *cell_ptr(vol, dm, p2, d2) : -1.f;
+            const float c1 = d1 >= m ? *cell_ptr(vol, dm, p1, d1 - m) : -1.f;
+            const float c2 = d2 >= m ? *cell_ptr(vol, dm, p2, d2 - m) : -1.f;
             if (c1 != -1.f && c1 < cost) { d = d1; cost = c1; }
             if (c2 != -1.f && c2 < cost) { d = d2; }
         }
@@ -751,8 +756,9 @@ __global__ void k_subpixel(const int32_t* __restrict__ disp, Vol vol, Dims dm, f
     if (p >= npx) return;
     const int d = disp[p];
     float f = (float)d;
-    if (d > 0 && d < Dn - 1) {
-        const float cost = *cell_ptr(vol, dm, p, d), cp = *cell_ptr(vol, dm, p, d + 1), cm = *cell_ptr(vol, dm, p, d - 1);
+    const int q = d - dm.minD;  // minD < d < maxD, planes d - minD and its neighbours (:1355-1362)
+    if (q > 0 && q < Dn - 1) {
+        const float cost = *cell_ptr(vol, dm, p, q), cp = *cell_ptr(vol, dm, p, q + 1), cm = *cell_ptr(vol, dm, p, q - 1);
         const float num = __fsub_rn(cp, cm);
         const float den = __fmul_rn(2.f, __fsub_rn(__fadd_rn(cp, cm), __fmul_rn(2.f, cost)));
         const float diff = __fdiv_rn(num, den);

@@ -181,20 +181,20 @@ __global__ void k_flags(const uint32_t* __restrict__ img4, uint8_t* __restrict__
 
 // ---- scan tables for the scanline kernels -------------------------------------------
 // stab[plane][y][kTfPad + c], c in [-kTfPad, pitch - kTfPad):
-//   bits 0..15: flag bit `plane` of the OTHER image at (y, c + s*32k), k = 0..K-1, 0 outside the image --
+//   bits 0..23: flag bit `plane` of the OTHER image at (y, c + s*(32k + minD)), k = 0..K-1, 0 outside the image --
 //               a lane of the scanline warp that handles d = lane + 32k gets all its K similarity
 //               bits from the one word at column x + s*lane;
 //   bit 31    : flag bit `plane` of the OWN image at (y, c);
 //   bits 30/29: mask matching only, see below.
 __global__ void k_scan_table(const uint8_t* __restrict__ fown, const uint8_t* __restrict__ foth, uint32_t* __restrict__ stab,
-                             int H, int W, int Wp, int s, int K)
+                             int H, int W, int Wp, int s, int K, int minD)
 {
     const int cx = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
     if (cx >= Wp) return;
     const int c = cx - kTfPad;
     unsigned tv = 0, th = 0;
     for (int k = 0; k < K; ++k) {
-        const int x = c + s * 32 * k;
+        const int x = c + s * (32 * k + minD);  // plane p = lane + 32 k looks at x +- (p + minD), ADCensus.cpp:890
         if (x >= 0 && x < W) {
             const unsigned f = foth[(size_t)y * W + x];
             tv |= (f & 1u) << k;
@@ -223,8 +223,8 @@ void prep_scan_tables(const Launcher& L, const Dims& d, const uint8_t* flags_lef
     const int Wp = d.stab_pitch(), K = (d.Dn + 31) / 32;
     dim3 tg((Wp + 127) / 128, d.H);
     // the left volume looks at the right image at x + d, the right volume at the left image at x - d
-    k_scan_table<<<tg, 128, 0, L.stream>>>(flags_left, flags_right, stab_left, d.H, d.W, Wp, 1, K);
-    k_scan_table<<<tg, 128, 0, L.stream>>>(flags_right, flags_left, stab_right, d.H, d.W, Wp, -1, K);
+    k_scan_table<<<tg, 128, 0, L.stream>>>(flags_left, flags_right, stab_left, d.H, d.W, Wp, 1, K, d.minD);
+    k_scan_table<<<tg, 128, 0, L.stream>>>(flags_right, flags_left, stab_right, d.H, d.W, Wp, -1, K, d.minD);
     L.count(2);
 }
 

@@ -165,15 +165,26 @@ __device__ __forceinline__ void store_vec(float* dst, float* tdst, const float (
 }
 
 // cost2disparity: first strict minimum over d (ADCensus.cpp:1398-1409).
+// Only the planes minD .. Dn - 1 take part (:1398); costs are >= 0, so their bit patterns order like unsigned integers and
+// 0xffffffff stands for "excluded".
 template <int K>
-__device__ __forceinline__ int warp_argmin(const float (&v)[K], int lane)
+__device__ __forceinline__ int warp_argmin(const float (&v)[K], int lane, int minD)
 {
     unsigned bb = __float_as_uint(v[0]);
     int bd = lane;
+    if (minD == 0) {  // warp-uniform: the usual case pays nothing for the range test
 #pragma unroll
-    for (int k = 1; k < K; ++k) {
-        const unsigned b = __float_as_uint(v[k]);
-        if (b < bb) { bb = b; bd = lane + 32 * k; }
+        for (int k = 1; k < K; ++k) {
+            const unsigned b = __float_as_uint(v[k]);
+            if (b < bb) { bb = b; bd = lane + 32 * k; }
+        }
+    } else {
+        if (lane < minD) bb = 0xffffffffu;
+#pragma unroll
+        for (int k = 1; k < K; ++k) {
+            const unsigned b = lane + 32 * k >= minD ? __float_as_uint(v[k]) : 0xffffffffu;
+            if (b < bb) { bb = b; bd = lane + 32 * k; }
+        }
     }
     const unsigned gmin = __reduce_min_sync(0xffffffffu, bb);
     return (int)__reduce_min_sync(0xffffffffu, bb == gmin ? (unsigned)bd : 0x7fffffffu);
@@ -281,12 +292,12 @@ __device__ __forceinline__ void scan_dir(float (&prev)[K], const Vol& vol, const
         if (i + SC_NST < count && elect_one()) issue(st + dep, bar);
         advance_producer();
 
-        const bool changed = scan_step<K>(prev, cur, tw & 0xffffu, ow >> 31, lane, sp, ((ow >> (dir > 0 ? 30 : 29)) & 1u) != 0);
+        const bool changed = scan_step<K>(prev, cur, tw & 0x1fffffffu, ow >> 31, lane, sp, ((ow >> (dir > 0 ? 30 : 29)) & 1u) != 0);
         if (changed && do_store) store_vec<K>(dst, tdst, prev, lane, has_tail, lastvalid);
         dst += vstep;
         tdst += wstep;
         if (WTA) {
-            const int best = warp_argmin<K>(prev, lane);
+            const int best = warp_argmin<K>(prev, lane, dm.minD);
             if (lane == 0) *wdst = best;
             wdst += pstep;
         }
@@ -359,7 +370,7 @@ k_scanline(Dims dm, ViewPtrs v0, ViewPtrs v1, ScanParams sp, int32_t* wta0, int3
     } else {
         // last pass: fuse the WTA; pixel len-1 is final after the forward pass.
         int32_t* wta_out = view ? wta1 : wta0;
-        const int best = warp_argmin<K>(prev, lane);
+        const int best = warp_argmin<K>(prev, lane, dm.minD);
         if (lane == 0) wta_out[(size_t)line * dm.W + len - 1] = best;
         const bool do_store = view == 0 || sp.store_right_final != 0;
         scan_dir<K, VERT, true>(prev, v.vol, v.stab, dm, pipe, line, len - 2, -1, len - 1, sgn, lane, has_tail, lastvalid, do_store,
@@ -405,8 +416,11 @@ void scanline(const Launcher& L, const Dims& d, const ViewPtrs& left, const View
     switch (K) {
         TSM_SCAN_CASE(1) TSM_SCAN_CASE(2) TSM_SCAN_CASE(3) TSM_SCAN_CASE(4) TSM_SCAN_CASE(5) TSM_SCAN_CASE(6)
         TSM_SCAN_CASE(7) TSM_SCAN_CASE(8) TSM_SCAN_CASE(9) TSM_SCAN_CASE(10) TSM_SCAN_CASE(11) TSM_SCAN_CASE(12)
-        TSM_SCAN_CASE(13) TSM_SCAN_CASE(14) TSM_SCAN_CASE(15)
-        default: launch_scan<16>(L, d, left, right, sp, wta_left, wta_right); break;  // Dn <= 512 (checked by the caller)
+        TSM_SCAN_CASE(13) TSM_SCAN_CASE(14) TSM_SCAN_CASE(15) TSM_SCAN_CASE(16)
+        // ROI / mask matching searches W / 2 + 1 levels (ADCensus.cpp:339-340): 641 at the reference's 1280-wide demo size
+        TSM_SCAN_CASE(17) TSM_SCAN_CASE(18) TSM_SCAN_CASE(19) TSM_SCAN_CASE(20) TSM_SCAN_CASE(21) TSM_SCAN_CASE(22)
+        TSM_SCAN_CASE(23)
+        default: launch_scan<24>(L, d, left, right, sp, wta_left, wta_right); break;  // Dn <= kMaxLevels (checked by the caller)
     }
 #undef TSM_SCAN_CASE
 }

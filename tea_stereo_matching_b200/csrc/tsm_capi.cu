@@ -37,7 +37,7 @@ struct tsm_ctx {
     long long launches = 0;
 
     // geometry of the arena
-    Dims dm{0, 0, 0, 0, 0};
+    Dims dm{0, 0, 0, 0, 0, 0};
     tsm_adcensus_config cfg{};
     bool have_pair = false;
 
@@ -148,11 +148,17 @@ int check_cfg(tsm_ctx* c, const tsm_adcensus_config* cfg, int H, int W)
     if ((long long)cfg->min_disparity * cfg->max_disparity < 0 || cfg->min_disparity >= cfg->max_disparity)
         return fail(c, TSM_E_ARG, "[ADCensus] Set MinMaxDisparity error.");
     if (cfg->offset < 0) return fail(c, TSM_E_ARG, "[ADCensus] Offset must be positive.");  // ADCensus.cpp:325-326
-    if (cfg->min_disparity != 0)
-        return fail(c, TSM_E_UNSUPPORTED, "[ADCensus] min_disparity != 0 is not built yet");
+    if (cfg->min_disparity < 0)
+        return fail(c, TSM_E_UNSUPPORTED, "[ADCensus] negative disparities index the reference's cost planes out of range (ADCensus.cpp:1398)");
+    // cost2disparity walks the planes minD .. maxD - minD (ADCensus.cpp:1398): with maxD < 2 minD the loop is empty and the
+    // reference returns uninitialised memory
+    if (!(cfg->roi_matching || cfg->mask_matching) && cfg->max_disparity < 2 * (long long)cfg->min_disparity)
+        return fail(c, TSM_E_UNSUPPORTED, "[ADCensus] max_disparity < 2 * min_disparity: the reference's WTA range is empty");
     // ROI mode searches the whole half width: maxDisparity = width / 2 at compute time (ADCensus.cpp:339-340)
-    if (((cfg->roi_matching || cfg->mask_matching) ? W / 2 : cfg->max_disparity) + 1 > 512)
-        return fail(c, TSM_E_UNSUPPORTED, "[ADCensus] more than 512 disparity levels");
+    if ((cfg->roi_matching || cfg->mask_matching) && W / 2 < 2 * (long long)cfg->min_disparity)
+        return fail(c, TSM_E_UNSUPPORTED, "[ADCensus] W / 2 < 2 * min_disparity: the reference's WTA range is empty");
+    if (((cfg->roi_matching || cfg->mask_matching) ? W / 2 : cfg->max_disparity) - cfg->min_disparity + 1 > kMaxLevels)
+        return fail(c, TSM_E_UNSUPPORTED, "[ADCensus] more than %d disparity levels", kMaxLevels);
     if ((cfg->roi_matching || cfg->mask_matching) && W / 2 < 1) return fail(c, TSM_E_ARG, "[ADCensus] Image error.");
     if (H <= 0 || W <= 0) return fail(c, TSM_E_ARG, "[ADCensus] Image error.");  // ADCensus.cpp:332-333
     if (cfg->max_disparity > 65535) return fail(c, TSM_E_ARG, "[ADCensus] max_disparity too large");
@@ -273,7 +279,7 @@ int ensure_arena(tsm_ctx* c, const tsm_adcensus_config* cfg, int H, int W)
     c->roi = cfg->roi_matching != 0 || cfg->mask_matching != 0;  // both: maxD = W / 2, hue filter, offset, final marking
     c->mask = cfg->mask_matching != 0;
     c->roi_offset = cfg->offset;
-    d.set(H, W, (c->roi ? W / 2 : cfg->max_disparity) - cfg->min_disparity + 1);
+    d.set(H, W, (c->roi ? W / 2 : cfg->max_disparity) - cfg->min_disparity + 1, cfg->min_disparity);
     c->dm = d;
     c->cfg = *cfg;
     const size_t npx = d.npx();
@@ -406,7 +412,10 @@ int run_stages(tsm_ctx* c, int mask, int arg)
     }
     if (mask & TSM_STAGE_INIT) {
         ScopedStage s(c, "cost_init");
-        cost_init(L, d, vl, vr, (const float*)(c->hsi ? c->tab_ad_hsi.p : c->tab_ad.p), (const float*)c->tab_c.p, c->hsi, c->mask);
+        if (d.minD != 0)
+            cost_init_general(L, d, vl, vr, (const float*)(c->hsi ? c->tab_ad_hsi.p : c->tab_ad.p), (const float*)c->tab_c.p, c->hsi, c->mask);
+        else
+            cost_init(L, d, vl, vr, (const float*)(c->hsi ? c->tab_ad_hsi.p : c->tab_ad.p), (const float*)c->tab_c.p, c->hsi, c->mask);
     }
     if (mask & TSM_STAGE_AGGREGATE) {
         ScopedStage s(c, "aggregate");

@@ -72,9 +72,9 @@ def test_hsi_default_constructed_matcher_end_to_end(pair_0600):
     got = m.compute(left, right)
     diff = np.abs(got.astype(np.float64) - want)
     assert (diff > 1).mean() <= 1e-3 and (diff > 0.05).mean() <= 1e-3
-    m.setMinMaxDisparity(4, 48)
+    m.setMinMaxDisparity(30, 48)
     with pytest.raises(t.ADCensusError):
-        m.compute(left, right)  # min_disparity != 0 is not built
+        m.compute(left, right)  # max < 2 * min: the reference's own WTA range is empty (ADCensus.cpp:1398)
 
 
 def test_roi_matching_mode_rgb_and_hsi():
@@ -109,3 +109,25 @@ def test_mask_matching_mode_rgb_and_hsi():
         assert np.array_equal(got < 0, want < 0), key
         diff = np.abs(got.astype(np.float64) - want)
         assert (diff > 1).mean() <= 1e-3 and (diff > 0.05).mean() <= 1e-3, key
+
+
+def test_roi_and_mask_matching_at_the_demo_width():
+    """ROI / mask matching search W / 2 + 1 levels: 641 at the reference's 1280-px demo width (21 registers per lane in the
+    scanline warp, ADCensus.cpp:339-340).  Golden: the unmodified reference on a 1280 x 96 stripe of demo-imgs/0600
+    (tests/golden/make_wide_roi_golden.py)."""
+    import tea_stereo_matching_b200 as t
+
+    f = GOLD / "ref_0600_stripe_1280x96_roi.npz"
+    if not f.exists():
+        pytest.skip("wide ROI golden not generated")
+    z = np.load(f)
+    for model, roi, mask, off, key, lk, rk in ((t.ColorModel.RGB, True, False, 5, "rgb_roi_off5", "left", "right"),
+                                               (t.ColorModel.HSI, False, True, 0, "hsi_mask_off0", "left_mask", "right_mask")):
+        m = t.ADCensus()
+        m.setMatchingStrategy(model, roi, mask)
+        m.setMinMaxDisparity(0, 64)  # replaced by W / 2 = 640 inside compute
+        m.setOffset(off)
+        got, want = m.compute(z[lk], z[rk]), z[key]
+        assert np.array_equal(got < 0, want < 0), key
+        diff = np.abs(got.astype(np.float64) - want)
+        assert (diff > 1).mean() <= 1e-3 and (diff > 0.05).mean() <= 1e-3, (key, float(diff.max()))
