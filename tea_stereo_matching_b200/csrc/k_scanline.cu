@@ -71,6 +71,10 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, unsigned bytes)
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, unsigned parity)
 {
     asm volatile(
@@ -165,26 +169,16 @@ __device__ __forceinline__ void store_vec(float* dst, float* tdst, const float (
 }
 
 // cost2disparity: first strict minimum over d (ADCensus.cpp:1398-1409).
-// Only the planes minD .. Dn - 1 take part (:1398); costs are >= 0, so their bit patterns order like unsigned integers and
-// 0xffffffff stands for "excluded".
+// (With minD != 0 only the planes minD .. Dn - 1 take part: the caller then runs the stand-alone k_wta instead, k_post.cu.)
 template <int K>
-__device__ __forceinline__ int warp_argmin(const float (&v)[K], int lane, int minD)
+__device__ __forceinline__ int warp_argmin(const float (&v)[K], int lane)
 {
     unsigned bb = __float_as_uint(v[0]);
     int bd = lane;
-    if (minD == 0) {  // warp-uniform: the usual case pays nothing for the range test
 #pragma unroll
-        for (int k = 1; k < K; ++k) {
-            const unsigned b = __float_as_uint(v[k]);
-            if (b < bb) { bb = b; bd = lane + 32 * k; }
-        }
-    } else {
-        if (lane < minD) bb = 0xffffffffu;
-#pragma unroll
-        for (int k = 1; k < K; ++k) {
-            const unsigned b = lane + 32 * k >= minD ? __float_as_uint(v[k]) : 0xffffffffu;
-            if (b < bb) { bb = b; bd = lane + 32 * k; }
-        }
+    for (int k = 1; k < K; ++k) {
+        const unsigned b = __float_as_uint(v[k]);
+        if (b < bb) { bb = b; bd = lane + 32 * k; }
     }
     const unsigned gmin = __reduce_min_sync(0xffffffffu, bb);
     return (int)__reduce_min_sync(0xffffffffu, bb == gmin ? (unsigned)bd : 0x7fffffffu);
@@ -281,26 +275,60 @@ __device__ __forceinline__ void scan_dir(float (&prev)[K], const Vol& vol, const
         // ordered behind this warp's outstanding ld.shared: with a shared-memory-heavy kernel of
         // another stream co-resident on the SM (slow LDS) and the volume L2-resident (fast copy), the
         // copy overtook the loads and a step consumed the data of step i+8 (seen as rare run-to-run
-        // differences with several contexts in flight).  So the copy's destination address is made
-        // data-dependent on every loaded register (`zero` is a kernel argument the compiler cannot
-        // fold): the copies cannot issue before the loads have returned.
+        // differences with several contexts in flight).  Four ways to close it were built and measured at
+        // C3 (ms per pair, both launches; profiles/README.md):
+        //   TSM_SCAN_REFILL_DEP          5.47  round 1: copy address data-dependent on every loaded register
+        //   (default) proxy fence         5.54  fence.proxy.async of the issuing lane after __syncwarp
+        //   TSM_SCAN_REFILL_LATE         6.40  "empty" mbarrier (all lanes arrive, producer waits) AFTER the step used the values
+        //   TSM_SCAN_REFILL_EMPTY_EARLY  6.44  the same right after the loads: NOT safe, see below
+        // The empty-mbarrier phase parity equals that of the full barrier: both complete once per use of the stage.
+#ifdef TSM_SCAN_REFILL_DEP
+        // round-1 form, kept for A/B: the destination address is data-dependent on every loaded register
         uint32_t dep = tw ^ ow;
 #pragma unroll
         for (int k = 0; k < K; ++k) dep ^= __float_as_uint(cur[k]);
         dep &= (uint32_t)sp.zero;
         __syncwarp();  // every lane has read the stage
         if (i + SC_NST < count && elect_one()) issue(st + dep, bar);
+#elif defined(TSM_SCAN_REFILL_EMPTY_EARLY)
+        // measured and REJECTED: the arrive issues while the ld.shared above are still in flight (nothing consumes their
+        // results before it), the copy overtakes them and the determinism test fails again (250 pixels at D = 48)
+        mbar_arrive(bar + SC_NST * 8u);
+        if (i + SC_NST < count && elect_one()) {
+            mbar_wait(bar + SC_NST * 8u, pipe.parity);
+            issue(st, bar);
+        }
+#elif !defined(TSM_SCAN_REFILL_LATE)
+        // default: the warp's generic-proxy reads of the stage (all lanes: __syncwarp) are ordered before the async-proxy
+        // copy by a proxy fence of the issuing lane -- the PTX mechanism for exactly this pair of proxies
+        __syncwarp();
+        if (i + SC_NST < count && elect_one()) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            issue(st, bar);
+        }
+#endif
+#ifndef TSM_SCAN_REFILL_LATE
         advance_producer();
+#endif
 
         const bool changed = scan_step<K>(prev, cur, tw & 0x1fffffffu, ow >> 31, lane, sp, ((ow >> (dir > 0 ? 30 : 29)) & 1u) != 0);
         if (changed && do_store) store_vec<K>(dst, tdst, prev, lane, has_tail, lastvalid);
         dst += vstep;
         tdst += wstep;
         if (WTA) {
-            const int best = warp_argmin<K>(prev, lane, dm.minD);
+            const int best = warp_argmin<K>(prev, lane);
             if (lane == 0) *wdst = best;
             wdst += pstep;
         }
+#ifdef TSM_SCAN_REFILL_LATE
+        // release after the step has consumed the loaded values
+        mbar_arrive(bar + SC_NST * 8u);
+        if (i + SC_NST < count && elect_one()) {
+            mbar_wait(bar + SC_NST * 8u, pipe.parity);
+            issue(st, bar);
+        }
+        advance_producer();
+#endif
         pc += pstep;
         tc += tstep;
         st += stage_bytes;
@@ -334,13 +362,16 @@ k_scanline(Dims dm, ViewPtrs v0, ViewPtrs v1, ScanParams sp, int32_t* wta0, int3
 
     constexpr int SC_NST = ScanCfg<K>::NST;
     ScanPipe pipe;
-    const uint32_t warp_bytes = SC_NST * (unsigned)sp.stage_bytes + SC_NST * 8u;
+    const uint32_t warp_bytes = SC_NST * (unsigned)sp.stage_bytes + 2 * SC_NST * 8u;  // stages, "full" barriers, "empty" barriers
     pipe.stage0 = (uint32_t)__cvta_generic_to_shared(scan_smem) + warp * ((warp_bytes + 127u) & ~127u);
     pipe.bar0 = pipe.stage0 + SC_NST * (unsigned)sp.stage_bytes;
     pipe.slot = 0;
     pipe.parity = 0;
     if (lane == 0) {
-        for (int s = 0; s < SC_NST; ++s) mbar_init(pipe.bar0 + s * 8u, 1);
+        for (int s = 0; s < SC_NST; ++s) {
+            mbar_init(pipe.bar0 + s * 8u, 1);                 // full: one expect_tx arrival + the copies' bytes
+            mbar_init(pipe.bar0 + (SC_NST + s) * 8u, 32);     // empty: every lane of the warp after its loads
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
@@ -370,7 +401,7 @@ k_scanline(Dims dm, ViewPtrs v0, ViewPtrs v1, ScanParams sp, int32_t* wta0, int3
     } else {
         // last pass: fuse the WTA; pixel len-1 is final after the forward pass.
         int32_t* wta_out = view ? wta1 : wta0;
-        const int best = warp_argmin<K>(prev, lane, dm.minD);
+        const int best = warp_argmin<K>(prev, lane);
         if (lane == 0) wta_out[(size_t)line * dm.W + len - 1] = best;
         const bool do_store = view == 0 || sp.store_right_final != 0;
         scan_dir<K, VERT, true>(prev, v.vol, v.stab, dm, pipe, line, len - 2, -1, len - 1, sgn, lane, has_tail, lastvalid, do_store,
@@ -383,7 +414,7 @@ static void launch_scan(const Launcher& L, const Dims& d, const ViewPtrs& left, 
                         int32_t* wta0, int32_t* wta1)
 {
     constexpr int SC_NST = ScanCfg<K>::NST;
-    const unsigned warp_bytes = ((unsigned)(SC_NST * sp.stage_bytes + SC_NST * 8) + 127u) & ~127u;
+    const unsigned warp_bytes = ((unsigned)(SC_NST * sp.stage_bytes + 2 * SC_NST * 8) + 127u) & ~127u;
     const size_t smem = (size_t)SCAN_WARPS * warp_bytes;
     static PerDevice smem_set;
     if (smem > smem_set.cur()) {

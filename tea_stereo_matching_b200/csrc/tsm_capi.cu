@@ -424,9 +424,10 @@ int run_stages(tsm_ctx* c, int mask, int arg)
     if (mask & TSM_STAGE_SCANLINE) {
         ScopedStage s(c, "scanline");
         // the last (leftward) pass also writes both WTA maps (cost2disparity fused)
-        scanline(L, d, vl, vr, c->p1_lo, c->p2_lo, (int32_t*)c->wta_[0].p, (int32_t*)c->wta_[1].p, c->stage_mode);
+        // (minD != 0: the WTA range is restricted, the stand-alone kernel below does it and needs the right volume's last store)
+        scanline(L, d, vl, vr, c->p1_lo, c->p2_lo, (int32_t*)c->wta_[0].p, (int32_t*)c->wta_[1].p, c->stage_mode || d.minD != 0);
     }
-    if ((mask & TSM_STAGE_WTA) && !(mask & TSM_STAGE_SCANLINE)) {
+    if (((mask & TSM_STAGE_WTA) && !(mask & TSM_STAGE_SCANLINE)) || ((mask & TSM_STAGE_SCANLINE) && d.minD != 0)) {
         ScopedStage s(c, "wta");
         wta(L, d, vl.vol, (int32_t*)c->wta_[0].p);
         wta(L, d, vr.vol, (int32_t*)c->wta_[1].p);

@@ -27,10 +27,11 @@ def test_pipeline_is_deterministic_next_to_other_contexts(pair_0600):
             run.run(N.STAGE_AGGREGATE)
         run.close()
 
-    ths = [threading.Thread(target=noise, args=(D,)) for D in (95, 48)]
+    # D = 95 / 48: the geometry the hazard was first seen with; D = 192: the benchmark's disparity range on both sides
+    ths = [threading.Thread(target=noise, args=(D,)) for D in (95, 48, 192)]
     [th.start() for th in ths]
     try:
-        for D in (48, 31, 64):
+        for D in (48, 31, 64, 192):
             m = t.ADCensus()
             m.setMatchingStrategy(t.ColorModel.RGB)
             m.setMinMaxDisparity(0, D)
