@@ -179,6 +179,15 @@ int tsm_apply_colormap(tsm_ctx* ctx, const float* disparity, size_t step, int H,
                        float max_val, const uint8_t* colormap, uint8_t* dst, size_t dstep);
 void tsm_jet_colormap(uint8_t* table768);
 
+/* ---- stereo::writePointCloudToPCD / writePointCloudToPLY, source/stereo.cpp:204-356 ----
+ * ASCII point-cloud files of the finite points of an XYZ map (CV_32FC3, row stride xstep bytes) coloured by a CV_8UC3 BGR
+ * image (row stride cstep bytes): points with an infinite coordinate are dropped (:263-266), numbers are written with
+ * std::to_chars (shortest round-trip form), PCD packs the colour as r << 16 | g << 8 | b | 1 << 24 (:240).  Host file I/O:
+ * no context, no device work.  format: 0 = PCD v0.7, 1 = PLY.  *points (optional) receives the number of points written. */
+enum tsm_cloud_format { TSM_CLOUD_PCD = 0, TSM_CLOUD_PLY = 1 };
+int tsm_write_point_cloud(const uint8_t* bgr, size_t cstep, const float* xyz, size_t xstep, int H, int W, const char* path,
+                          int format, size_t* points);
+
 /* ---- parity taps: the analogue of the reference's writeProcess debug dumps
  * (source/ADCensus.cpp:573-580, 785-792, 1003-1010).  tsm_stage_begin uploads a pair and
  * sizes the arena; tsm_stage_run runs the stages in `mask` (TSM_STAGE_* bits, in pipeline

@@ -109,3 +109,50 @@ def reproject_to_3d_q(disp: np.ndarray, Q: np.ndarray) -> np.ndarray:
     with np.errstate(all="ignore"):
         xyz = (xyzw[:3] / xyzw[3:4]).astype(F)  # cv::divide on floats: plain IEEE division
     return np.ascontiguousarray(xyz.T.reshape(H, W, 3))
+
+
+# ---- writePointCloudToPCD / writePointCloudToPLY (source/stereo.cpp:204-356) ------------------------------------
+def to_chars_f32(x) -> str:
+    """std::to_chars(first, last, float) (C++17 [charconv.to.chars]): the shortest decimal representation that round-trips,
+    printed in fixed or scientific notation, whichever is shorter (fixed on a tie)."""
+    x = np.float32(x)
+    if np.isnan(x):
+        return "-nan" if np.signbit(x) else "nan"
+    if np.isinf(x):
+        return "-inf" if x < 0 else "inf"
+    sign = "-" if np.signbit(x) else ""
+    ax = abs(x)
+    if ax == 0:
+        return sign + "0"
+    sci = np.format_float_scientific(ax, unique=True, trim="-", exp_digits=2)  # d.ddde+XX, shortest round-trip digits
+    mant, exp = sci.split("e")
+    e = int(exp)
+    digits = mant.replace(".", "")
+    sci_str = mant + "e" + ("-" if e < 0 else "+") + f"{abs(e):02d}"
+    if e >= 0:
+        fixed = digits + "0" * (e - (len(digits) - 1)) if len(digits) - 1 <= e else digits[: e + 1] + "." + digits[e + 1:]
+    else:
+        fixed = "0." + "0" * (-e - 1) + digits
+    return sign + (fixed if len(fixed) <= len(sci_str) else sci_str)
+
+
+def point_cloud_text(bgr: np.ndarray, xyz: np.ndarray, fmt: str) -> bytes:
+    """The exact bytes writePCD / writePLY produce for the finite points of `xyz` (HxWx3 float32) coloured by `bgr`."""
+    pts = xyz.reshape(-1, 3).astype(np.float32)
+    col = bgr.reshape(-1, 3)
+    keep = ~np.isposinf(pts).any(axis=1)  # == +infinity only, like the reference (:263-266)
+    pts, col = pts[keep], col[keep]
+    n = len(pts)
+    if fmt == "pcd":
+        out = ["# .PCD v0.7 - Point Cloud Data file format\n", "VERSION 0.7\n", "FIELDS x y z rgb\n", "SIZE 4 4 4 4\n",
+               "TYPE F F F U\n", "COUNT 1 1 1 1\n", f"WIDTH {n}\n", "HEIGHT 1\n", "VIEWPOINT 0 0 0 1 0 0 0\n", f"POINTS {n}\n",
+               "DATA ascii\n"]
+        for p, c in zip(pts, col):
+            rgb = int(c[2]) << 16 | int(c[1]) << 8 | int(c[0]) | 1 << 24
+            out.append(f"{to_chars_f32(p[0])} {to_chars_f32(p[1])} {to_chars_f32(p[2])} {rgb}\n")
+    else:
+        out = ["ply\n", "format ascii 1.0\n", f"element vertex {n}\n", "property float x\n", "property float y\n",
+               "property float z\n", "property uchar red\n", "property uchar green\n", "property uchar blue\n", "end_header\n"]
+        for p, c in zip(pts, col):
+            out.append(f"{to_chars_f32(p[0])} {to_chars_f32(p[1])} {to_chars_f32(p[2])} {int(c[2])} {int(c[1])} {int(c[0])}\n")
+    return "".join(out).encode()

@@ -6,12 +6,13 @@ Host-side mirror of the reference's operator interface for this one path
 """
 from ._native import LIB_PATH, NativeLibraryMissing, build_native, lib
 from .adcensus import ADCensus, ADCensusError, ColorModel, Context, StageRunner
-from .consumers import JETColorMap, applyColorMap, reprojectTo3D, reprojectToDepth
+from .consumers import (JETColorMap, applyColorMap, reprojectTo3D, reprojectToDepth, writePointCloudToPCD,
+                        writePointCloudToPLY)
 from .rectify import (CameraIntrinsic, EpipolarRectify, EpipolarRectifyMap, StereoPair, StereoParams,
                       initUndistortRectifyMap)
 
 __all__ = [
     "ADCensus", "ADCensusError", "ColorModel", "Context", "StageRunner", "EpipolarRectify", "EpipolarRectifyMap",
-    "CameraIntrinsic", "StereoPair", "StereoParams", "initUndistortRectifyMap", "JETColorMap", "applyColorMap", "reprojectToDepth", "reprojectTo3D",
+    "CameraIntrinsic", "StereoPair", "StereoParams", "initUndistortRectifyMap", "JETColorMap", "applyColorMap", "reprojectToDepth", "reprojectTo3D", "writePointCloudToPCD", "writePointCloudToPLY",
     "build_native", "lib", "LIB_PATH", "NativeLibraryMissing",
 ]

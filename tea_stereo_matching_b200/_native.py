@@ -34,7 +34,7 @@ EXPORTS = [
     "tsm_rectify_adcensus_device", "tsm_rectify_adcensus_enqueue",
     "tsm_invalidate_maps", "tsm_stage_begin", "tsm_stage_run", "tsm_volume_pitch", "tsm_buffer_bytes", "tsm_tap",
     "tsm_poke", "tsm_set_profiling", "tsm_get_stage_times", "tsm_launch_count", "tsm_selftest",
-    "tsm_init_undistort_rectify_map", "tsm_reproject_to_depth", "tsm_reproject_to_3d", "tsm_reproject_to_3d_q", "tsm_apply_colormap", "tsm_jet_colormap",
+    "tsm_init_undistort_rectify_map", "tsm_reproject_to_depth", "tsm_reproject_to_3d", "tsm_reproject_to_3d_q", "tsm_apply_colormap", "tsm_jet_colormap", "tsm_write_point_cloud",
 ]
 
 
@@ -123,6 +123,7 @@ def lib() -> C.CDLL:
     L.tsm_apply_colormap.argtypes = [vp, vp, sz, i32, i32, i32, f32, f32, vp, vp, sz]
     dp = C.POINTER(C.c_double)
     L.tsm_init_undistort_rectify_map.argtypes = [vp, dp, dp, i32, dp, dp, i32, i32, i32, vp, sz, vp, sz]
+    L.tsm_write_point_cloud.argtypes = [vp, sz, vp, sz, i32, i32, C.c_char_p, i32, C.POINTER(sz)]
     L.tsm_jet_colormap.argtypes = [vp]
     L.tsm_jet_colormap.restype = None
     _lib = L

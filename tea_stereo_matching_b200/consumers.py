@@ -12,7 +12,7 @@ import ctypes as C
 import numpy as np
 
 from . import _native as N
-from .adcensus import ADCensus, Context
+from .adcensus import ADCensus, ADCensusError, Context, _ptr
 
 
 def _source(disparity, context: Context | None):
@@ -88,3 +88,30 @@ def reprojectTo3D(disparity, *args, context: Context | None = None) -> np.ndarra
     else:
         raise TypeError("reprojectTo3D(disparity, focalLength, baseline, cx, cy) or reprojectTo3D(disparity, Q)")
     return xyz
+
+
+def _write_cloud(RGBImage, XYZPoints, path: str, fmt: int) -> int:
+    if RGBImage is None or XYZPoints is None or not path or np.asarray(RGBImage).size == 0 or np.asarray(XYZPoints).size == 0:
+        print("[ERROR] Empty input.")  # the reference logs and returns (stereo.cpp:252-256)
+        return 0
+    rgb = np.ascontiguousarray(RGBImage, np.uint8)
+    xyz = np.ascontiguousarray(XYZPoints, np.float32)
+    if rgb.ndim != 3 or rgb.shape[2] != 3 or xyz.shape != rgb.shape:
+        raise ADCensusError("writePointCloud: RGBImage must be HxWx3 uint8 and XYZPoints HxWx3 float32 of the same size")
+    L = N.lib()
+    n = C.c_size_t(0)
+    rc = L.tsm_write_point_cloud(_ptr(rgb), rgb.strides[0], _ptr(xyz), xyz.strides[0], rgb.shape[0], rgb.shape[1],
+                                 str(path).encode(), fmt, C.byref(n))
+    if rc != N.TSM_OK:
+        raise ADCensusError(L.tsm_last_error(None).decode(), rc)
+    return int(n.value)
+
+
+def writePointCloudToPCD(RGBImage, XYZPoints, pcdPath: str) -> int:
+    """stereo::writePointCloudToPCD (stereo.cpp:250-278): ASCII PCD v0.7 of the finite points; returns the point count."""
+    return _write_cloud(RGBImage, XYZPoints, pcdPath, 0)
+
+
+def writePointCloudToPLY(RGBImage, XYZPoints, plyPath: str) -> int:
+    """stereo::writePointCloudToPLY (stereo.cpp:328-356): ASCII PLY of the finite points; returns the point count."""
+    return _write_cloud(RGBImage, XYZPoints, plyPath, 1)

@@ -409,6 +409,28 @@ void stereo::applyColorMap(const cv::Mat& src, cv::Mat& dst, float minVal, float
 	apply_color_map(src, dst, false, minVal, maxVal, colorMap);
 }
 
+static void write_cloud(const cv::Mat& RGBImage, const cv::Mat& XYZPoints, const std::string& path, int format)
+{
+	if (RGBImage.empty() or XYZPoints.empty() or path.empty()) { log_error("Empty input."); return; }  // stereo.cpp:252-256
+	if (RGBImage.type() != CV_8UC3 or XYZPoints.type() != CV_32FC3 or RGBImage.size() != XYZPoints.size())
+		throw std::runtime_error("writePointCloud: RGBImage must be CV_8UC3 and XYZPoints CV_32FC3 of the same size");
+	size_t n = 0;
+	if (tsm_write_point_cloud(RGBImage.data, RGBImage.step, (const float*)XYZPoints.data, XYZPoints.step, RGBImage.rows,
+		RGBImage.cols, path.c_str(), format, &n) != TSM_OK)
+		throw std::runtime_error(tsm_last_error(nullptr));
+	log_info("Write Done. Points: " + std::to_string(n) + ".");
+}
+
+void stereo::writePointCloudToPCD(const cv::Mat& RGBImage, const cv::Mat& XYZPoints, const std::string& pcdPath)
+{
+	write_cloud(RGBImage, XYZPoints, pcdPath, TSM_CLOUD_PCD);
+}
+
+void stereo::writePointCloudToPLY(const cv::Mat& RGBImage, const cv::Mat& XYZPoints, const std::string& plyPath)
+{
+	write_cloud(RGBImage, XYZPoints, plyPath, TSM_CLOUD_PLY);
+}
+
 void stereo::reprojectToDepth(const cv::Mat& disparity, float focalLength, float baseline, cv::Mat& depth)
 {
 	check_disparity(disparity, "reprojectToDepth");

@@ -165,5 +165,8 @@ void applyColorMap(const cv::Mat& src, cv::Mat& dst, float minVal, float maxVal,
 void reprojectToDepth(const cv::Mat& disparity, float focalLength, float baseline, cv::Mat& depth);
 void reprojectTo3D(const cv::Mat& disparity, float focalLength, float baseline, float cx, float cy, cv::Mat& XYZPoints);
 void reprojectTo3D(const cv::Mat& disparity, const cv::Mat& Q, cv::Mat& XYZPoints);  // Q: 4x4 CV_64FC1 or CV_32FC1
+// source/stereo.cpp:250-278, 328-356: ASCII point clouds of the finite points (RGBImage CV_8UC3, XYZPoints CV_32FC3)
+void writePointCloudToPCD(const cv::Mat& RGBImage, const cv::Mat& XYZPoints, const std::string& pcdPath);
+void writePointCloudToPLY(const cv::Mat& RGBImage, const cv::Mat& XYZPoints, const std::string& plyPath);
 
 }

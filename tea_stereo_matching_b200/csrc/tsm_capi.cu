@@ -3,6 +3,9 @@
 // (reference source/ADCensus.cpp:330-407) and multiOptimize (:1376-1392).
 #include "tsm_common.cuh"
 #include <algorithm>
+#include <charconv>
+#include <limits>
+#include <memory>
 #include <mutex>
 #include <thread>
 #include <limits.h>
@@ -1151,6 +1154,70 @@ int tsm_apply_colormap(tsm_ctx* c, const float* disparity, size_t step, int H, i
 void tsm_jet_colormap(uint8_t* table768)
 {
     if (table768) jet_colormap(table768);
+}
+
+// writePointCloudToPCD / writePointCloudToPLY (stereo.cpp:204-356): same headers, same number formatting (std::to_chars),
+// same point filter.  Host-only.
+int tsm_write_point_cloud(const uint8_t* bgr, size_t cstep, const float* xyz, size_t xstep, int H, int W, const char* path,
+                          int format, size_t* points)
+{
+    if (!bgr || !xyz || !path || !path[0] || H <= 0 || W <= 0 || cstep < (size_t)W * 3 || xstep < (size_t)W * 12)
+        return fail(nullptr, TSM_E_ARG, "Empty input.");  // the reference logs "Empty input." and returns
+    if (format != TSM_CLOUD_PCD && format != TSM_CLOUD_PLY) return fail(nullptr, TSM_E_ARG, "tsm_write_point_cloud: unknown format %d", format);
+    const float inf = std::numeric_limits<float>::infinity();
+    size_t n = 0;
+    for (int y = 0; y < H; ++y) {
+        const float* row = (const float*)((const uint8_t*)xyz + (size_t)y * xstep);
+        for (int x = 0; x < W; ++x)
+            if (!(row[3 * x] == inf || row[3 * x + 1] == inf || row[3 * x + 2] == inf)) ++n;
+    }
+    std::string header;
+    if (format == TSM_CLOUD_PCD) {
+        header += "# .PCD v0.7 - Point Cloud Data file format\nVERSION 0.7\nFIELDS x y z rgb\nSIZE 4 4 4 4\nTYPE F F F U\nCOUNT 1 1 1 1\n";
+        header += "WIDTH " + std::to_string(n) + "\nHEIGHT 1\nVIEWPOINT 0 0 0 1 0 0 0\nPOINTS " + std::to_string(n) + "\nDATA ascii\n";
+    } else {
+        header += "ply\nformat ascii 1.0\nelement vertex " + std::to_string(n) + "\n";
+        header += "property float x\nproperty float y\nproperty float z\nproperty uchar red\nproperty uchar green\nproperty uchar blue\nend_header\n";
+    }
+    const size_t cap = header.size() + 128 * n + 16;
+    std::unique_ptr<char[]> buf(new (std::nothrow) char[cap]);
+    if (!buf) return fail(nullptr, TSM_E_OOM, "tsm_write_point_cloud: out of host memory");
+    char* cur = buf.get();
+    char* const end = buf.get() + cap;
+    memcpy(cur, header.data(), header.size());
+    cur += header.size();
+    for (int y = 0; y < H; ++y) {
+        const float* prow = (const float*)((const uint8_t*)xyz + (size_t)y * xstep);
+        const uint8_t* crow = bgr + (size_t)y * cstep;
+        for (int x = 0; x < W; ++x) {
+            const float* p = prow + 3 * x;
+            if (p[0] == inf || p[1] == inf || p[2] == inf) continue;
+            const uint8_t* c = crow + 3 * x;
+            for (int k = 0; k < 3; ++k) {
+                cur = std::to_chars(cur, end, p[k]).ptr;
+                *cur++ = ' ';
+            }
+            if (format == TSM_CLOUD_PCD) {
+                const unsigned rgb = (unsigned)c[2] << 16 | (unsigned)c[1] << 8 | (unsigned)c[0] | 1u << 24;
+                cur = std::to_chars(cur, end, rgb).ptr;
+            } else {
+                cur = std::to_chars(cur, end, (int)c[2]).ptr;
+                *cur++ = ' ';
+                cur = std::to_chars(cur, end, (int)c[1]).ptr;
+                *cur++ = ' ';
+                cur = std::to_chars(cur, end, (int)c[0]).ptr;
+            }
+            *cur++ = '\n';
+        }
+    }
+    FILE* f = fopen(path, "wb");  // binary mode: no newline translation (:248)
+    if (!f) return fail(nullptr, TSM_E_ARG, "tsm_write_point_cloud: cannot open %s", path);
+    const size_t want = (size_t)(cur - buf.get());
+    const size_t wrote = fwrite(buf.get(), 1, want, f);
+    fclose(f);
+    if (wrote != want) return fail(nullptr, TSM_E_ARG, "tsm_write_point_cloud: short write to %s", path);
+    if (points) *points = n;
+    return TSM_OK;
 }
 
 int tsm_set_profiling(tsm_ctx* c, int enabled)

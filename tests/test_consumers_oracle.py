@@ -63,3 +63,26 @@ def test_colormap_auto_and_explicit_range():
     assert np.array_equal(a[0, 1], cm[0, 0]) and np.array_equal(a[0, 3], cm[0, 255]) and np.array_equal(a[0, 2], cm[0, 127])
     b = co.apply_colormap(d, cm, 2.0, 8.0)
     assert np.all(b[0, 1] == 0) and np.all(b[0, 3] == 0) and np.array_equal(b[1, 0], cm[0, int(np.float32(0.5 / 6) * 255)])
+
+
+def test_point_cloud_writers_match_the_restatement(tmp_path):
+    """writePointCloudToPCD / writePointCloudToPLY (stereo.cpp:204-356) are host file I/O: the library's writers against the
+    oracle's restatement of std::to_chars formatting, byte for byte (no GPU involved)."""
+    import tea_stereo_matching_b200 as t
+    from oracle import consumers_oracle as co
+
+    rng = np.random.default_rng(11)
+    H, W = 23, 31
+    xyz = (rng.standard_normal((H, W, 3)) * rng.choice([1e-6, 1e-3, 1.0, 37.5, 1e4, 1e9], (H, W, 1))).astype(np.float32)
+    xyz[3, 4] = (np.inf, 1.0, 2.0)       # dropped
+    xyz[5, 6] = (1.0, 2.0, np.inf)       # dropped
+    xyz[7, 8] = (0.0, -0.0, 100000.0)    # zeros and an integer-valued float
+    xyz[9, 1] = (1e-5, 123456792.0, 0.1)
+    xyz[2, 2] = (-np.inf, 1.0, 1.0)      # kept: only +infinity is filtered
+    bgr = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+    for fmt, fn in (("pcd", t.writePointCloudToPCD), ("ply", t.writePointCloudToPLY)):
+        path = tmp_path / f"cloud.{fmt}"
+        n = fn(bgr, xyz, str(path))
+        assert n == H * W - 2
+        assert path.read_bytes() == co.point_cloud_text(bgr, xyz, fmt), fmt
+    assert t.writePointCloudToPCD(None, xyz, "x.pcd") == 0  # empty input: logged, nothing written (stereo.cpp:252-256)
