@@ -130,7 +130,9 @@ def to_chars_f32(x) -> str:
     digits = mant.replace(".", "")
     sci_str = mant + "e" + ("-" if e < 0 else "+") + f"{abs(e):02d}"
     if e >= 0:
-        fixed = digits + "0" * (e - (len(digits) - 1)) if len(digits) - 1 <= e else digits[: e + 1] + "." + digits[e + 1:]
+        # an integer-valued float whose shortest digits end before the units: libstdc++ prints the EXACT integer there
+        # (510307072, not 510307070), which has the same length as the zero-padded digits
+        fixed = str(int(ax)) if len(digits) - 1 <= e else digits[: e + 1] + "." + digits[e + 1:]
     else:
         fixed = "0." + "0" * (-e - 1) + digits
     return sign + (fixed if len(fixed) <= len(sci_str) else sci_str)
