@@ -113,11 +113,16 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t a)
     return v;
 }
 
+// (P1, P2) of the three similarity classes, held in registers for the whole walk
+struct Penalties {
+    float p1[3], p2[3];
+};
+
 // Updates prev (the predecessor's vector) to the new vector of this pixel; returns whether
 // the pixel changed (m != 0).
 template <int K>
 __device__ __forceinline__ bool scan_step(float (&prev)[K], const float (&cur)[K], unsigned tf, unsigned own, int lane,
-                                          const ScanParams& sp, bool hole = false)
+                                          const Penalties& pen, bool hole = false)
 {
     if (hole) {  // mask matching: the predecessor is a masked pixel, the step is skipped (ADCensus.cpp:824, 862)
 #pragma unroll
@@ -135,8 +140,8 @@ __device__ __forceinline__ bool scan_step(float (&prev)[K], const float (&cur)[K
         return false;
     }
     // candidate penalties for "other view similar" = 0 / 1 (own is warp-uniform)
-    const float p1a = own ? sp.p1[1] : sp.p1[0], p1b = own ? sp.p1[2] : sp.p1[1];
-    const float mp2a = __fadd_rn(m, own ? sp.p2[1] : sp.p2[0]), mp2b = __fadd_rn(m, own ? sp.p2[2] : sp.p2[1]);
+    const float p1a = own ? pen.p1[1] : pen.p1[0], p1b = own ? pen.p1[2] : pen.p1[1];
+    const float mp2a = __fadd_rn(m, own ? pen.p2[1] : pen.p2[0]), mp2b = __fadd_rn(m, own ? pen.p2[2] : pen.p2[1]);
     float rl[K], rr[K];
 #pragma unroll
     for (int k = 0; k < K; ++k) {
@@ -220,22 +225,29 @@ __device__ __forceinline__ void scan_dir(float (&prev)[K], const Vol& vol, const
     const int t0 = (VERT ? f0 * Wp + line : line * Wp + f0) + kTfPad + lo_off;
     const ptrdiff_t vstep = (ptrdiff_t)pstep * dm.Dm, wstep = (ptrdiff_t)pstep * dm.Rp;
 
-    // ---- producer (lane 0 issues; the running state is kept by every lane so the warp stays uniform) ----
+    // ---- producer (one elected lane issues; the running state is kept by every lane so the warp stays uniform) ----
+    // The three copies of a step read from running 64-bit pointers wherever the source advances linearly along the path
+    // (always for the main part; for the narrow tail chunk and the 16-byte aligned table window on vertical paths with an even
+    // row pitch): recomputing them from the pixel / table index cost ~20 uniform instructions per step inside the elected
+    // lane's block, which the whole warp waits for.
     const float* gmain = vol.main + (size_t)p0 * dm.Dm;
     int pi = p0, ti = t0;
+    const bool tail_linear = wide_tail || (VERT && (W & 1) == 0);  // else (pi & ~1) does not advance by a constant
+    const float* gtail = vol.tail + (wide_tail ? (size_t)p0 * dm.Rp : (size_t)(p0 & ~1) * 2);
+    const ptrdiff_t tail_inc = wide_tail ? (ptrdiff_t)pstep * dm.Rp : (ptrdiff_t)pstep * 2;
+    const uint32_t* gtab = tab + (t0 & ~3);  // vertical: Wp % 4 == 0, the aligned window start advances by tstep words
     uint32_t islot = pipe.slot;
     // arm the stage's mbarrier and launch the three bulk copies of the producer's current pixel
     auto issue = [&](uint32_t st, uint32_t bar) {
         mbar_expect_tx(bar, total_bytes);
         if (main_bytes) tma_load_1d(st, gmain, main_bytes, bar);
-        if (tail_bytes) {
-            const size_t te = wide_tail ? (size_t)pi * dm.Rp : (size_t)(pi & ~1) * 2;
-            tma_load_1d(st + main_bytes, vol.tail + te, tail_bytes, bar);
-        }
-        tma_load_1d(st + main_bytes + tail_bytes, tab + (ti & ~3), SC_WIN * 4u, bar);
+        if (tail_bytes) tma_load_1d(st + main_bytes, tail_linear ? gtail : vol.tail + (size_t)(pi & ~1) * 2, tail_bytes, bar);
+        tma_load_1d(st + main_bytes + tail_bytes, VERT ? gtab : tab + (ti & ~3), SC_WIN * 4u, bar);
     };
     auto advance_producer = [&]() {
         gmain += vstep;
+        gtail += tail_inc;
+        if (VERT) gtab += tstep;
         pi += pstep;
         ti += tstep;
     };
@@ -254,6 +266,26 @@ __device__ __forceinline__ void scan_dir(float (&prev)[K], const Vol& vol, const
     int32_t* wdst = WTA ? wta_out + p0 : nullptr;
     int pc = p0, tc = t0;
     uint32_t st = pipe.stage0 + pipe.slot * stage_bytes, bar = pipe.bar0 + pipe.slot * 8u;
+    // per-lane shared-memory offsets that do not change along a vertical path (the row pitches W and Wp are even / multiples
+    // of 4 there): the tail element's slot in its 16-byte chunk and the table window index of the flag pixel
+    const bool tail_slot_fixed = wide_tail || (VERT && (W & 1) == 0);
+    const uint32_t tail_off0 = main_bytes + ((wide_tail ? 0 : (p0 & 1) * 2) + lane) * 4;
+    const uint32_t win0 = main_bytes + tail_bytes;
+    const int w0_fixed = (t0 & 3) - lo_off;
+    // The consumer's strides live in ordinary (per-thread) registers: everything here is warp-uniform, the compiler keeps
+    // warp-uniform values in the 63 uniform registers, runs out of them in this loop and then RE-DERIVES the strides from the
+    // kernel parameters in every iteration (64-bit multiplies: ~25 instructions per step in the first version).  An opaque
+    // asm makes the copies "divergent" for the compiler.
+    Penalties pen;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        pen.p1[c] = sp.p1[c];
+        pen.p2[c] = sp.p2[c];
+        asm volatile("" : "+f"(pen.p1[c]), "+f"(pen.p2[c]));
+    }
+    ptrdiff_t vstep_c = vstep, wstep_c = wstep;
+    int pstep_c = pstep, tstep_c = tstep;
+    asm volatile("" : "+l"(vstep_c), "+l"(wstep_c), "+r"(pstep_c), "+r"(tstep_c));
 
     for (int i = 0; i < count; ++i) {
         mbar_wait(bar, pipe.parity);
@@ -262,12 +294,12 @@ __device__ __forceinline__ void scan_dir(float (&prev)[K], const Vol& vol, const
         for (int k = 0; k < K; ++k) {
             if (k < K - 1 || !has_tail) cur[k] = lds_f32(st + (lane + 32 * k) * 4);
             else {
-                const int toff = wide_tail ? 0 : (pc & 1) * 2;
-                cur[k] = lastvalid ? lds_f32(st + main_bytes + (toff + lane) * 4) : CUDART_INF_F;
+                const uint32_t toff = tail_slot_fixed ? tail_off0 : main_bytes + ((pc & 1) * 2 + lane) * 4;
+                cur[k] = lastvalid ? lds_f32(st + toff) : CUDART_INF_F;
             }
         }
-        const int w0 = (tc & 3) - lo_off;  // window index of the flag pixel itself
-        const uint32_t wbase = st + main_bytes + tail_bytes;
+        const int w0 = VERT ? w0_fixed : (tc & 3) - lo_off;  // window index of the flag pixel itself
+        const uint32_t wbase = st + win0;
         const uint32_t tw = lds_u32(wbase + (w0 + sgn * lane) * 4);
         const uint32_t ow = lds_u32(wbase + w0 * 4);
 
@@ -311,14 +343,14 @@ __device__ __forceinline__ void scan_dir(float (&prev)[K], const Vol& vol, const
         advance_producer();
 #endif
 
-        const bool changed = scan_step<K>(prev, cur, tw & 0x1fffffffu, ow >> 31, lane, sp, ((ow >> (dir > 0 ? 30 : 29)) & 1u) != 0);
+        const bool changed = scan_step<K>(prev, cur, tw & 0x1fffffffu, ow >> 31, lane, pen, ((ow >> (dir > 0 ? 30 : 29)) & 1u) != 0);
         if (changed && do_store) store_vec<K>(dst, tdst, prev, lane, has_tail, lastvalid);
-        dst += vstep;
-        tdst += wstep;
+        dst += vstep_c;
+        tdst += wstep_c;
         if (WTA) {
             const int best = warp_argmin<K>(prev, lane);
             if (lane == 0) *wdst = best;
-            wdst += pstep;
+            wdst += pstep_c;
         }
 #ifdef TSM_SCAN_REFILL_LATE
         // release after the step has consumed the loaded values
@@ -329,8 +361,8 @@ __device__ __forceinline__ void scan_dir(float (&prev)[K], const Vol& vol, const
         }
         advance_producer();
 #endif
-        pc += pstep;
-        tc += tstep;
+        pc += pstep_c;
+        tc += tstep_c;
         st += stage_bytes;
         bar += 8u;
         if (++pipe.slot == SC_NST) {
