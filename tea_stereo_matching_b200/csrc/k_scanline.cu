@@ -268,10 +268,16 @@ __device__ __forceinline__ void scan_dir(float (&prev)[K], const Vol& vol, const
     uint32_t st = pipe.stage0 + pipe.slot * stage_bytes, bar = pipe.bar0 + pipe.slot * 8u;
     // per-lane shared-memory offsets that do not change along a vertical path (the row pitches W and Wp are even / multiples
     // of 4 there): the tail element's slot in its 16-byte chunk and the table window index of the flag pixel
+    // The narrow tail chunk (16 bytes) holds two pixels: the lane's element sits at float (pixel & 1) * 2 + lane, which
+    // toggles along a path exactly when the pixel index changes parity with every step.
     const bool tail_slot_fixed = wide_tail || (VERT && (W & 1) == 0);
-    const uint32_t tail_off0 = main_bytes + ((wide_tail ? 0 : (p0 & 1) * 2) + lane) * 4;
+    uint32_t tail_off = main_bytes + ((wide_tail ? 0 : (p0 & 1) * 2) + lane) * 4;
+    uint32_t tail_toggle = tail_slot_fixed ? 0u : 8u;
     const uint32_t win0 = main_bytes + tail_bytes;
     const int w0_fixed = (t0 & 3) - lo_off;
+    uint32_t lane_win = (uint32_t)(sgn * lane * 4);  // byte offset of the lane's table word relative to the flag pixel's
+    uint32_t win_fixed = win0 + (uint32_t)(w0_fixed * 4);  // vertical paths: the flag pixel's word in the window never moves
+    asm volatile("" : "+r"(tail_off), "+r"(tail_toggle), "+r"(lane_win), "+r"(win_fixed));
     // The consumer's strides live in ordinary (per-thread) registers: everything here is warp-uniform, the compiler keeps
     // warp-uniform values in the 63 uniform registers, runs out of them in this loop and then RE-DERIVES the strides from the
     // kernel parameters in every iteration (64-bit multiplies: ~25 instructions per step in the first version).  An opaque
@@ -293,15 +299,12 @@ __device__ __forceinline__ void scan_dir(float (&prev)[K], const Vol& vol, const
 #pragma unroll
         for (int k = 0; k < K; ++k) {
             if (k < K - 1 || !has_tail) cur[k] = lds_f32(st + (lane + 32 * k) * 4);
-            else {
-                const uint32_t toff = tail_slot_fixed ? tail_off0 : main_bytes + ((pc & 1) * 2 + lane) * 4;
-                cur[k] = lastvalid ? lds_f32(st + toff) : CUDART_INF_F;
-            }
+            else cur[k] = lastvalid ? lds_f32(st + tail_off) : CUDART_INF_F;
         }
-        const int w0 = VERT ? w0_fixed : (tc & 3) - lo_off;  // window index of the flag pixel itself
-        const uint32_t wbase = st + win0;
-        const uint32_t tw = lds_u32(wbase + (w0 + sgn * lane) * 4);
-        const uint32_t ow = lds_u32(wbase + w0 * 4);
+        // shared address of the flag pixel's own table word
+        const uint32_t wown = st + (VERT ? win_fixed : win0 + (uint32_t)(((tc & 3) - lo_off) * 4));
+        const uint32_t tw = lds_u32(wown + lane_win);
+        const uint32_t ow = lds_u32(wown);
 
         // Refill the stage.  The bulk copy writes shared memory through the async proxy and is NOT
         // ordered behind this warp's outstanding ld.shared: with a shared-memory-heavy kernel of
@@ -363,6 +366,7 @@ __device__ __forceinline__ void scan_dir(float (&prev)[K], const Vol& vol, const
 #endif
         pc += pstep_c;
         tc += tstep_c;
+        tail_off ^= tail_toggle;
         st += stage_bytes;
         bar += 8u;
         if (++pipe.slot == SC_NST) {
