@@ -37,13 +37,21 @@
 
 namespace tsm {
 
+#ifndef TSM_SCAN_WARPS_H
+#define TSM_SCAN_WARPS_H 1
+#endif
 #ifndef TSM_SCAN_WARPS
 #define TSM_SCAN_WARPS 4
 #endif
 #ifndef TSM_SC_NST
 #define TSM_SC_NST 0
 #endif
-constexpr int SCAN_WARPS = TSM_SCAN_WARPS;
+// Warps (= lines) per CTA.  Vertical launch: 4.  Horizontal launch: 1 -- a 1080p pair has only 2160 rows for 148 SMs, and with
+// single-warp CTAs the busiest SM holds 15 warps instead of 16 (the kernel is issue-bound: 2.64 -> 2.56 ms; vertical unchanged).
+template <bool VERT>
+struct ScanWarps {
+    static constexpr int N = VERT ? TSM_SCAN_WARPS : TSM_SCAN_WARPS_H;
+};
 // TMA stages (steps in flight) per warp: 12 while a stage is small (K <= 8 registers = up to 256 disparities,
 // <= 1.2 KB per stage: measured 5.47 -> 5.31 ms against 8 stages at K = 7; 16 stages cost a CTA per SM and lose),
 // 8 for the wide vectors.  -DTSM_SC_NST=n overrides it for experiments.
@@ -379,7 +387,7 @@ __device__ __forceinline__ void scan_dir(float (&prev)[K], const Vol& vol, const
 }
 
 template <int K, bool VERT>
-__global__ void __launch_bounds__(SCAN_WARPS * 32)
+__global__ void __launch_bounds__(ScanWarps<VERT>::N * 32)
 k_scanline(Dims dm, ViewPtrs v0, ViewPtrs v1, ScanParams sp, int32_t* wta0, int32_t* wta1)
 {
     extern __shared__ __align__(128) unsigned char scan_smem[];
@@ -388,7 +396,7 @@ k_scanline(Dims dm, ViewPtrs v0, ViewPtrs v1, ScanParams sp, int32_t* wta0, int3
     // warp index through a lane-0 broadcast: the compiler then knows it (and the line, the pointers and the stage
     // addresses derived from it) is warp-uniform and keeps the bulk-copy operands in uniform registers
     const int lane = threadIdx.x & 31, warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
-    const int line = blockIdx.x * SCAN_WARPS + warp;
+    const int line = blockIdx.x * ScanWarps<VERT>::N + warp;
     const int nlines = VERT ? dm.W : dm.H, len = VERT ? dm.H : dm.W;
     if (line >= nlines) return;
     const int sgn = view == 0 ? 1 : -1;
@@ -451,19 +459,20 @@ static void launch_scan(const Launcher& L, const Dims& d, const ViewPtrs& left, 
 {
     constexpr int SC_NST = ScanCfg<K>::NST;
     const unsigned warp_bytes = ((unsigned)(SC_NST * sp.stage_bytes + 2 * SC_NST * 8) + 127u) & ~127u;
-    const size_t smem = (size_t)SCAN_WARPS * warp_bytes;
+    constexpr int WV = ScanWarps<true>::N, WH = ScanWarps<false>::N;
+    const size_t smem_v = (size_t)WV * warp_bytes, smem_h = (size_t)WH * warp_bytes, smem = smem_v > smem_h ? smem_v : smem_h;
     static PerDevice smem_set;
     if (smem > smem_set.cur()) {
         cudaFuncSetAttribute(k_scanline<K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cudaFuncSetAttribute(k_scanline<K, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         smem_set.cur() = smem;
     }
-    dim3 gv((d.W + SCAN_WARPS - 1) / SCAN_WARPS, 2), gh((d.H + SCAN_WARPS - 1) / SCAN_WARPS, 2);
+    dim3 gv((d.W + WV - 1) / WV, 2), gh((d.H + WH - 1) / WH, 2);
     L.begin("scanline/vertical");
-    k_scanline<K, true><<<gv, SCAN_WARPS * 32, smem, L.stream>>>(d, left, right, sp, wta0, wta1);
+    k_scanline<K, true><<<gv, WV * 32, smem_v, L.stream>>>(d, left, right, sp, wta0, wta1);
     L.end();
     L.begin("scanline/horizontal");
-    k_scanline<K, false><<<gh, SCAN_WARPS * 32, smem, L.stream>>>(d, left, right, sp, wta0, wta1);
+    k_scanline<K, false><<<gh, WH * 32, smem_h, L.stream>>>(d, left, right, sp, wta0, wta1);
     L.end();
     L.count(2);
 }
