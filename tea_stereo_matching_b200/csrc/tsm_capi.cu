@@ -36,6 +36,8 @@ struct tsm_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
+    cudaStream_t side = nullptr;        // second stream for work independent of the main chain (Launcher::side)
+    cudaEvent_t fork_join[2] = {nullptr, nullptr};
     std::string err;
     long long launches = 0;
 
@@ -393,6 +395,7 @@ Launcher make_launcher(tsm_ctx* c)
 {
     Launcher L{c->stream, &c->launches};
     if (c->profiling) { L.prof = c; L.mark = prof_mark; }
+    if (c->side && c->fork_join[0] && c->fork_join[1]) { L.side = c->side; L.events = c->fork_join; }
     return L;
 }
 
@@ -572,6 +575,10 @@ int tsm_create_on_stream(int device, void* cuda_stream, tsm_ctx** out)
         }
         c->own_stream = true;
     }
+    // side stream + fork / join events (best effort: without them everything stays on the one stream)
+    if (cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking) != cudaSuccess) c->side = nullptr;
+    for (auto& e : c->fork_join)
+        if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) e = nullptr;
     *out = c;
     return TSM_OK;
 }
@@ -597,6 +604,9 @@ void tsm_destroy(tsm_ctx* c)
         cudaEventDestroy(t.beg);
         cudaEventDestroy(t.end);
     }
+    if (c->side) { cudaStreamSynchronize(c->side); cudaStreamDestroy(c->side); }
+    for (auto& e : c->fork_join)
+        if (e) cudaEventDestroy(e);
     if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
 }
