@@ -567,10 +567,12 @@ __device__ __forceinline__ uint64_t fix48(float v)
     return (uint64_t)__double_as_longlong(__dadd_rn(w, magic));
 }
 // (hi - lo) mod 2^48 of two ring entries, times 2^-S, rounded once to fp32 -- for both chains of the pair
+// `exp_word` = (1023 + 52 - S) << 20, handed in from a per-thread register: as a literal the compiler parks it in a uniform
+// register and copies it into a vector register in front of every PRMT (15 extra instructions per batch).
 template <int S>
-__device__ __forceinline__ void diff48(const uint32_t* h, const uint32_t* l, float& r0, float& r1)
+__device__ __forceinline__ void diff48(const uint32_t* h, const uint32_t* l, float& r0, float& r1, uint32_t exp_word)
 {
-    constexpr uint32_t EXP = (uint32_t)(1023 + 52 - S) << 20;
+    const uint32_t EXP = exp_word;
     constexpr double base = (double)(1ull << (52 - S));
     uint32_t d0lo, d0hi, d1lo, d1hi;
     asm("sub.cc.u32 %0, %2, %3;\n\tsubc.u32 %1, %4, %5;" : "=r"(d0lo), "=r"(d0hi) : "r"(h[0]), "r"(l[0]), "r"(h[2]), "r"(l[2]));
@@ -662,6 +664,9 @@ __device__ __forceinline__ void walk_fused(const uint32_t tm, const uint32_t sl,
 
     uint64_t PA0 = 0, PA1 = 0, PB0 = 0, PB1 = 0;
     uint32_t topA = 0, topB = AGF_SPAN3 - 3 * AGG_PF;  // ring position (x3) of the newest batch of each pass; B trails A by one batch
+    // (len >> 31 is 0, but neither nvcc nor ptxas can fold it: the words stay in per-thread registers)
+    const uint32_t exp_a = ((uint32_t)(1023 + 52 - AGF_SA) << 20) | ((uint32_t)len >> 31);
+    const uint32_t exp_b = ((uint32_t)(1023 + 52 - AGF_SB) << 20) | ((uint32_t)len >> 31);
 
     // pass A pushes of one batch: prefixes of the inputs in `buf`, packed for tensor memory (no memory traffic here)
     auto push_a = [&](int buf, uint32_t (&wa)[3 * AGG_PF]) {
@@ -734,7 +739,7 @@ __device__ __forceinline__ void walk_fused(const uint32_t tm, const uint32_t sl,
 #pragma unroll
         for (int u = 0; u < AGG_PF; ++u) {
             float r0, r1;
-            diff48<AGF_SB>(hb[u], lb[u], r0, r1);
+            diff48<AGF_SB>(hb[u], lb[u], r0, r1, exp_b);
             st_stream_if(const_cast<char*>(step_addr(out_ptr, u)), r0, r1, o_out + u, len);
         }
         // ---- pass A outputs c = window sum / N, pushed into pass B's ring for the next body ----
@@ -742,7 +747,7 @@ __device__ __forceinline__ void walk_fused(const uint32_t tm, const uint32_t sl,
 #pragma unroll
         for (int u = 0; u < AGG_PF; ++u) {
             float r0, r1;
-            diff48<AGF_SA>(ha[u], la[u], r0, r1);
+            diff48<AGF_SA>(ha[u], la[u], r0, r1, exp_a);
             const float nf = __fsub_rn(__uint_as_float(0x4B000000u | (fa[b][u] >> 16)), 8388608.f);  // (float)N, N < 2^16
             PB0 += fix48<AGF_SB>(div_exact_rn(r0, nf, yv[b][u]));
             PB1 += fix48<AGF_SB>(div_exact_rn(r1, nf, yv[b][u]));
