@@ -10,9 +10,26 @@
 
 namespace tsm {
 
+// Both views go through every preparation kernel in ONE launch (blockIdx.z or blockIdx.y = view): the stage is a chain of
+// small latency-bound kernels, half as many launches with twice the CTAs each.
+struct PrepView {
+    const uint8_t* img;
+    uint32_t* img4;
+    uint64_t* census;
+    uchar4* arms;
+    uint32_t *desc_h, *desc_v, *fdesc_h, *fdesc_v;
+    float *rcp_h, *rcp_v;
+    uint8_t* flags;
+};
+struct PrepPair {
+    PrepView v[2];
+};
+
 // ---- BGR -> BGRx ---------------------------------------------------------
-__global__ void k_pack_bgrx(const uint8_t* __restrict__ img, uint32_t* __restrict__ img4, size_t npx)
+__global__ void k_pack_bgrx(PrepPair pp, size_t npx)
 {
+    const uint8_t* __restrict__ img = pp.v[blockIdx.y].img;
+    uint32_t* __restrict__ img4 = pp.v[blockIdx.y].img4;
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= npx) return;
     const uint8_t* p = img + i * 3;
@@ -31,8 +48,10 @@ constexpr int CS_W = CT_W + 2 * CH_W, CS_H = CT_H + 2 * CH_H;
 // match word (lt_L & gt_R) | (gt_L & lt_R) of k_cost_init evaluates exactly that.
 template <bool HSI>
 __global__ void __launch_bounds__(CT_W* CT_H)
-k_census(const uint32_t* __restrict__ img4, uint64_t* __restrict__ census, int H, int W)
+k_census(PrepPair pp, int H, int W)
 {
+    const uint32_t* __restrict__ img4 = pp.v[blockIdx.z].img4;
+    uint64_t* __restrict__ census = pp.v[blockIdx.z].census;
     __shared__ uint32_t tile[CS_H][CS_W + 1];
     const int x0 = blockIdx.x * CT_W, y0 = blockIdx.y * CT_H;
     const int tid = threadIdx.y * CT_W + threadIdx.x;
@@ -120,16 +139,35 @@ __device__ __forceinline__ int arm_length(const uint32_t* __restrict__ img4, int
     return d - 1;
 }
 
-__global__ void k_arms(const uint32_t* __restrict__ img4, uchar4* __restrict__ arms, int H, int W, ModelParams mp)
+// One thread = one pixel and one AXIS (blockIdx.z = 2 * view + axis): the vertical thread walks up and down and also writes
+// the pixel's similarity flags, the horizontal one walks left and right.  (One thread for all four walks measured 0.25 ms per
+// view at 1080p: the walks are serial chains of dependent L1 loads and a warp waits for its longest arm four times over.)
+__global__ void k_arms_flags(PrepPair pp, int H, int W, ModelParams mp)
 {
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
     if (x >= W || y >= H) return;
-    uchar4 a;
-    a.x = (unsigned char)arm_length(img4, H, W, y, x, -1, 0, mp);
-    a.y = (unsigned char)arm_length(img4, H, W, y, x, 1, 0, mp);
-    a.z = (unsigned char)arm_length(img4, H, W, y, x, 0, -1, mp);
-    a.w = (unsigned char)arm_length(img4, H, W, y, x, 0, 1, mp);
-    arms[(size_t)y * W + x] = a;
+    const PrepView& v = pp.v[blockIdx.z >> 1];
+    const uint32_t* __restrict__ img4 = v.img4;
+    const size_t p = (size_t)y * W + x;
+    unsigned char* a = reinterpret_cast<unsigned char*>(v.arms + p);  // (up, down, left, right)
+    if ((blockIdx.z & 1) == 0) {
+        uchar2 ud;
+        ud.x = (unsigned char)arm_length(img4, H, W, y, x, -1, 0, mp);
+        ud.y = (unsigned char)arm_length(img4, H, W, y, x, 1, 0, mp);
+        *reinterpret_cast<uchar2*>(a) = ud;
+        // similarity flags of computeP1P2 (:927-934)
+        const uint32_t c = img4[p];
+        uint8_t f = 0;
+        if (y > 0 && (mp.hsi ? hue_diff_u32(c, img4[p - W]) : color_diff_u32(c, img4[p - W])) < mp.sim) f |= 1;
+        if (x > 0 && (mp.hsi ? hue_diff_u32(c, img4[p - 1]) : color_diff_u32(c, img4[p - 1])) < mp.sim) f |= 2;
+        if (mp.mask && c == 0u) f |= 4;  // mask matching: a black pixel (ADCensus.cpp:824, 862)
+        v.flags[p] = f;
+    } else {
+        uchar2 lr;
+        lr.x = (unsigned char)arm_length(img4, H, W, y, x, 0, -1, mp);
+        lr.y = (unsigned char)arm_length(img4, H, W, y, x, 0, 1, mp);
+        *reinterpret_cast<uchar2*>(a + 2) = lr;
+    }
 }
 
 // ---- aggregation step descriptors -----------------------------------------------
@@ -138,10 +176,16 @@ __global__ void k_arms(const uint32_t* __restrict__ img4, uchar4* __restrict__ a
 // lengths; vertical-first -> N_vf = sum over the horizontal arm of the column lengths.
 // The pass that ENDS an iteration divides by N (:743-749): a vertical pass ends a
 // horizontal-first iteration (N_hf), a horizontal pass a vertical-first one (N_vf).
-__global__ void k_agg_desc(const uchar4* __restrict__ arms, uint32_t* __restrict__ desc_h, uint32_t* __restrict__ desc_v,
-                           float* __restrict__ rcp_h, float* __restrict__ rcp_v, uint32_t* __restrict__ fdesc_h,
-                           uint32_t* __restrict__ fdesc_v, int H, int W, int Wd, int Hd)
+__global__ void k_agg_desc(PrepPair pp, int H, int W, int Wd, int Hd)
 {
+    const PrepView& v = pp.v[blockIdx.z];
+    const uchar4* __restrict__ arms = v.arms;
+    uint32_t* __restrict__ desc_h = v.desc_h;
+    uint32_t* __restrict__ desc_v = v.desc_v;
+    float* __restrict__ rcp_h = v.rcp_h;
+    float* __restrict__ rcp_v = v.rcp_v;
+    uint32_t* __restrict__ fdesc_h = v.fdesc_h;
+    uint32_t* __restrict__ fdesc_v = v.fdesc_v;
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
     if (x >= W || y >= H) return;
     const size_t p = (size_t)y * W + x;
@@ -165,20 +209,6 @@ __global__ void k_agg_desc(const uchar4* __restrict__ arms, uint32_t* __restrict
     rcp_v[(size_t)x * Hd + y] = __frcp_rn((float)nh);
 }
 
-// ---- similarity flags ---------------------------------------------------------
-__global__ void k_flags(const uint32_t* __restrict__ img4, uint8_t* __restrict__ flags, int H, int W, ModelParams mp)
-{
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
-    if (x >= W || y >= H) return;
-    const size_t p = (size_t)y * W + x;
-    const uint32_t c = img4[p];
-    uint8_t f = 0;
-    if (y > 0 && (mp.hsi ? hue_diff_u32(c, img4[p - W]) : color_diff_u32(c, img4[p - W])) < mp.sim) f |= 1;
-    if (x > 0 && (mp.hsi ? hue_diff_u32(c, img4[p - 1]) : color_diff_u32(c, img4[p - 1])) < mp.sim) f |= 2;
-    if (mp.mask && c == 0u) f |= 4;  // mask matching: a black pixel (ADCensus.cpp:824, 862)
-    flags[p] = f;
-}
-
 // ---- scan tables for the scanline kernels -------------------------------------------
 // stab[plane][y][kTfPad + c], c in [-kTfPad, pitch - kTfPad):
 //   bits 0..23: flag bit `plane` of the OTHER image at (y, c + s*(32k + minD)), k = 0..K-1, 0 outside the image --
@@ -186,9 +216,14 @@ __global__ void k_flags(const uint32_t* __restrict__ img4, uint8_t* __restrict__
 //               bits from the one word at column x + s*lane;
 //   bit 31    : flag bit `plane` of the OWN image at (y, c);
 //   bits 30/29: mask matching only, see below.
-__global__ void k_scan_table(const uint8_t* __restrict__ fown, const uint8_t* __restrict__ foth, uint32_t* __restrict__ stab,
-                             int H, int W, int Wp, int s, int K, int minD)
+__global__ void k_scan_table(const uint8_t* __restrict__ flags_left, const uint8_t* __restrict__ flags_right, uint32_t* __restrict__ stab_left,
+                             uint32_t* __restrict__ stab_right, int H, int W, int Wp, int K, int minD)
 {
+    // blockIdx.z = view: the left volume looks at the right image at x + d, the right volume at the left image at x - d
+    const uint8_t* __restrict__ fown = blockIdx.z ? flags_right : flags_left;
+    const uint8_t* __restrict__ foth = blockIdx.z ? flags_left : flags_right;
+    uint32_t* __restrict__ stab = blockIdx.z ? stab_right : stab_left;
+    const int s = blockIdx.z ? -1 : 1;
     const int cx = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
     if (cx >= Wp) return;
     const int c = cx - kTfPad;
@@ -221,11 +256,9 @@ void prep_scan_tables(const Launcher& L, const Dims& d, const uint8_t* flags_lef
                       uint32_t* stab_left, uint32_t* stab_right)
 {
     const int Wp = d.stab_pitch(), K = (d.Dn + 31) / 32;
-    dim3 tg((Wp + 127) / 128, d.H);
-    // the left volume looks at the right image at x + d, the right volume at the left image at x - d
-    k_scan_table<<<tg, 128, 0, L.stream>>>(flags_left, flags_right, stab_left, d.H, d.W, Wp, 1, K, d.minD);
-    k_scan_table<<<tg, 128, 0, L.stream>>>(flags_right, flags_left, stab_right, d.H, d.W, Wp, -1, K, d.minD);
-    L.count(2);
+    dim3 tg((Wp + 127) / 128, d.H, 2);
+    k_scan_table<<<tg, 128, 0, L.stream>>>(flags_left, flags_right, stab_left, stab_right, d.H, d.W, Wp, K, d.minD);
+    L.count(1);
 }
 
 // ---- HSI preprocessing (ADCensus::compute, ADCensus.cpp:350-371) ---------------------------------------
@@ -233,9 +266,11 @@ void prep_scan_tables(const Launcher& L, const Dims& d, const uint8_t* flags_lef
 // for all 2^24 inputs once per process with its own libm (tsm_capi.cu) -- the same trick as the exp() tables --
 // so the conversion is a table lookup and bit-identical to the reference.
 // `filter` (ROI mode, bgr2hsi(..., true), :1463-1470): pixels whose hue is >= 60 or <= 10 become (0, 0, 0).
-__global__ void k_hsi_lookup(const uint32_t* __restrict__ bgr4, const uint32_t* __restrict__ lut, uint32_t* __restrict__ hsi4, size_t n,
-                             int filter)
+__global__ void k_hsi_lookup(PrepPair pp, int to_arms, const uint32_t* __restrict__ lut, size_t n, int filter)
 {
+    // in: the view's BGRx image; out: the same buffer (ROI mode) or the arms buffer as scratch (free until k_arms_flags, same size)
+    const uint32_t* __restrict__ bgr4 = pp.v[blockIdx.y].img4;
+    uint32_t* __restrict__ hsi4 = to_arms ? reinterpret_cast<uint32_t*>(pp.v[blockIdx.y].arms) : pp.v[blockIdx.y].img4;
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint32_t v = lut[bgr4[i] & 0xffffffu];
@@ -247,8 +282,10 @@ __global__ void k_hsi_lookup(const uint32_t* __restrict__ bgr4, const uint32_t* 
 // computeGaussMedian(src, dst, 3) (:1475-1499): filter2D with the 3x3 kernel [1 2 1; 2 4 2; 1 2 1] / 16
 // (cv::getGaussianKernel(3, -1)), BORDER_CONSTANT 0, rounded half to even; a channel takes the filtered value
 // when it is far from it (hue: circular distance >= 2; S, I: >= 3).
-__global__ void k_gauss_median(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, int H, int W)
+__global__ void k_gauss_median(PrepPair pp, int H, int W)
 {
+    const uint32_t* __restrict__ src = reinterpret_cast<const uint32_t*>(pp.v[blockIdx.z].arms);  // scratch filled by k_hsi_lookup
+    uint32_t* __restrict__ dst = pp.v[blockIdx.z].img4;
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
     if (x >= W || y >= H) return;
     int sum[3] = {0, 0, 0};
@@ -280,31 +317,38 @@ __global__ void k_gauss_median(const uint32_t* __restrict__ src, uint32_t* __res
     dst[(size_t)y * W + x] = out;
 }
 
-void prep_view(const Launcher& L, const Dims& d, int view, const uint8_t* img, uint32_t* img4, uint64_t* census,
-               uchar4* arms, uint32_t* desc_h, uint32_t* desc_v, uint32_t* fdesc_h, uint32_t* fdesc_v, uint8_t* flags,
-               const ModelParams& mp, const uint32_t* hsi_lut, bool roi)
+void prep_views(const Launcher& L, const Dims& d, const uint8_t* const img[2], uint32_t* const img4[2], uint64_t* const census[2],
+                uchar4* const arms[2], uint32_t* const desc_h[2], uint32_t* const desc_v[2], uint32_t* const fdesc_h[2],
+                uint32_t* const fdesc_v[2], uint8_t* const flags[2], const ModelParams& mp, const uint32_t* hsi_lut, bool roi)
 {
     const size_t npx = d.npx();
-    dim3 b(32, 8), g((d.W + 31) / 32, (d.H + 7) / 8);
-    k_pack_bgrx<<<(unsigned)((npx + 255) / 256), 256, 0, L.stream>>>(img, img4, npx);
+    PrepPair pp;
+    for (int k = 0; k < 2; ++k) {
+        PrepView& v = pp.v[k];
+        v.img = img[k]; v.img4 = img4[k]; v.census = census[k]; v.arms = arms[k];
+        v.desc_h = desc_h[k]; v.desc_v = desc_v[k];
+        v.rcp_h = reinterpret_cast<float*>(desc_h[k] + d.desc_h_words());
+        v.rcp_v = reinterpret_cast<float*>(desc_v[k] + d.desc_v_words());
+        v.fdesc_h = fdesc_h[k] + kFdescFront; v.fdesc_v = fdesc_v[k] + kFdescFront;
+        v.flags = flags[k];
+    }
+    dim3 b(32, 8), g((d.W + 31) / 32, (d.H + 7) / 8, 2), g1((unsigned)((npx + 255) / 256), 2);
+    k_pack_bgrx<<<g1, 256, 0, L.stream>>>(pp, npx);
     if (mp.hsi && roi) {  // ADCensus.cpp:354-360: hue-filtered HSI, no Gauss-median
-        k_hsi_lookup<<<(unsigned)((npx + 255) / 256), 256, 0, L.stream>>>(img4, hsi_lut, img4, npx, 1);
+        k_hsi_lookup<<<g1, 256, 0, L.stream>>>(pp, 0, hsi_lut, npx, 1);
         L.count(1);
     } else if (mp.hsi) {  // :361-370
-        uint32_t* tmp = reinterpret_cast<uint32_t*>(arms);  // free until k_arms, same size
-        k_hsi_lookup<<<(unsigned)((npx + 255) / 256), 256, 0, L.stream>>>(img4, hsi_lut, tmp, npx, 0);
-        k_gauss_median<<<g, b, 0, L.stream>>>(tmp, img4, d.H, d.W);
+        k_hsi_lookup<<<g1, 256, 0, L.stream>>>(pp, 1, hsi_lut, npx, 0);
+        k_gauss_median<<<g, b, 0, L.stream>>>(pp, d.H, d.W);
         L.count(2);
     }
-    dim3 cb(CT_W, CT_H), cg((d.W + CT_W - 1) / CT_W, (d.H + CT_H - 1) / CT_H);
-    if (mp.hsi) k_census<true><<<cg, cb, 0, L.stream>>>(img4, census, d.H, d.W);
-    else k_census<false><<<cg, cb, 0, L.stream>>>(img4, census, d.H, d.W);
-    k_arms<<<g, b, 0, L.stream>>>(img4, arms, d.H, d.W, mp);
-    k_agg_desc<<<g, b, 0, L.stream>>>(arms, desc_h, desc_v, reinterpret_cast<float*>(desc_h + d.desc_h_words()),
-                                      reinterpret_cast<float*>(desc_v + d.desc_v_words()), fdesc_h + kFdescFront,
-                                      fdesc_v + kFdescFront, d.H, d.W, d.Wd(), d.Hd());
-    k_flags<<<g, b, 0, L.stream>>>(img4, flags, d.H, d.W, mp);
-    L.count(5);
+    dim3 cb(CT_W, CT_H), cg((d.W + CT_W - 1) / CT_W, (d.H + CT_H - 1) / CT_H, 2);
+    if (mp.hsi) k_census<true><<<cg, cb, 0, L.stream>>>(pp, d.H, d.W);
+    else k_census<false><<<cg, cb, 0, L.stream>>>(pp, d.H, d.W);
+    dim3 ga(g.x, g.y, 4);  // 2 views x 2 axes
+    k_arms_flags<<<ga, b, 0, L.stream>>>(pp, d.H, d.W, mp);
+    k_agg_desc<<<g, b, 0, L.stream>>>(pp, d.H, d.W, d.Wd(), d.Hd());
+    L.count(4);
 }
 
 __global__ void k_roi_finish(float* __restrict__ fin, const uint8_t* __restrict__ bgr, size_t n, float offset)

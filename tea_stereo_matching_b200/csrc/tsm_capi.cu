@@ -408,11 +408,15 @@ int run_stages(tsm_ctx* c, int mask, int arg)
     if (c->profiling && mask == TSM_STAGE_ALL && arg != -2) c->timers_used = 0;  // -2: the caller already recorded a stage
     if (mask & TSM_STAGE_PREP) {
         ScopedStage s(c, "prep");
-        for (int k = 0; k < 2; ++k)
-            prep_view(L, d, k, (const uint8_t*)c->img[k].p, (uint32_t*)c->img4[k].p, (uint64_t*)c->census[k].p,
-                      (uchar4*)c->arms[k].p, (uint32_t*)c->desc_h[k].p, (uint32_t*)c->desc_v[k].p, (uint32_t*)c->fdesc_h[k].p,
-                      (uint32_t*)c->fdesc_v[k].p, (uint8_t*)c->flags[k].p,
-                      model_params(c->hsi, c->mask), (const uint32_t*)c->hsi_lut.p, c->roi);
+        const uint8_t* img[2]; uint32_t* img4[2]; uint64_t* census[2]; uchar4* arms[2];
+        uint32_t *desc_h[2], *desc_v[2], *fdesc_h[2], *fdesc_v[2]; uint8_t* flags[2];
+        for (int k = 0; k < 2; ++k) {
+            img[k] = (const uint8_t*)c->img[k].p; img4[k] = (uint32_t*)c->img4[k].p; census[k] = (uint64_t*)c->census[k].p;
+            arms[k] = (uchar4*)c->arms[k].p; desc_h[k] = (uint32_t*)c->desc_h[k].p; desc_v[k] = (uint32_t*)c->desc_v[k].p;
+            fdesc_h[k] = (uint32_t*)c->fdesc_h[k].p; fdesc_v[k] = (uint32_t*)c->fdesc_v[k].p; flags[k] = (uint8_t*)c->flags[k].p;
+        }
+        prep_views(L, d, img, img4, census, arms, desc_h, desc_v, fdesc_h, fdesc_v, flags, model_params(c->hsi, c->mask),
+                   (const uint32_t*)c->hsi_lut.p, c->roi);
         prep_scan_tables(L, d, (const uint8_t*)c->flags[0].p, (const uint8_t*)c->flags[1].p, (uint32_t*)c->tflags[0].p,
                          (uint32_t*)c->tflags[1].p);
     }
