@@ -46,7 +46,7 @@ import numpy as np
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
-IN_FLIGHT = 3
+IN_FLIGHT = 4
 DISTINCT = 8  # distinct frames per rank; the batch cycles through them
 UNIT = "Mpix*disp/s"
 HASH_FRAMES = 8  # global frames 0..7 are hashed into outputs_sha256

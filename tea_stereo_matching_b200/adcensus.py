@@ -169,7 +169,7 @@ class ADCensus:
         ctx.check(ctx._lib.tsm_adcensus_wait(ctx.handle, _ptr(out), out.strides[0]))
         return out
 
-    IN_FLIGHT = 3  # pairs in flight per device of computeBatch (measured best, profiles/README.md)
+    IN_FLIGHT = 4  # pairs in flight per device of computeBatch (measured: 2 -> 17.1, 3 -> 16.7, 4 -> 16.5, 6 -> 16.5 ms per 1080p pair)
 
     def computeBatch(self, leftImages, rightImages, devices=None) -> list:
         """ADCensus::compute(vector, vector, vector&) of the C++ facade (cpp/stereo.h; the reference's batched signature

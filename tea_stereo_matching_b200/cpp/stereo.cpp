@@ -185,7 +185,7 @@ public:
 	int m_offset = 0;
 	int device = default_device();  // -1: the batched compute shards over every visible device
 	Ctx ctx[1];                     // single-pair compute / fused rectify
-	static constexpr size_t kInFlight = 3;  // pairs in flight per device of the batched compute (measured best: profiles/README.md)
+	static constexpr size_t kInFlight = 4;  // pairs in flight per device of the batched compute (measured: 2 -> 17.1, 3 -> 16.7, 4 -> 16.5, 6 -> 16.5 ms per 1080p pair)
 	std::vector<Ctx> batch;         // [device][kInFlight] contexts of the batched compute
 	tsm_adcensus_config config() const
 	{

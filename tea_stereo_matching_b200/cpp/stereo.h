@@ -128,7 +128,7 @@ public:
 	void setOffset(const int& offset);
 	void compute(const cv::Mat& leftImage, const cv::Mat& rightImage, cv::Mat& disparity) override;
 	// Batched form in the style of the reference's batched ONNX signature (include/stereo.h:381,
-	// SURVEY 8(f) row f4): pair i runs on device i % N (one worker thread per device, three pairs in flight each);
+	// SURVEY 8(f) row f4): pair i runs on device i % N (one worker thread per device, four pairs in flight each);
 	// N = 1 (the device of setDevice) or, after setDevice(-1), every visible device.
 	void compute(const std::vector<cv::Mat>& leftImages, const std::vector<cv::Mat>& rightImages, std::vector<cv::Mat>& disparities);
 	// Extension: fused rectify -> ADCensus on a side-by-side frame (BASELINE config C4).
