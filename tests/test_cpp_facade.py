@@ -55,7 +55,7 @@ def test_facade_compute_matches_python_mirror_and_oracle(demo, pair_0600, port, 
     assert r.returncode == 0, r.stderr
     b = np.fromfile(out, np.float32).reshape(3, H, W)
     assert all(np.array_equal(b[i], got) for i in range(3))
-    # setDevice(-1): the same batch sharded over every visible device (thread per GPU, three pairs in flight each) returns the same bits
+    # setDevice(-1): the same batch sharded over every visible device (thread per GPU, four pairs in flight each) returns the same bits
     r = subprocess.run([str(demo), "batchall", str(inp), str(out), "7"], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     b = np.fromfile(out, np.float32).reshape(7, H, W)

@@ -106,7 +106,7 @@ def test_two_devices_in_one_process(pair_0600):
 
 
 def test_batch_sharded_over_devices_equals_one_device(pair_0600):
-    """every frame of a batch sharded over N GPUs equals the 1-GPU bits (thread per device, three
+    """every frame of a batch sharded over N GPUs equals the 1-GPU bits (thread per device, four
     pairs in flight each).  With one visible device the same code path runs with N = 1 worker."""
     import ctypes as C
 
