@@ -184,25 +184,33 @@ k_cost_init(Dims dm, ViewPtrs vl, ViewPtrs vr, const float* __restrict__ g_tab_a
         }
     }
     // ---- right view: diagonals of the tile.  Right pixel c gets d in [x0 - c, x0 + npix - 1 - c] (clipped to [0, Dn)),
-    // a run of at most COST_TX consecutive d: lanes over d from the run's start (the stores are 4-byte aligned
-    // 128-byte pieces either way; starting at d0 instead of a multiple of 32 saves a third of the iterations).
+    // a run of at most COST_TX consecutive d.  Main part (d < Dm): the run is at most COST_TX <= 64 long, i.e. exactly two
+    // predicated warp stores per column starting at the run's first d (no loop, no alignment prologue: the stores are 4-byte
+    // aligned 128-byte pieces either way).  Tail part (d >= Dm, usually the single last disparity): lanes over COLUMNS.
     {
         const int stride = DnP + 1;
         float* const rmain = vr.vol.main + row * Dm;
-        float* const rtail = vr.vol.tail + row * Rp - Dm;  // indexed with d >= Dm
+        static_assert(COST_TX <= 64, "two warp stores cover a run");
         for (int i = warp; i < COST_TX + Dn - 1; i += COST_WARPS) {
             const int c = cbase + i;
             if ((unsigned)c >= (unsigned)W) continue;
-            const int d0 = max(0, x0 - c), d1 = min(Dn - 1, x0 + npix - 1 - c);
+            const int d0 = max(0, x0 - c), d1 = min(Dm - 1, x0 + npix - 1 - c);
             const float* src = ctile + (c - x0) * DnP;  // + d * stride
             float* const pm = rmain + (size_t)c * Dm;
-            float* const pt = rtail + (size_t)c * Rp;
             const bool hole = MASK && vr.img4[row + c] == 0u;
-            // main part and tail part as two plain loops: one pointer select per element cost more address
-            // arithmetic than the copy itself
-            const int dm_last = min(d1, Dm - 1);
-            for (int d = d0 + lane; d <= dm_last; d += 32) pm[d] = hole ? 2.f : src[d * stride];
-            for (int d = max(d0, Dm) + lane; d <= d1; d += 32) pt[d] = hole ? 2.f : src[d * stride];
+            const int da = d0 + lane, db = da + 32;
+            if (da <= d1) pm[da] = hole ? 2.f : src[da * stride];
+            if (db <= d1) pm[db] = hole ? 2.f : src[db * stride];
+        }
+        if (r > 0) {
+            float* const rtail = vr.vol.tail + row * Rp;
+            for (int i = threadIdx.x; i < COST_TX + Dn - 1; i += COST_WARPS * 32) {
+                const int c = cbase + i;
+                if ((unsigned)c >= (unsigned)W) continue;
+                const int d0 = max(Dm, x0 - c), d1 = min(Dn - 1, x0 + npix - 1 - c);
+                const bool hole = MASK && vr.img4[row + c] == 0u;
+                for (int d = d0; d <= d1; ++d) rtail[(size_t)c * Rp + d - Dm] = hole ? 2.f : ctile[(c - x0 + d) * DnP + d];
+            }
         }
     }
     // ---- right view, cells whose left pixel c + d lies beyond the image: 2.f (ADCensus.cpp:562-566).  Last tile of the row.
