@@ -32,6 +32,7 @@
 // (a register prefetch ring measured 4.2 + 3.5 ms per pair: every short-scoreboard wait also
 // waited for the DRAM loads sharing its slot).
 #include "tsm_common.cuh"
+#include <cstdlib>
 #include <limits.h>
 #include <math_constants.h>
 
@@ -453,9 +454,297 @@ k_scanline(Dims dm, ViewPtrs v0, ViewPtrs v1, ScanParams sp, int32_t* wta0, int3
     }
 }
 
+// =====================================================================================================================
+// Two pixels per pipeline stage (k_scanline2).
+//
+// The walk above is issue-bound (72 % of the issue slots, ~235 warp instructions per step at K = 7), and more than half of a
+// step is bookkeeping that does not depend on K: the mbarrier wait, the proxy fence and the three bulk-copy issues of the
+// refill (one elected lane, the warp waits), the ring / pointer updates.  Two x-adjacent pixels are 2 * Dm * 4 contiguous
+// bytes in the volume, share one 32-byte tail chunk and one 36-word table window, so ONE stage can carry both:
+//   horizontal launch: the two pixels are consecutive steps of the row's path (pairs aligned to even x; the first / last pair
+//                      of a path may have only one pixel on it);
+//   vertical launch:   the two pixels are the same step of two neighbouring columns -- a warp walks TWO lines, two independent
+//                      recurrences (twice the registers, twice the instruction-level parallelism).
+// Per pixel the stage / fence / copy / loop overhead halves; the arithmetic (scan_step) is unchanged.
 template <int K>
-static void launch_scan(const Launcher& L, const Dims& d, const ViewPtrs& left, const ViewPtrs& right, const ScanParams& sp,
-                        int32_t* wta0, int32_t* wta1)
+struct Scan2Cfg {
+#ifndef TSM_SC2_NST
+#define TSM_SC2_NST 0
+#endif
+    static constexpr int NST = TSM_SC2_NST ? TSM_SC2_NST : (K <= 8 ? 8 : 5);  // stages per warp, each two pixels deep
+};
+
+template <int K, bool VERT, bool WTA>
+__device__ __forceinline__ void scan_dir2(float (&prev)[VERT ? 2 : 1][K], const Vol& vol, const uint32_t* __restrict__ stab, const Dims& dm,
+                                          ScanPipe& pipe, int unit, int dir, int sgn, int lane, bool has_tail, bool lastvalid,
+                                          bool do_store, int32_t* wta_out, const ScanParams& sp)
+{
+    constexpr int NST = Scan2Cfg<K>::NST;
+    const int W = dm.W, H = dm.H, Wp = dm.stab_pitch();
+    const uint32_t* tab = stab + (size_t)(VERT ? 0 : 1) * H * Wp;
+    const unsigned main_bytes = (unsigned)dm.Dm * 4u;                      // one pixel
+    const bool wide_tail = dm.Rp >= 4;
+    const unsigned tail_bytes = !has_tail ? 0u : (wide_tail ? 2u * dm.Rp * 4u : 32u);  // two pixels (narrow: the 4-pixel chunk around them)
+    const unsigned total_bytes = 2 * main_bytes + tail_bytes + SC_WIN * 4u;
+    const unsigned stage_bytes = (unsigned)sp.stage_bytes;
+    const int lo_off = sgn > 0 ? 0 : -31;
+
+    // ---- geometry of the stages ----
+    // pmin = pixel index of the stage's first (lower-x) pixel; tmin = table word of the lower of its two flag pixels
+    int nstages, pmin, tmin, pstep, tstep;
+    int lo = 0, hi = 0;  // HORZ: x range of the path
+    if (VERT) {
+        const int x0 = 2 * unit, first = dir > 0 ? 1 : H - 2, f0 = dir > 0 ? first : first + 1;
+        nstages = H - 1;
+        pmin = first * W + x0;
+        tmin = f0 * Wp + kTfPad + x0;
+        pstep = dir * W;
+        tstep = dir * Wp;
+    } else {
+        lo = dir > 0 ? 1 : 0;
+        hi = dir > 0 ? W - 1 : W - 2;
+        const int m0 = dir > 0 ? lo / 2 : hi / 2;
+        nstages = hi / 2 - lo / 2 + 1;
+        pmin = unit * W + 2 * m0;
+        // flag pixel of x = max(x, predecessor): forward x, backward x + 1 -> the lower one of the pair (2m, 2m+1) is 2m / 2m+1
+        tmin = unit * Wp + kTfPad + 2 * m0 + (dir > 0 ? 0 : 1);
+        pstep = dir * 2;
+        tstep = dir * 2;
+    }
+
+    // ---- producer ----
+    const float* gmain = vol.main + (size_t)pmin * dm.Dm;
+    const ptrdiff_t vstep = (ptrdiff_t)pstep * dm.Dm;
+    int ppi = pmin, pti = tmin;
+    uint32_t islot = pipe.slot;
+    auto issue = [&](uint32_t st, uint32_t bar) {
+        mbar_expect_tx(bar, total_bytes);
+        if (main_bytes) tma_load_1d(st, gmain, 2 * main_bytes, bar);
+        if (tail_bytes)
+            tma_load_1d(st + 2 * main_bytes, wide_tail ? vol.tail + (size_t)ppi * dm.Rp : vol.tail + (size_t)(ppi & ~1) * 2, tail_bytes, bar);
+        tma_load_1d(st + 2 * main_bytes + tail_bytes, tab + ((pti + lo_off) & ~3), SC_WIN * 4u, bar);
+    };
+    auto advance_producer = [&]() {
+        gmain += vstep;
+        ppi += pstep;
+        pti += tstep;
+    };
+    {
+        const int npro = nstages < NST ? nstages : NST;
+        for (int i = 0; i < npro; ++i) {
+            if (elect_one()) issue(pipe.stage0 + islot * stage_bytes, pipe.bar0 + islot * 8u);
+            advance_producer();
+            islot = islot + 1 == NST ? 0 : islot + 1;
+        }
+    }
+
+    // ---- consumer ----
+    Penalties pen;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        pen.p1[c] = sp.p1[c];
+        pen.p2[c] = sp.p2[c];
+        asm volatile("" : "+f"(pen.p1[c]), "+f"(pen.p2[c]));
+    }
+    int pc = pmin, tc = tmin;  // of the stage being consumed
+    int pstep_c = pstep, tstep_c = tstep;
+    uint32_t lane_win = (uint32_t)(sgn * lane * 4), lane4 = (uint32_t)lane * 4u;
+    asm volatile("" : "+r"(pstep_c), "+r"(tstep_c), "+r"(lane_win), "+r"(lane4));
+    uint32_t st = pipe.stage0 + pipe.slot * stage_bytes, bar = pipe.bar0 + pipe.slot * 8u;
+    const uint32_t win0 = 2 * main_bytes + tail_bytes;
+    const int Rp = dm.Rp;
+    // running per-lane output pointers of the stage's first pixel (the second one is one pixel vector further); everything the
+    // stores need lives in per-thread registers (see scan_dir: the compiler otherwise re-derives it from the kernel parameters)
+    char* dmain = reinterpret_cast<char*>(vol.main + (size_t)pmin * dm.Dm) + lane * 4;
+    char* dtail = reinterpret_cast<char*>(vol.tail + (size_t)pmin * Rp) + lane * 4;
+    int32_t* dwta = WTA ? wta_out + pmin : nullptr;
+    ptrdiff_t dstep_m = (ptrdiff_t)pstep * dm.Dm * 4, dstep_t = (ptrdiff_t)pstep * Rp * 4;
+    uint32_t mb = main_bytes, rp4 = (uint32_t)Rp * 4u;
+    asm volatile("" : "+l"(dstep_m), "+l"(dstep_t), "+r"(mb), "+r"(rp4));
+    const bool second_line = VERT && 2 * unit + 1 < W;
+
+    for (int i = 0; i < nstages; ++i) {
+        mbar_wait(bar, pipe.parity);
+        // sub-step q handles the pixel in stage slot sl(q): path order = slot order except on a backward horizontal path
+        float cur[2][K];
+        uint32_t tw[2], ow[2];
+        bool act[2];
+        const int wbase = tc + lo_off - ((tc + lo_off) & ~3);  // window index of table word tc + lo_off
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const int sl = (VERT || dir > 0) ? q : 1 - q;
+            const int x = VERT ? 0 : (pc - unit * W) + sl;
+            act[q] = VERT ? (sl == 0 || second_line) : (x >= lo && x <= hi);
+            // table word of this pixel's flag pixel: tc is the lower one of the pair
+            const int tw_idx = wbase - lo_off + sl;  // = (tc + sl) - window start
+            const uint32_t wown = st + win0 + (uint32_t)(tw_idx * 4);
+            tw[q] = lds_u32(wown + lane_win);
+            ow[q] = lds_u32(wown);
+            const uint32_t mbase = st + (uint32_t)sl * mb + lane4;
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                if (k < K - 1 || !has_tail) cur[q][k] = lds_f32(mbase + 128u * k);
+                else {
+                    const int tslot = wide_tail ? sl * Rp : ((pc & 1) + sl) * 2;  // float index of the pixel's tail vector in the chunk
+                    cur[q][k] = lastvalid ? lds_f32(st + 2 * main_bytes + (uint32_t)(tslot * 4) + lane4) : CUDART_INF_F;
+                }
+            }
+        }
+        // refill: the warp's generic-proxy reads of the stage are ordered before the async-proxy copy by a proxy fence of the issuing lane
+        __syncwarp();
+        if (i + NST < nstages && elect_one()) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            issue(st, bar);
+        }
+        advance_producer();
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            if (!act[q]) continue;  // warp-uniform
+            const int sl = (VERT || dir > 0) ? q : 1 - q;
+            float (&pv)[K] = prev[VERT ? q : 0];
+            const bool changed = scan_step<K>(pv, cur[q], tw[q] & 0x1fffffffu, ow[q] >> 31, lane, pen,
+                                              ((ow[q] >> (dir > 0 ? 30 : 29)) & 1u) != 0);
+            if (changed && do_store) {
+                char* om = dmain + (size_t)((uint32_t)sl * mb);
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    if (k < K - 1 || !has_tail) *reinterpret_cast<float*>(om + 128 * k) = pv[k];
+                    else if (lastvalid) *reinterpret_cast<float*>(dtail + (size_t)((uint32_t)sl * rp4)) = pv[k];
+                }
+            }
+            if (WTA) {
+                const int best = warp_argmin<K>(pv, lane);
+                if (lane == 0) dwta[sl] = best;
+            }
+        }
+        dmain += dstep_m;
+        dtail += dstep_t;
+        if (WTA) dwta += pstep_c;
+        pc += pstep_c;
+        tc += tstep_c;
+        st += stage_bytes;
+        bar += 8u;
+        if (++pipe.slot == NST) {
+            pipe.slot = 0;
+            pipe.parity ^= 1u;
+            st = pipe.stage0;
+            bar = pipe.bar0;
+        }
+    }
+}
+
+template <int K, bool VERT>
+__global__ void __launch_bounds__(ScanWarps<VERT>::N * 32)
+k_scanline2(Dims dm, ViewPtrs v0, ViewPtrs v1, ScanParams sp, int32_t* wta0, int32_t* wta1)
+{
+    extern __shared__ __align__(128) unsigned char scan_smem[];
+    const int view = blockIdx.y;
+    const ViewPtrs& v = view ? v1 : v0;
+    const int lane = threadIdx.x & 31, warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+    const int unit = blockIdx.x * ScanWarps<VERT>::N + warp;  // vertical: columns 2 unit, 2 unit + 1; horizontal: row
+    const int nunits = VERT ? (dm.W + 1) / 2 : dm.H;
+    if (unit >= nunits) return;
+    const int sgn = view == 0 ? 1 : -1;
+    const bool has_tail = dm.Rp != 0;
+    const bool lastvalid = !has_tail || lane < dm.tail();
+    constexpr int NST = Scan2Cfg<K>::NST;
+    constexpr int NL = VERT ? 2 : 1;
+    ScanPipe pipe;
+    const uint32_t warp_bytes = NST * (unsigned)sp.stage_bytes + NST * 8u;
+    pipe.stage0 = (uint32_t)__cvta_generic_to_shared(scan_smem) + warp * ((warp_bytes + 127u) & ~127u);
+    pipe.bar0 = pipe.stage0 + NST * (unsigned)sp.stage_bytes;
+    pipe.slot = 0;
+    pipe.parity = 0;
+    if (lane == 0) {
+        for (int s = 0; s < NST; ++s) mbar_init(pipe.bar0 + s * 8u, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+
+    float prev[NL][K];
+    auto load_prev = [&](int l, size_t p0, bool valid) {
+        const float* src = v.vol.main + p0 * dm.Dm;
+        const float* tsrc = v.vol.tail + p0 * dm.Rp;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            if (!valid) prev[l][k] = CUDART_INF_F;
+            else if (k < K - 1 || !has_tail) prev[l][k] = src[lane + 32 * k];
+            else prev[l][k] = lastvalid ? tsrc[lane] : CUDART_INF_F;
+        }
+    };
+    if (VERT) {
+        load_prev(0, (size_t)2 * unit, true);
+        load_prev(NL - 1, (size_t)2 * unit + 1, 2 * unit + 1 < dm.W);
+    } else {
+        load_prev(0, (size_t)unit * dm.W, true);
+    }
+    scan_dir2<K, VERT, false>(prev, v.vol, v.stab, dm, pipe, unit, 1, sgn, lane, has_tail, lastvalid, true, nullptr, sp);
+    // the backward pass re-reads through the async proxy what this warp has just written with ordinary stores
+    __threadfence();
+    __syncwarp();
+    asm volatile("fence.proxy.async;" ::: "memory");
+    if (VERT) {
+        scan_dir2<K, VERT, false>(prev, v.vol, v.stab, dm, pipe, unit, -1, sgn, lane, has_tail, lastvalid, true, nullptr, sp);
+    } else {
+        int32_t* wta_out = view ? wta1 : wta0;
+        const int best = warp_argmin<K>(prev[0], lane);
+        if (lane == 0) wta_out[(size_t)unit * dm.W + dm.W - 1] = best;
+        const bool do_store = view == 0 || sp.store_right_final != 0;
+        scan_dir2<K, VERT, true>(prev, v.vol, v.stab, dm, pipe, unit, -1, sgn, lane, has_tail, lastvalid, do_store, wta_out, sp);
+    }
+}
+
+static bool scan2_enabled()
+{
+    static const bool on = [] {
+        const char* e = getenv("TSM_SCAN2");
+        return !(e && e[0] == '0');
+    }();
+    return on;
+}
+
+template <int K>
+static void launch_scan_vertical(const Launcher& L, const Dims& d, const ViewPtrs& left, const ViewPtrs& right, const ScanParams& sp,
+                                 int32_t* wta0, int32_t* wta1);
+
+template <int K>
+static void launch_scan2(const Launcher& L, const Dims& d, const ViewPtrs& left, const ViewPtrs& right, ScanParams sp,
+                         int32_t* wta0, int32_t* wta1)
+{
+    const ScanParams sp1 = sp;  // one-pixel stage geometry (vertical launch)
+    constexpr int NST = Scan2Cfg<K>::NST;
+    const unsigned tail2 = d.Rp == 0 ? 0u : (d.Rp >= 4 ? 2u * d.Rp * 4u : 32u);
+    sp.stage_bytes = 2 * d.Dm * 4 + (int)tail2 + SC_WIN * 4;
+    const unsigned warp_bytes = ((unsigned)(NST * sp.stage_bytes + NST * 8) + 127u) & ~127u;
+    constexpr int WV = ScanWarps<true>::N, WH = ScanWarps<false>::N;
+    const size_t smem_v = (size_t)WV * warp_bytes, smem_h = (size_t)WH * warp_bytes, smem = smem_v > smem_h ? smem_v : smem_h;
+    static PerDevice smem_set;
+    if (smem > smem_set.cur()) {
+        cudaFuncSetAttribute(k_scanline2<K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(k_scanline2<K, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        smem_set.cur() = smem;
+    }
+    const int nunits_v = (d.W + 1) / 2;
+    dim3 gv((nunits_v + WV - 1) / WV, 2), gh((d.H + WH - 1) / WH, 2);
+    // Measured at C3 (ms): vertical launch 2.41 with one pixel per stage, 2.45 with two (half as many warps, each with two
+    // recurrences: the issue slots are not filled better); horizontal launch 2.58 -> 2.48.  So only the horizontal launch uses it.
+    static const bool vert2 = getenv("TSM_SCAN2_VERT") != nullptr;
+    if (!vert2) {
+        launch_scan_vertical<K>(L, d, left, right, sp1, wta0, wta1);
+    } else {
+        L.begin("scanline/vertical");
+        k_scanline2<K, true><<<gv, WV * 32, smem_v, L.stream>>>(d, left, right, sp, wta0, wta1);
+        L.end();
+        L.count(1);
+    }
+    L.begin("scanline/horizontal");
+    k_scanline2<K, false><<<gh, WH * 32, smem_h, L.stream>>>(d, left, right, sp, wta0, wta1);
+    L.end();
+    L.count(1);
+}
+
+template <int K>
+static size_t scan1_smem(const ScanParams& sp, bool vert)
 {
     constexpr int SC_NST = ScanCfg<K>::NST;
     const unsigned warp_bytes = ((unsigned)(SC_NST * sp.stage_bytes + 2 * SC_NST * 8) + 127u) & ~127u;
@@ -467,14 +756,34 @@ static void launch_scan(const Launcher& L, const Dims& d, const ViewPtrs& left, 
         cudaFuncSetAttribute(k_scanline<K, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         smem_set.cur() = smem;
     }
-    dim3 gv((d.W + WV - 1) / WV, 2), gh((d.H + WH - 1) / WH, 2);
+    return vert ? smem_v : smem_h;
+}
+
+template <int K>
+static void launch_scan_vertical(const Launcher& L, const Dims& d, const ViewPtrs& left, const ViewPtrs& right, const ScanParams& sp,
+                                 int32_t* wta0, int32_t* wta1)
+{
+    constexpr int WV = ScanWarps<true>::N;
+    const size_t smem_v = scan1_smem<K>(sp, true);
+    dim3 gv((d.W + WV - 1) / WV, 2);
     L.begin("scanline/vertical");
     k_scanline<K, true><<<gv, WV * 32, smem_v, L.stream>>>(d, left, right, sp, wta0, wta1);
     L.end();
+    L.count(1);
+}
+
+template <int K>
+static void launch_scan(const Launcher& L, const Dims& d, const ViewPtrs& left, const ViewPtrs& right, const ScanParams& sp,
+                        int32_t* wta0, int32_t* wta1)
+{
+    constexpr int WH = ScanWarps<false>::N;
+    launch_scan_vertical<K>(L, d, left, right, sp, wta0, wta1);
+    const size_t smem_h = scan1_smem<K>(sp, false);
+    dim3 gh((d.H + WH - 1) / WH, 2);
     L.begin("scanline/horizontal");
     k_scanline<K, false><<<gh, WH * 32, smem_h, L.stream>>>(d, left, right, sp, wta0, wta1);
     L.end();
-    L.count(2);
+    L.count(1);
 }
 
 void scanline(const Launcher& L, const Dims& d, const ViewPtrs& left, const ViewPtrs& right, float p1_lo, float p2_lo,
@@ -488,6 +797,17 @@ void scanline(const Launcher& L, const Dims& d, const ViewPtrs& left, const View
     sp.tail_bytes = d.Rp == 0 ? 0 : (d.Rp >= 4 ? d.Rp * 4 : 16);
     sp.stage_bytes = d.Dm * 4 + sp.tail_bytes + SC_WIN * 4;
     const int K = (d.Dn + 31) / 32;
+    // two pixels per stage for the usual disparity ranges (K <= 13: up to 416 levels); the one-pixel walk for the wide ones
+#define TSM_SCAN2_CASE(k) case k: launch_scan2<k>(L, d, left, right, sp, wta_left, wta_right); return;
+    if (scan2_enabled() && d.W >= 4 && d.H >= 2) {
+        switch (K) {
+            TSM_SCAN2_CASE(1) TSM_SCAN2_CASE(2) TSM_SCAN2_CASE(3) TSM_SCAN2_CASE(4) TSM_SCAN2_CASE(5) TSM_SCAN2_CASE(6)
+            TSM_SCAN2_CASE(7) TSM_SCAN2_CASE(8) TSM_SCAN2_CASE(9) TSM_SCAN2_CASE(10) TSM_SCAN2_CASE(11) TSM_SCAN2_CASE(12)
+            TSM_SCAN2_CASE(13)
+            default: break;
+        }
+    }
+#undef TSM_SCAN2_CASE
 #define TSM_SCAN_CASE(k) case k: launch_scan<k>(L, d, left, right, sp, wta_left, wta_right); break;
     switch (K) {
         TSM_SCAN_CASE(1) TSM_SCAN_CASE(2) TSM_SCAN_CASE(3) TSM_SCAN_CASE(4) TSM_SCAN_CASE(5) TSM_SCAN_CASE(6)
