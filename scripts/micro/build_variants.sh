@@ -12,7 +12,7 @@ while [ $# -ge 2 ]; do
   name=$1; flags=$2; shift 2
   nvcc -O3 -std=c++17 $ARCH -lineinfo -fmad=false -Xcompiler -fPIC -Xptxas -v $flags -c $src -o build/var/${base}_$name.o 2> build/var/${base}_$name.log
   objs=""
-  for o in tsm_capi k_prep k_cost k_aggregate k_scanline k_post k_rectify k_consumers; do
+  for o in tsm_capi k_prep k_cost k_aggregate k_scanline k_scanline3 k_post k_rectify k_consumers; do
     if [ $o = $base ]; then objs="$objs build/var/${base}_$name.o"; else objs="$objs build/$o.o"; fi
   done
   nvcc $ARCH -shared -o ../../scripts/micro/libs/$name.so $objs -lpthread

@@ -47,7 +47,7 @@ struct tsm_ctx {
     bool have_pair = false;
 
     // device buffers
-    Buf img[2], img4[2], census[2], arms[2], desc_h[2], desc_v[2], fdesc_h[2], fdesc_v[2], flags[2], tflags[2], vol[2], vtail[2], wta_[2];
+    Buf img[2], img4[2], census[2], arms[2], desc_h[2], desc_v[2], fdesc_h[2], fdesc_v[2], flags[2], tflags[2], sbits[2], vol[2], vtail[2], wta_[2];
     Buf dense;  // [H][W][Dn] staging for volume taps / pokes
     bool stage_mode = false;  // tsm_stage_run: keep every tap-able buffer complete
     Buf disp[2], fin, ftmp;
@@ -299,6 +299,7 @@ int ensure_arena(tsm_ctx* c, const tsm_adcensus_config* cfg, int H, int W)
         if ((rc = ensure(c, c->fdesc_v[k], d.fdesc_v_words() * 4, true))) return rc;
         if ((rc = ensure(c, c->flags[k], npx))) return rc;
         if ((rc = ensure(c, c->tflags[k], ((size_t)2 * H * d.stab_pitch() + 64) * 4, true))) return rc;
+        if (scanline3_supported(d) && (rc = ensure(c, c->sbits[k], (sb_layout(H, W).words + 64) * 4, true))) return rc;
         if ((rc = ensure(c, c->vol[k], (npx * d.Dm + aggregate_overread_floats(d)) * 4 + 256, true))) return rc;
         if ((rc = ensure(c, c->vtail[k], (npx * d.Rp + aggregate_overread_floats(d)) * 4 + 256, true))) return rc;
         if ((rc = ensure(c, c->wta_[k], npx * 4))) return rc;
@@ -343,6 +344,7 @@ ViewPtrs view_ptrs(tsm_ctx* c, int k)
     v.fdesc_v = (const uint32_t*)c->fdesc_v[k].p + kFdescFront;
     v.flags = (const uint8_t*)c->flags[k].p;
     v.stab = (const uint32_t*)c->tflags[k].p;
+    v.sbits = (const uint32_t*)c->sbits[k].p;
     v.vol.main = (float*)c->vol[k].p;
     v.vol.tail = (float*)c->vtail[k].p;
     return v;
@@ -417,8 +419,12 @@ int run_stages(tsm_ctx* c, int mask, int arg)
         }
         prep_views(L, d, img, img4, census, arms, desc_h, desc_v, fdesc_h, fdesc_v, flags, model_params(c->hsi, c->mask),
                    (const uint32_t*)c->hsi_lut.p, c->roi);
-        prep_scan_tables(L, d, (const uint8_t*)c->flags[0].p, (const uint8_t*)c->flags[1].p, (uint32_t*)c->tflags[0].p,
-                         (uint32_t*)c->tflags[1].p);
+        if (scanline3_supported(d))
+            prep_scan_bits(L, d, (const uint8_t*)c->flags[0].p, (const uint8_t*)c->flags[1].p, (uint32_t*)c->sbits[0].p,
+                           (uint32_t*)c->sbits[1].p);
+        else
+            prep_scan_tables(L, d, (const uint8_t*)c->flags[0].p, (const uint8_t*)c->flags[1].p, (uint32_t*)c->tflags[0].p,
+                             (uint32_t*)c->tflags[1].p);
     }
     if (mask & TSM_STAGE_INIT) {
         ScopedStage s(c, "cost_init");
@@ -435,7 +441,10 @@ int run_stages(tsm_ctx* c, int mask, int arg)
         ScopedStage s(c, "scanline");
         // the last (leftward) pass also writes both WTA maps (cost2disparity fused)
         // (minD != 0: the WTA range is restricted, the stand-alone kernel below does it and needs the right volume's last store)
-        scanline(L, d, vl, vr, c->p1_lo, c->p2_lo, (int32_t*)c->wta_[0].p, (int32_t*)c->wta_[1].p, c->stage_mode || d.minD != 0);
+        if (scanline3_supported(d))
+            scanline3(L, d, vl, vr, c->p1_lo, c->p2_lo, (int32_t*)c->wta_[0].p, (int32_t*)c->wta_[1].p, c->stage_mode || d.minD != 0);
+        else
+            scanline(L, d, vl, vr, c->p1_lo, c->p2_lo, (int32_t*)c->wta_[0].p, (int32_t*)c->wta_[1].p, c->stage_mode || d.minD != 0);
     }
     if (((mask & TSM_STAGE_WTA) && !(mask & TSM_STAGE_SCANLINE)) || ((mask & TSM_STAGE_SCANLINE) && d.minD != 0)) {
         ScopedStage s(c, "wta");
@@ -595,7 +604,7 @@ void tsm_destroy(tsm_ctx* c)
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     Buf* all[] = {&c->img[0], &c->img[1], &c->img4[0], &c->img4[1], &c->census[0], &c->census[1], &c->arms[0], &c->arms[1],
-                  &c->desc_h[0], &c->desc_h[1], &c->desc_v[0], &c->desc_v[1], &c->fdesc_h[0], &c->fdesc_h[1], &c->fdesc_v[0], &c->fdesc_v[1], &c->flags[0], &c->flags[1], &c->tflags[0], &c->tflags[1], &c->vtail[0], &c->vtail[1], &c->dense, &c->vol[0], &c->vol[1], &c->wta_[0], &c->wta_[1],
+                  &c->desc_h[0], &c->desc_h[1], &c->desc_v[0], &c->desc_v[1], &c->fdesc_h[0], &c->fdesc_h[1], &c->fdesc_v[0], &c->fdesc_v[1], &c->flags[0], &c->flags[1], &c->tflags[0], &c->tflags[1], &c->sbits[0], &c->sbits[1], &c->vtail[0], &c->vtail[1], &c->dense, &c->vol[0], &c->vol[1], &c->wta_[0], &c->wta_[1],
                   &c->disp[0], &c->disp[1], &c->fin, &c->ftmp, &c->v_vote, &c->v_lowcnt, &c->v_off, &c->v_mark, &c->v_start, &c->v_stash,
                   &c->v_sums, &c->v_flat, &c->e_gray, &c->e_blur, &c->e_mag, &c->e_gx, &c->e_gy, &c->e_map, &c->e_edges,
                   &c->e_hist, &c->e_lut, &c->e_changed, &c->tab_ad, &c->tab_c, &c->agg_ctr, &c->tab_ad_hsi, &c->hsi_lut, &c->k_in, &c->k_out, &c->k_tab, &c->k_range, &c->r_src, &c->r_map1[0], &c->r_map1[1],
