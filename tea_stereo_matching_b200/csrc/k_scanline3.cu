@@ -293,9 +293,10 @@ __device__ __forceinline__ void walk_v(float (&pm)[KM], float& pt, const Vol& vo
     uint32_t woff = main_all + tail_bytes + (uint32_t)(rel >> 5) * 4u, sh = (uint32_t)rel & 31u;
     uint32_t twoff = main_all + tail_bytes + (uint32_t)(trel >> 5) * 4u, tsh = (uint32_t)trel & 31u;
     uint32_t tail_off = main_all + (wide_tail ? 0u : (uint32_t)(pl0 & 1) * 8u) + (uint32_t)(w * dm.Rp + lane) * 4u;
-    uint32_t tail_toggle = (!wide_tail && (W & 1)) ? 8u : 0u;
+    // odd width and two pixels per 16-byte chunk: the chunk offset of the row's first pixel alternates 0, 8, 0, ... along the path
+    int tail_delta = (!wide_tail && (W & 1)) ? ((pl0 & 1) ? -8 : 8) : 0;
     uint32_t lane_off = (uint32_t)w * main_bytes + (uint32_t)(KM * 4 * lane);
-    asm volatile("" : "+r"(tail_off), "+r"(tail_toggle), "+r"(lane_off), "+r"(woff), "+r"(sh), "+r"(twoff), "+r"(tsh));
+    asm volatile("" : "+r"(tail_off), "+r"(tail_delta), "+r"(lane_off), "+r"(woff), "+r"(sh), "+r"(twoff), "+r"(tsh));
 
     Pen3 pen;
 #pragma unroll
@@ -344,7 +345,8 @@ __device__ __forceinline__ void walk_v(float (&pm)[KM], float& pt, const Vol& vo
         __syncwarp();
         mbar_arrive_lane0(bar + NST * 8u + (dep & zero), lane);
         f += dir_c;
-        tail_off ^= tail_toggle;
+        tail_off += (uint32_t)tail_delta;
+        tail_delta = -tail_delta;
         st += stage_bytes;
         bar += 8u;
         if (++slot == NST) {
@@ -784,15 +786,18 @@ void launch3(const Launcher& L, const Dims& d, const ViewPtrs& left, const ViewP
 
 }  // namespace
 
-bool scanline3_supported(const Dims& d)
+bool scanline3_geometry(const Dims& d)
 {
-    static const bool on = [] {
-        const char* e = getenv("TSM_SCAN3");
-        return !(e && e[0] == '0');
-    }();
-    if (!on || d.Rp == 0 || d.W < 4 || d.H < 2) return false;
+    if (d.Rp == 0 || d.W < 4 || d.H < 2) return false;
     const int km = d.Dm / 32;
     return (km >= 1 && km <= 8) || km == 12;
+}
+
+bool scanline3_supported(const Dims& d)
+{
+    // TSM_SCAN3=0 selects k_scanline.cu for every geometry (read per call: the parity test switches it inside one process)
+    const char* e = getenv("TSM_SCAN3");
+    return !(e && e[0] == '0') && scanline3_geometry(d);
 }
 
 void prep_scan_bits(const Launcher& L, const Dims& d, const uint8_t* flags_left, const uint8_t* flags_right, uint32_t* sbits_left,

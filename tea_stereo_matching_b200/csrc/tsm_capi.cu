@@ -54,6 +54,7 @@ struct tsm_ctx {
     Buf v_vote, v_lowcnt, v_off, v_mark, v_start, v_sums, v_flat, v_stash;
     Buf e_gray, e_blur, e_mag, e_gx, e_gy, e_map, e_edges, e_hist, e_lut, e_changed;
     Buf tab_ad, tab_c, agg_ctr, tab_ad_hsi, hsi_lut;
+    bool use_scan3 = false;  // the flags of the blocked scanline walk (k_scanline3.cu) were prepared for the current pair
     bool mask = false;     // mask matching mode: black pixels are holes (cost 2, zero arms, skipped scanline steps)
     bool roi = false;      // ROI / mask matching mode: maxD = W / 2, HSI hue filter instead of the Gauss-median, offset + final marking
     int roi_offset = 0;
@@ -299,7 +300,7 @@ int ensure_arena(tsm_ctx* c, const tsm_adcensus_config* cfg, int H, int W)
         if ((rc = ensure(c, c->fdesc_v[k], d.fdesc_v_words() * 4, true))) return rc;
         if ((rc = ensure(c, c->flags[k], npx))) return rc;
         if ((rc = ensure(c, c->tflags[k], ((size_t)2 * H * d.stab_pitch() + 64) * 4, true))) return rc;
-        if (scanline3_supported(d) && (rc = ensure(c, c->sbits[k], (sb_layout(H, W).words + 64) * 4, true))) return rc;
+        if (scanline3_geometry(d) && (rc = ensure(c, c->sbits[k], (sb_layout(H, W).words + 64) * 4, true))) return rc;
         if ((rc = ensure(c, c->vol[k], (npx * d.Dm + aggregate_overread_floats(d)) * 4 + 256, true))) return rc;
         if ((rc = ensure(c, c->vtail[k], (npx * d.Rp + aggregate_overread_floats(d)) * 4 + 256, true))) return rc;
         if ((rc = ensure(c, c->wta_[k], npx * 4))) return rc;
@@ -419,7 +420,8 @@ int run_stages(tsm_ctx* c, int mask, int arg)
         }
         prep_views(L, d, img, img4, census, arms, desc_h, desc_v, fdesc_h, fdesc_v, flags, model_params(c->hsi, c->mask),
                    (const uint32_t*)c->hsi_lut.p, c->roi);
-        if (scanline3_supported(d))
+        c->use_scan3 = scanline3_supported(d);  // the scanline stage follows what was prepared
+        if (c->use_scan3)
             prep_scan_bits(L, d, (const uint8_t*)c->flags[0].p, (const uint8_t*)c->flags[1].p, (uint32_t*)c->sbits[0].p,
                            (uint32_t*)c->sbits[1].p);
         else
@@ -441,7 +443,7 @@ int run_stages(tsm_ctx* c, int mask, int arg)
         ScopedStage s(c, "scanline");
         // the last (leftward) pass also writes both WTA maps (cost2disparity fused)
         // (minD != 0: the WTA range is restricted, the stand-alone kernel below does it and needs the right volume's last store)
-        if (scanline3_supported(d))
+        if (c->use_scan3)
             scanline3(L, d, vl, vr, c->p1_lo, c->p2_lo, (int32_t*)c->wta_[0].p, (int32_t*)c->wta_[1].p, c->stage_mode || d.minD != 0);
         else
             scanline(L, d, vl, vr, c->p1_lo, c->p2_lo, (int32_t*)c->wta_[0].p, (int32_t*)c->wta_[1].p, c->stage_mode || d.minD != 0);
