@@ -1,7 +1,4 @@
 t() { timeout 120 python scripts/run_one.py --D 192 --reps 4 | tail -2 | head -1 | tr "," "\n" | grep scanline | grep -v "#n" | tr "\n" " "; echo; }
-echo default; t
-echo NWH=15; TSM_S3_NWH=15 t; TSM_S3_NWH=15 t
-echo NWH=15 P4 N4; TSM_S3_NWH=15 TSM_S3_P=4 TSM_S3_NSTH=4 t
-echo NWH=8; TSM_S3_NWH=8 t
-echo NWH=5; TSM_S3_NWH=5 t
-echo NWH=3; TSM_S3_NWH=3 t
+timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_scanline3.py tests/test_gpu_hsi.py tests/test_gpu_determinism.py tests/test_gpu_mindisp.py -x -q 2>&1 | tail -3
+echo default; t; t; t
+for D in 48 192; do timeout 300 python scripts/stress_mixed.py $D 30 2>&1 | tail -2; done

@@ -176,39 +176,25 @@ struct Pen3 {
 // One step of partialOptimization (ADCensus.cpp:869-913) on the blocked vector: pm[k] is disparity KM * lane + k, pt the
 // tail element Dm + lane (+inf in the lanes beyond the tail).  sim: bit k = the other view's pair is similar for pm[k];
 // simt the same for the tail element.  Returns whether the pixel changed.
-// A skipped step (hole, m == 0) only copies the loaded vector: `dep` then collects every loaded register, so that the release /
-// refill of the stage, whose address is made to depend on it, cannot be issued while one of these loads is still in flight.
-// (A step that changes the pixel consumes all of them in the arithmetic that its stores, which precede the release, wait for.)
+// One step of partialOptimization (ADCensus.cpp:869-913) on the blocked vector: pm[k] is disparity KM * lane + k, pt the
+// tail element Dm + lane (+inf in the lanes beyond the tail).  sim: bit k = the other view's pair is similar for pm[k];
+// simt the same for the tail element.
+// A skipped step (black predecessor in mask matching, :824 / :862; m == 0, :880) leaves the pixel as it is.  It is computed
+// and selected away instead of branched around, and the caller stores the vector in either case: every loaded register is
+// then consumed by arithmetic that the stores wait for, and the stores precede the release / refill of the stage in program
+// order -- the bulk copy into the stage can never be issued while a ld.shared of it is still in flight (the hazard of
+// k_scanline.cu), without a per-step dependency chain on the release.  Re-storing an unchanged vector costs nothing extra:
+// the traffic budget counts every cell as written.
 template <int KM>
-__device__ __forceinline__ uint32_t skip3(float (&pm)[KM], float& pt, const float (&cm)[KM], float ct)
+__device__ __forceinline__ void step3(float (&pm)[KM], float& pt, const float (&cm)[KM], float ct, unsigned sim, bool simt,
+                                      unsigned own, bool hole, int lane, const Pen3& pen)
 {
-    uint32_t dep = __float_as_uint(ct);
-#pragma unroll
-    for (int k = 0; k < KM; ++k) {
-        pm[k] = cm[k];
-        dep ^= __float_as_uint(cm[k]);
-    }
-    pt = ct;
-    return dep;
-}
-
-template <int KM>
-__device__ __forceinline__ bool step3(float (&pm)[KM], float& pt, const float (&cm)[KM], float ct, unsigned sim, bool simt,
-                                      unsigned own, bool hole, int lane, const Pen3& pen, uint32_t& dep)
-{
-    if (hole) {  // mask matching: the predecessor is a masked pixel, the step is skipped (ADCensus.cpp:824, 862)
-        dep ^= skip3<KM>(pm, pt, cm, ct);
-        return false;
-    }
     unsigned mb = __float_as_uint(pt);
 #pragma unroll
     for (int k = 0; k < KM; ++k) mb = min(mb, __float_as_uint(pm[k]));
     mb = __reduce_min_sync(0xffffffffu, mb);
     const float m = __uint_as_float(mb);
-    if (m == 0.f) {  // ADCensus.cpp:880 -- pixel left untouched
-        dep ^= skip3<KM>(pm, pt, cm, ct);
-        return false;
-    }
+    const bool skip = hole || m == 0.f;
     const float p1a = own ? pen.p1[1] : pen.p1[0], p1b = own ? pen.p1[2] : pen.p1[1];
     const float mp2a = __fadd_rn(m, own ? pen.p2[1] : pen.p2[0]), mp2b = __fadd_rn(m, own ? pen.p2[2] : pen.p2[1]);
     // the four values that cross a lane boundary: block ends and the tail register
@@ -236,11 +222,11 @@ __device__ __forceinline__ bool step3(float (&pm)[KM], float& pt, const float (&
         const float mp2 = simt ? mp2b : mp2a;
         const float nb = __fadd_rn(fminf(lot, hit), p1);
         const float mo = fminf(fminf(mp2, pt), nb);
-        pt = __fmul_rn(__fadd_rn(__fsub_rn(ct, m), mo), 0.5f);
+        const float nt = __fmul_rn(__fadd_rn(__fsub_rn(ct, m), mo), 0.5f);
+        pt = skip ? ct : nt;
     }
 #pragma unroll
-    for (int k = 0; k < KM; ++k) pm[k] = nm[k];
-    return true;
+    for (int k = 0; k < KM; ++k) pm[k] = skip ? cm[k] : nm[k];
 }
 
 // cost2disparity: first strict minimum over d (ADCensus.cpp:1398-1409) of the blocked vector
@@ -309,8 +295,7 @@ __device__ __forceinline__ void walk_v(float (&pm)[KM], float& pt, const Vol& vo
     float* tdst = vol.tail + (size_t)p0 * dm.Rp + lane;
     ptrdiff_t vstep = (ptrdiff_t)pstep * dm.Dm, wstep = (ptrdiff_t)pstep * dm.Rp;
     int dir_c = dir;
-    uint32_t zero = (uint32_t)sp.zero;
-    asm volatile("" : "+l"(vstep), "+l"(wstep), "+r"(dir_c), "+r"(zero));
+    asm volatile("" : "+l"(vstep), "+l"(wstep), "+r"(dir_c));
     const unsigned hole_bit = dir > 0 ? 2u : 4u;
 
     uint32_t st = base + slot * stage_bytes, bar = bars + slot * 8u;
@@ -327,23 +312,14 @@ __device__ __forceinline__ void walk_v(float (&pm)[KM], float& pt, const Vol& vo
         const bool simt = (wt >> tsh) & 1u;
         const uint32_t nib = nw >> (((uint32_t)f & 7u) * 4u);
 
-        uint32_t dep = w0 ^ w1 ^ wt ^ nw;
-        const bool changed = step3<KM>(pm, pt, cm, ct, g, simt, nib & 1u, (nib & hole_bit) != 0, lane, pen, dep);
-        if (changed) {
-            stg_block<KM>(dst, pm);
-            if (lastvalid) *tdst = pt;
-        }
+        step3<KM>(pm, pt, cm, ct, g, simt, nib & 1u, (nib & hole_bit) != 0, lane, pen);
+        stg_block<KM>(dst, pm);
+        if (lastvalid) *tdst = pt;
         dst += vstep;
         tdst += wstep;
-        // Release the stage to the producer: one arrival per warp, after __syncwarp has collected the lanes.  It must not
-        // overtake any lane's ld.shared of the stage (the bulk copy that follows writes it through the async proxy): every
-        // lane has either stored results that depend on all its loads or folded them into `dep` (step3), and lane 0's
-        // arrival address depends on its own `dep`.
-#ifdef TSM_S3_WEAKDEP  // experiment: the release depends on the last load only (fails scripts/stress_mixed.py)
-        dep = nw;
-#endif
+        // Release the stage to the producer: one arrival per warp, after the stores of every lane (see step3).
         __syncwarp();
-        mbar_arrive_lane0(bar + NST * 8u + (dep & zero), lane);
+        mbar_arrive_lane0(bar + NST * 8u, lane);
         f += dir_c;
         tail_off += (uint32_t)tail_delta;
         tail_delta = -tail_delta;
@@ -529,8 +505,7 @@ __device__ __forceinline__ void walk_h(float (&pm)[KM], float& pt, const Vol& vo
     int32_t* wdst = WTA ? wta_out + rowp + x : nullptr;
     ptrdiff_t vstep = (ptrdiff_t)dir * dm.Dm, wstep = (ptrdiff_t)dir * dm.Rp;
     int dir_c = dir;
-    uint32_t zero = (uint32_t)sp.zero;
-    asm volatile("" : "+l"(vstep), "+l"(wstep), "+r"(dir_c), "+r"(zero));
+    asm volatile("" : "+l"(vstep), "+l"(wstep), "+r"(dir_c));
     const unsigned hole_bit = dir > 0 ? 2u : 4u;
 
     uint32_t st = wbase + slot * stage_bytes, bar = bars + slot * 8u;
@@ -540,7 +515,6 @@ __device__ __forceinline__ void walk_h(float (&pm)[KM], float& pt, const Vol& vo
         const int n = dir > 0 ? xe - x + 1 : x - xe + 1;
         uint32_t qm = st + (uint32_t)(x - gx) * mstride + lane_off;
         uint32_t qt = st + toff0 + (uint32_t)(x - gx) * tstride;
-        uint32_t last = 0;
         mbar_wait(bar, parity);
         for (int j = 0; j < n; ++j) {
             float cm[KM];
@@ -551,17 +525,13 @@ __device__ __forceinline__ void walk_h(float (&pm)[KM], float& pt, const Vol& vo
             const uint32_t w0 = lds_u32(a), w1 = lds_u32(a + 4u);
             const uint32_t wt = lds_u32(row_bits + (((uint32_t)Bt >> 5) << 2));
             const uint32_t nw = lds_u32(own_base + (((uint32_t)f >> 3) << 2));
-            last ^= w0 ^ w1 ^ wt ^ nw;
             uint32_t gb = __funnelshift_r(w0, w1, (uint32_t)Bl);
             if (sgn < 0) gb = __brev(gb) >> (32 - KM);
             const bool simt = (wt >> ((uint32_t)Bt & 31u)) & 1u;
             const uint32_t nib = nw >> (((uint32_t)f & 7u) * 4u);
 
-            const bool changed = step3<KM>(pm, pt, cm, ct, gb, simt, nib & 1u, (nib & hole_bit) != 0, lane, pen, last);
-#ifdef TSM_S3_WEAKDEP
-            last = nw;
-#endif
-            if (changed && do_store) {
+            step3<KM>(pm, pt, cm, ct, gb, simt, nib & 1u, (nib & hole_bit) != 0, lane, pen);
+            if (do_store) {
                 stg_block<KM>(dst, pm);
                 if (lastvalid) *tdst = pt;
             }
@@ -581,15 +551,16 @@ __device__ __forceinline__ void walk_h(float (&pm)[KM], float& pt, const Vol& vo
         x += dir_c * n;
         // Refill the stage with the group NST ahead.  The bulk copy writes shared memory through the async proxy and is not
         // ordered behind this warp's ld.shared of the stage by itself (k_scanline.cu: the copy once overtook loads that were
-        // still in flight).  Every lane has either stored results that depend on all its loads of the group or folded them
-        // into `last` (step3); __syncwarp collects the lanes and the copy's destination address depends on the issuing
-        // lane's `last`.  -DTSM_S3_FENCE adds the proxy fence of the issuing lane in front (no measurable difference).
+        // still in flight).  Every lane's loads of the group have been consumed by arithmetic that its stores (the cost
+        // vectors, or the WTA word where the vectors are not kept) wait for, the stores precede this point in program order,
+        // and __syncwarp collects the lanes (see step3).  -DTSM_S3_FENCE adds the proxy fence of the issuing lane in front
+        // (no measurable difference).
         __syncwarp();
         if (gi + (int)NST < ngroups && elect_one()) {
 #ifdef TSM_S3_FENCE
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 #endif
-            issue(g + dir_c * (int)NST, st + (last & zero), bar);
+            issue(g + dir_c * (int)NST, st, bar);
         }
         g += dir_c;
         st += stage_bytes;
