@@ -53,9 +53,10 @@ constexpr int AGG_PF = TSM_AGG_PF;        // prefetch distance
 // Register buffers of the walk: NB-1 batches of AGG_PF loads in flight, NB*AGG_PF steps unrolled per loop
 // iteration.  More buffers = deeper prefetch but a bigger loop body, and the instruction cache matters: with
 // two ring homes (two copies of the loop) resident per SM, 8 buffers spent more cycles in no_instruction
-// stalls than in memory stalls (ncu), 6 is the measured optimum; the single-copy kernel is best at 8.
+// stalls than in memory stalls (ncu), 6 was the measured optimum without the L2 prefetch below, 4 with it; the single-copy
+// kernel is best at 8.
 #ifndef TSM_AGG_NBUF
-#define TSM_AGG_NBUF 6
+#define TSM_AGG_NBUF 4
 #endif
 constexpr int AGG_NBUF_PERSIST = TSM_AGG_NBUF, AGG_NBUF_STATIC = 8;
 constexpr int AGG_U = 8 * AGG_PF;         // upper bound of the steps per main-loop iteration (over-read slack, minimum line length)
@@ -144,6 +145,19 @@ __device__ __forceinline__ float2 ld_stream(const char* p)
     else { asm volatile("ld.global.L1::no_allocate.f32 %0, [%1];" : "=f"(v.x) : "l"(p)); v.y = 0.f; }
     return v;
 }
+// Single-pass walk: batches the L2 prefetch runs ahead of the register loads (0 = off).  All global loads of a warp share
+// one or two scoreboard slots, so register buffers cannot cover the DRAM latency (see k_agg_fused); a prefetch has no
+// destination register.  Measured at C3 (ms, horizontal pass / normalising horizontal pass; 6 register buffers unless noted):
+// off 1.35 / 1.45, 4: 1.11 / 1.31, 6: 1.10 / 1.32, 8: 1.11 / 1.27, 10: 1.13 / 1.25, 16: 1.15 / 1.25; 8 with 4 buffers 1.10 / 1.27
+// (kept: smaller loop), 8 with 2 buffers 1.20 / 1.26.
+#ifndef TSM_AGG_PD
+#define TSM_AGG_PD 8
+#endif
+constexpr int AGG_PD = TSM_AGG_PD;
+__device__ __forceinline__ void prefetch_l2_lt(const char* p, int pos, int len)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.lt.u32 p, %1, %2;\n\t@p prefetch.global.L2 [%0];\n\t}" ::"l"(p), "r"(pos), "r"(len));
+}
 __device__ __forceinline__ void st_stream(char* p, float a, float b)
 {
 
@@ -209,9 +223,16 @@ __device__ __forceinline__ void walk_line(const Ring ring, float* cell, const ui
         asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(a) : "r"(cstride), "r"((uint32_t)u), "l"(base));
         return a;
     };
+    int t_load = AGG_LAG;  // position of in_ptr on the line
     auto load_batch = [&](int buf) {
 #pragma unroll
         for (int u = 0; u < AGG_PF; ++u) vin[buf][u] = ld_stream(step_addr(in_ptr, u));
+        if (AGG_PD > 0) {
+            // the DRAM latency is covered by an L2 prefetch (no destination register, no scoreboard slot) AGG_PD batches ahead
+#pragma unroll
+            for (int u = 0; u < AGG_PF; ++u) prefetch_l2_lt(step_addr(in_ptr, AGG_PD * AGG_PF + u), t_load + AGG_PD * AGG_PF + u, len);
+            t_load += AGG_PF;
+        }
         in_ptr = step_addr(in_ptr, AGG_PF);
         asm volatile("" : "+l"(in_ptr));
 #pragma unroll
