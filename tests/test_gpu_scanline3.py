@@ -22,6 +22,10 @@ GEOMETRIES = [
     (30, 700, 0, 250),   # KM 7, r 27
     (36, 600, 0, 280),   # KM 8, r 25
     (24, 900, 0, 384),   # KM 12, r 1
+    (2, 4, 0, 33),       # the smallest pair the blocked walk takes: one step per vertical path, one partial CTA
+    (3, 5, 0, 40),       # fewer columns than a CTA owns, odd width
+    (7, 9, 0, 33),       # a single partial pixel group per row
+    (300, 13, 0, 64),    # tall and narrow: one CTA per view in the vertical launch
 ]
 
 
@@ -42,7 +46,12 @@ def test_blocked_walk_equals_striped_walk_stage_by_stage(H, W, mind, maxd):
     from tea_stereo_matching_b200 import _native as N
     from tea_stereo_matching_b200.synth import synth_v1
 
-    left, right = synth_v1(H, W, min(maxd, W // 3), seed=500 + W)
+    if min(H, W) < 16:  # too small for the synthetic scene generator: smooth noise (similar neighbours do occur)
+        rng = np.random.default_rng(H * 1000 + W)
+        left = (rng.integers(0, 4, (H, W, 3)) * 8 + 100).astype(np.uint8)
+        right = (rng.integers(0, 4, (H, W, 3)) * 8 + 100).astype(np.uint8)
+    else:
+        left, right = synth_v1(H, W, min(maxd, W // 3), seed=500 + W)
 
     def run():
         r = t.StageRunner(left, right, maxd, min_disparity=mind)
