@@ -112,22 +112,121 @@ void lrc(const Launcher& L, const Dims& d, const int32_t* dl, const int32_t* dr,
 // Cross region of p (arms of the LEFT view): horizontal_first: rows y-up..y+down, each
 // with its own left/right arm; else columns x-left..x+right, each with its own up/down arm.
 
-// Calls f(valid, value) warp-synchronously for every pixel of the cross region of p.
+// ---- which rows of a region can hold a vote ----------------------------------------------------------------------------------
+// A third to two thirds of the outliers sit inside blobs of outliers (the left border band, occlusions): their cross region holds
+// no valid pixel, in every one of the five iterations (measured at C3: 60 / 50 / 46 / 35 / 30 % of the outliers, 34 - 57 % on the
+// 0600 pair), and the regions that do hold votes hold them in a few rows at the blob's edge.  One strip-local prefix count of the
+// valid mask along x per iteration (k_vote_prefix) answers "how many valid pixels between columns q0 and q1 of row c" with two or
+// three byte loads:
+//   horizontal first: the region IS a set of row segments -> the exact vote count without a traversal, and the rows worth walking;
+//   vertical first  : the region lies inside rows y - max(up) .. y + max(down), columns x - left .. x + right -> the rows of that box
+//                     that hold any valid pixel (a superset of the rows worth walking; the count is taken during the walk).
+// Strips of 128 pixels (a segment is at most 67 long: it crosses at most one strip boundary) keep the counts in one byte.
+constexpr int VP_STRIP = 128;
+__global__ void __launch_bounds__(256) k_vote_prefix(const int32_t* __restrict__ disp, uint8_t* __restrict__ pre, int H, int W, int minD)
+{
+    // a warp owns (row, strip of 128 columns), a lane 4 consecutive pixels
+    const int lane = threadIdx.x & 31;
+    const int nstrip = (W + VP_STRIP - 1) / VP_STRIP;
+    const int item = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (item >= H * nstrip) return;
+    const int y = item / nstrip, x0 = (item % nstrip) * VP_STRIP + 4 * lane;
+    int v[4], sum = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        v[k] = (x0 + k < W && disp[(size_t)y * W + x0 + k] >= minD) ? 1 : 0;
+        sum += v[k];
+    }
+    int inc = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    int run = inc - sum;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        run += v[k];
+        if (x0 + k < W) pre[(size_t)y * W + x0 + k] = (uint8_t)run;
+    }
+}
+
+// valid pixels at columns q0..q1 (inclusive, q0 <= q1 <= q0 + 127) of the row whose strip-local prefix counts start at `row`
+__device__ __forceinline__ int vp_count(const uint8_t* __restrict__ row, int q0, int q1)
+{
+    int r = row[q1];
+    if (q0 & (VP_STRIP - 1)) r -= row[q0 - 1];
+    if ((q0 ^ q1) & ~(VP_STRIP - 1)) r += row[q0 | (VP_STRIP - 1)];  // the strip q0 lies in, up to its end
+    return r;
+}
+
+struct RegionRows {
+    unsigned mask[3];  // bit b of mask[ch]: row y + first + 32 ch + b can hold a valid pixel of the region
+    int first;         // first row of the region (its bounding box), relative to y
+    int cnt;           // horizontal first: the exact vote count; vertical first: an upper bound (0 = the region is empty)
+};
+template <bool HF>
+__device__ __forceinline__ RegionRows region_rows(const uint8_t* __restrict__ pre, const uchar4* __restrict__ arms, int W, size_t p, int lane)
+{
+    const uchar4 a = arms[p];
+    const int y = (int)(p / W), x = (int)(p - (size_t)y * W);
+    int up = a.x, down = a.y;
+    if (!HF) {  // the tallest column of the region
+        const int n = (int)a.z + (int)a.w + 1;
+        int mu = 0, md = 0;
+        for (int o = lane; o < n; o += 32) {
+            const uchar4 ac = arms[p - a.z + o];
+            mu = max(mu, (int)ac.x);
+            md = max(md, (int)ac.y);
+        }
+        up = __reduce_max_sync(0xffffffffu, mu);
+        down = __reduce_max_sync(0xffffffffu, md);
+    }
+    RegionRows R;
+    R.first = -up;
+    const int n = up + down + 1;  // <= 67
+    int cnt = 0;
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+        const int o = 32 * ch + lane;
+        int cj = 0;
+        if (o < n) {
+            const int c = y - up + o;
+            int q0 = x - (int)a.z, q1 = x + (int)a.w;
+            if (HF) {
+                const uchar4 ac = arms[(size_t)c * W + x];
+                q0 = x - (int)ac.z;
+                q1 = x + (int)ac.w;
+            }
+            cj = vp_count(pre + (size_t)c * W, q0, q1);
+        }
+        R.mask[ch] = __ballot_sync(0xffffffffu, cj > 0);
+        cnt += cj;
+    }
+    R.cnt = __reduce_add_sync(0xffffffffu, cnt);
+    return R;
+}
+
+// Calls f(valid, value) warp-synchronously for every pixel of the cross region of p that lies in one of the rows of R.
 // Lanes always run along x so the disparity reads are coalesced.
 template <bool HF, typename F>
 __device__ __forceinline__ void for_each_region(const int32_t* __restrict__ disp, const uchar4* __restrict__ arms, int W,
-                                                size_t p, int lane, int minD, F f)
+                                                size_t p, int lane, int minD, const RegionRows& R, F f)
 {
     const uchar4 a = arms[p];
     if (HF) {
-        for (int o = -(int)a.x; o <= (int)a.y; ++o) {
-            const size_t c = p + (ptrdiff_t)o * W;
-            const uchar4 ac = arms[c];
-            for (int i0 = -(int)ac.z; i0 <= (int)ac.w; i0 += 32) {
-                const int i = i0 + lane;
-                const bool in = i <= (int)ac.w;
-                const int v = in ? disp[c + i] : -1;
-                f(in && v >= minD, v - minD);  // valid: disp >= minD; histogram bin disp - minD (:1127-1131)
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) {
+            for (unsigned m = R.mask[ch]; m; m &= m - 1) {
+                const int o = R.first + 32 * ch + __ffs(m) - 1;
+                const size_t c = p + (ptrdiff_t)o * W;
+                const uchar4 ac = arms[c];
+                for (int i0 = -(int)ac.z; i0 <= (int)ac.w; i0 += 32) {
+                    const int i = i0 + lane;
+                    const bool in = i <= (int)ac.w;
+                    const int v = in ? disp[c + i] : -1;
+                    f(in && v >= minD, v - minD);  // valid: disp >= minD; histogram bin disp - minD (:1127-1131)
+                }
             }
         }
     } else {
@@ -137,112 +236,18 @@ __device__ __forceinline__ void for_each_region(const int32_t* __restrict__ disp
             const bool oin = o <= (int)a.w;
             const size_t c = p + (oin ? o : 0);
             const uchar4 ac = arms[c];
-            int up = oin ? (int)ac.x : 0, down = oin ? (int)ac.y : 0;
-            int mup = up, mdown = down;
+            const int up = oin ? (int)ac.x : -1, down = oin ? (int)ac.y : -1;  // -1: no row matches
 #pragma unroll
-            for (int s = 16; s > 0; s >>= 1) {
-                mup = max(mup, __shfl_xor_sync(0xffffffffu, mup, s));
-                mdown = max(mdown, __shfl_xor_sync(0xffffffffu, mdown, s));
-            }
-            for (int i = -mup; i <= mdown; ++i) {
-                const bool in = oin && i >= -up && i <= down;
-                const int v = in ? disp[c + (ptrdiff_t)i * W] : -1;
-                f(in && v >= minD, v - minD);  // valid: disp >= minD; histogram bin disp - minD (:1127-1131)
+            for (int ch = 0; ch < 3; ++ch) {
+                for (unsigned m = R.mask[ch]; m; m &= m - 1) {
+                    const int i = R.first + 32 * ch + __ffs(m) - 1;
+                    const bool in = i >= -up && i <= down;
+                    const int v = in ? disp[c + (ptrdiff_t)i * W] : -1;
+                    f(in && v >= minD, v - minD);  // valid: disp >= minD; histogram bin disp - minD (:1127-1131)
+                }
             }
         }
     }
-}
-
-// ---- vote-count precount ---------------------------------------------------------------------------------------------------
-// A third to two thirds of the outliers sit inside blobs of outliers (the left border band, occlusions): their cross region holds
-// no valid pixel, in every one of the five iterations (measured at C3: 60 / 50 / 46 / 35 / 30 % of the outliers, 34 - 57 % on the
-// 0600 pair).  The vote COUNT is separable -- the region is a union of segments, one per row (horizontal first) or per column --
-// so it is the sum of prefix-count differences: one strip-local prefix of the valid mask per iteration (k_vote_prefix), then
-// <= 69 segment counts per outlier instead of a traversal.  Only outliers with at least one vote are traversed.
-// Strips of 128 pixels along the segment direction (a segment is at most 69 long: it crosses at most one strip boundary) keep
-// the counts in one byte.
-constexpr int VP_STRIP = 128;
-template <bool HF>
-__global__ void __launch_bounds__(256) k_vote_prefix(const int32_t* __restrict__ disp, uint8_t* __restrict__ pre, int H, int W, int minD)
-{
-    if (HF) {
-        // horizontal segments: a warp owns (row, strip of 128 columns), a lane 4 consecutive pixels
-        const int lane = threadIdx.x & 31;
-        const int nstrip = (W + VP_STRIP - 1) / VP_STRIP;
-        const int item = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-        if (item >= H * nstrip) return;
-        const int y = item / nstrip, x0 = (item % nstrip) * VP_STRIP + 4 * lane;
-        int v[4], sum = 0;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            v[k] = (x0 + k < W && disp[(size_t)y * W + x0 + k] >= minD) ? 1 : 0;
-            sum += v[k];
-        }
-        int inc = sum;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int t = __shfl_up_sync(0xffffffffu, inc, o);
-            if (lane >= o) inc += t;
-        }
-        int run = inc - sum;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            run += v[k];
-            if (x0 + k < W) pre[(size_t)y * W + x0 + k] = (uint8_t)run;
-        }
-    } else {
-        // vertical segments: a thread owns (column, strip of 128 rows)
-        const int x = blockIdx.x * blockDim.x + threadIdx.x;
-        if (x >= W) return;
-        const int y0 = blockIdx.y * VP_STRIP, y1 = min(y0 + VP_STRIP, H);
-        int run = 0;
-#pragma unroll 8
-        for (int y = y0; y < y1; ++y) {
-            run += disp[(size_t)y * W + x] >= minD ? 1 : 0;
-            pre[(size_t)y * W + x] = (uint8_t)run;
-        }
-    }
-}
-
-// valid pixels at positions q0..q1 (inclusive, q0 <= q1 <= q0 + 127) of the line whose strip-local prefix counts start at `line`
-// with element stride `stride`
-__device__ __forceinline__ int vp_count(const uint8_t* __restrict__ line, size_t stride, int q0, int q1)
-{
-    int r = line[(size_t)q1 * stride];
-    if (q0 & (VP_STRIP - 1)) r -= line[(size_t)(q0 - 1) * stride];
-    if ((q0 ^ q1) & ~(VP_STRIP - 1)) r += line[(size_t)(q0 | (VP_STRIP - 1)) * stride];  // the strip q0 lies in, up to its end
-    return r;
-}
-
-// vote count of outlier p = number of valid pixels of its cross region (warp-wide, every lane gets the sum)
-template <bool HF>
-__device__ __forceinline__ int vote_precount(const uint8_t* __restrict__ pre, const uchar4* __restrict__ arms, int W, size_t p, int lane)
-{
-    const uchar4 a = arms[p];
-    const int y = (int)(p / W), x = (int)(p - (size_t)y * W);
-    int cnt = 0;
-    if (HF) {
-        const int n = (int)a.x + (int)a.y + 1;  // rows y - up .. y + down, each with its own left / right arm
-        for (int o0 = 0; o0 < n; o0 += 32) {
-            const int o = o0 + lane;
-            if (o < n) {
-                const int c = y - (int)a.x + o;
-                const uchar4 ac = arms[(size_t)c * W + x];
-                cnt += vp_count(pre + (size_t)c * W, 1, x - (int)ac.z, x + (int)ac.w);
-            }
-        }
-    } else {
-        const int n = (int)a.z + (int)a.w + 1;  // columns x - left .. x + right, each with its own up / down arm
-        for (int o0 = 0; o0 < n; o0 += 32) {
-            const int o = o0 + lane;
-            if (o < n) {
-                const int c = x - (int)a.z + o;
-                const uchar4 ac = arms[(size_t)y * W + c];
-                cnt += vp_count(pre + c, (size_t)W, y - (int)ac.x, y + (int)ac.y);
-            }
-        }
-    }
-    return __reduce_add_sync(0xffffffffu, cnt);
 }
 
 // A CTA owns a tile of 256 consecutive pixels: every thread classifies its own pixel, the
@@ -321,8 +326,8 @@ k_vote_pass_a(const int32_t* __restrict__ disp, const uchar4* __restrict__ arms,
     for (int i = warp; i < n; i += VOTE_WARPS) {
         const size_t p = p0 + list[i];
         const int dp = disp[p];
-        const int cnt = vote_precount<HF>(pre, arms, W, p, lane);
-        if (cnt == 0) {  // empty region: nothing to vote with, nothing to park
+        const RegionRows R = region_rows<HF>(pre, arms, W, p, lane);
+        if (R.cnt == 0) {  // empty region: nothing to vote with, nothing to park
             if (lane == 0) {
                 vote[p] = 0;
                 lowcnt[p] = 0;
@@ -332,7 +337,11 @@ k_vote_pass_a(const int32_t* __restrict__ disp, const uchar4* __restrict__ arms,
         }
         for (int d = lane; d < Dn; d += 32) hist[d] = 0;
         __syncwarp();
-        for_each_region<HF>(disp, arms, W, p, lane, minD, [&](bool valid, int v) { hist_add(hist, valid, v, lane); });
+        int cnt = HF ? R.cnt : 0;
+        for_each_region<HF>(disp, arms, W, p, lane, minD, R, [&](bool valid, int v) {
+            if (!HF) cnt += __popc(__ballot_sync(0xffffffffu, valid));
+            hist_add(hist, valid, v, lane);
+        });
         __syncwarp();
         int res = dp;
         if (cnt > kVotingThresh) {
@@ -387,9 +396,9 @@ __global__ void k_vote_copy(const int32_t* __restrict__ lowcnt, const int32_t* _
 // Pass B: high-vote outliers that inherit leaked votes (start < off): own region again + the slice.
 template <bool HF>
 __global__ void __launch_bounds__(VOTE_TILE)
-k_vote_pass_b(const int32_t* __restrict__ disp, const uchar4* __restrict__ arms, const int32_t* __restrict__ vote,
-              const int32_t* __restrict__ off, const int32_t* __restrict__ start, const uint16_t* __restrict__ flat,
-              int32_t* __restrict__ out, size_t npx, int W, int Dn, int minD)
+k_vote_pass_b(const int32_t* __restrict__ disp, const uchar4* __restrict__ arms, const uint8_t* __restrict__ pre,
+              const int32_t* __restrict__ vote, const int32_t* __restrict__ off, const int32_t* __restrict__ start,
+              const uint16_t* __restrict__ flat, int32_t* __restrict__ out, size_t npx, int W, int Dn, int minD)
 {
     extern __shared__ int hist_all[];  // [VOTE_WARPS][Dn]
     __shared__ int list[VOTE_TILE];
@@ -406,7 +415,8 @@ k_vote_pass_b(const int32_t* __restrict__ disp, const uchar4* __restrict__ arms,
         const size_t p = p0 + list[i];
         for (int d = lane; d < Dn; d += 32) hist[d] = 0;
         __syncwarp();
-        for_each_region<HF>(disp, arms, W, p, lane, minD, [&](bool valid, int v) { hist_add(hist, valid, v, lane); });
+        const RegionRows R = region_rows<HF>(pre, arms, W, p, lane);
+        for_each_region<HF>(disp, arms, W, p, lane, minD, R, [&](bool valid, int v) { hist_add(hist, valid, v, lane); });
         for (int j0 = start[p]; j0 < off[p]; j0 += 32) {  // the leak
             const int j = j0 + lane;
             const bool in = j < off[p];
@@ -526,16 +536,12 @@ static void region_voting_t(const Launcher& L, const Dims& d, const int32_t* dis
     const size_t npx = d.npx();
     const unsigned wblocks = (unsigned)((npx + VOTE_TILE - 1) / VOTE_TILE);
     const size_t smem = (size_t)VOTE_WARPS * d.Dn * sizeof(int);
-    // strip-local prefix counts of the valid mask along the segment direction; they live in the (not yet used) `start` array
-    uint8_t* pre = reinterpret_cast<uint8_t*>(s.start);
-    if (HF) {
+    // strip-local prefix counts of the valid mask along x (both passes read them)
+    {
         const int items = d.H * ((d.W + VP_STRIP - 1) / VP_STRIP);
-        k_vote_prefix<true><<<(items + 7) / 8, 256, 0, L.stream>>>(disp_in, pre, d.H, d.W, d.minD);
-    } else {
-        dim3 g((d.W + 255) / 256, (d.H + VP_STRIP - 1) / VP_STRIP);
-        k_vote_prefix<false><<<g, 256, 0, L.stream>>>(disp_in, pre, d.H, d.W, d.minD);
+        k_vote_prefix<<<(items + 7) / 8, 256, 0, L.stream>>>(disp_in, s.pre, d.H, d.W, d.minD);
     }
-    k_vote_pass_a<HF><<<wblocks, VOTE_TILE, smem, L.stream>>>(disp_in, arms, pre, s.vote, s.lowcnt, s.stash, disp_out, npx, d.W, d.Dn, d.minD);
+    k_vote_pass_a<HF><<<wblocks, VOTE_TILE, smem, L.stream>>>(disp_in, arms, s.pre, s.vote, s.lowcnt, s.stash, disp_out, npx, d.W, d.Dn, d.minD);
     L.count(2);
     exclusive_scan<OpSum>(L, s.lowcnt, s.off, s.blocksums, npx);
     k_vote_mark<<<(unsigned)((npx + 255) / 256), 256, 0, L.stream>>>(disp_in, s.vote, s.off, s.mark, npx, d.minD);
@@ -543,7 +549,7 @@ static void region_voting_t(const Launcher& L, const Dims& d, const int32_t* dis
     exclusive_scan<OpMax>(L, s.mark, s.start, s.blocksums, npx);
     k_vote_copy<<<(unsigned)((npx + 255) / 256), 256, 0, L.stream>>>(s.lowcnt, s.off, s.stash, s.flat, npx);
     k_vote_pass_b<HF><<<wblocks, VOTE_TILE, smem, L.stream>>>(
-        disp_in, arms, s.vote, s.off, s.start, s.flat, disp_out, npx, d.W, d.Dn, d.minD);
+        disp_in, arms, s.pre, s.vote, s.off, s.start, s.flat, disp_out, npx, d.W, d.Dn, d.minD);
     L.count(2);
 }
 
