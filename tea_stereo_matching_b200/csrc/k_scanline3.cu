@@ -1,6 +1,6 @@
-// k_scanline3.cu -- the four scanline passes (scanlineOptimize, reference source/ADCensus.cpp:795-1011) as a BLOCKED walk
-// with a producer warp.  Same arithmetic, same pass order and same in-place volume as k_scanline.cu (see its header for
-// the recurrence and the bit-exactness argument); what changes is who holds which disparity and who issues the copies.
+// k_scanline3.cu -- the four scanline passes (scanlineOptimize, reference source/ADCensus.cpp:795-1011) as a BLOCKED walk.
+// Same arithmetic, same pass order and same in-place volume as k_scanline.cu (see its header for the recurrence and the
+// bit-exactness argument); what changes is who holds which disparity, where the flags come from and who issues the copies.
 //
 // k_scanline.cu is issue-bound: ~225 warp instructions per pixel step at D = 192, of which only ~75 are the recurrence.
 //   * There a lane holds d = lane + 32 k, so BOTH neighbours d-1 / d+1 of every register come from another lane: two
@@ -15,10 +15,14 @@
 //     A vertical step stages a 48-byte window of the flag row (was 144 bytes), a horizontal path keeps its whole flag row in
 //     shared memory.  The pixel's own flag and the mask-matching "black predecessor" bits are one nibble per pixel of a
 //     string along the path, also in shared memory.
-//   * The bulk copies are issued by a PRODUCER warp (one per CTA, one elected lane) that owns all address arithmetic; the
-//     consumer warps only wait on the stage's "full" mbarrier and release it through its "empty" mbarrier once the
-//     loaded values have been used.  That also settles the refill hazard of k_scanline.cu (async-proxy copy overtaking the
-//     warp's own outstanding ld.shared): the release is data-dependent on the last load of the step.
+//   * Vertical launch (k_scan3v): a CTA owns neighbouring columns, a stage is one image row of them -- three bulk copies per
+//     step for all its lines, issued by a PRODUCER warp (one elected lane) that owns the address arithmetic; the consumer
+//     warps wait on the stage's "full" mbarrier and release it through its "empty" mbarrier.
+//     Horizontal launch (k_scan3h): a stage is a group of consecutive pixels of a row, refilled by the warp itself.
+//   * The refill hazard of k_scanline.cu (async-proxy copy overtaking a warp's outstanding ld.shared) is settled by program
+//     order: every loaded register is consumed by arithmetic that the step's stores wait for, and the stores precede the
+//     release / refill (see step3).
+// ~160 warp instructions per step at D = 192; 4.97 -> 4.36 ms per 1080p pair (0.86 / 0.82 of the HBM copy bandwidth).
 #include "tsm_common.cuh"
 #include <cstdlib>
 #include <limits.h>
@@ -42,8 +46,7 @@ struct S3Params {
     int tail_bytes;         // bytes of the tail chunk of a stage
     int win_words;          // vertical launch: words of the flag-row window of a stage
     int stage_bytes;        // main_all + tail_bytes (+ win_words * 4), multiple of 16
-    int warp_bytes;         // horizontal launch: shared memory of one consumer warp (ring, barriers, strings), multiple of 128
-    int zero;               // always 0, unknown to the compiler
+    int warp_bytes;         // horizontal launch: shared memory of one warp (ring, barriers, strings), multiple of 128
     SbLayout lay;
 };
 
@@ -55,10 +58,6 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, unsigned count)
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, unsigned bytes)
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar)
-{
-    asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive_lane0(uint32_t bar, int lane)
 {
@@ -787,7 +786,6 @@ void scanline3(const Launcher& L, const Dims& d, const ViewPtrs& left, const Vie
     sp.p1[0] = p1_lo; sp.p1[1] = 0.25f; sp.p1[2] = 1.f;
     sp.p2[0] = p2_lo; sp.p2[1] = 0.75f; sp.p2[2] = 3.f;
     sp.store_right_final = store_right_final ? 1 : 0;
-    sp.zero = 0;
     sp.nw = sp.nst = sp.P = sp.main_all = sp.tail_bytes = sp.win_words = sp.stage_bytes = sp.warp_bytes = 0;
     sp.lay = sb_layout(d.H, d.W);
     switch (d.Dm / 32) {
