@@ -2,6 +2,11 @@
 // reference source/ADCensus.cpp:795-1011): down, up, right, left, per view, with the
 // winner-take-all of cost2disparity (:1394-1413) fused into the last pass.
 //
+// This is the STRIPED walk (a lane holds d = lane + 32 k).  Since round 2 the usual disparity ranges (a main part of 32..256
+// or 384 levels plus a tail: every BASELINE configuration) run through the blocked walk of k_scanline3.cu, which is bit-identical
+// and 12 % faster; this file serves the other geometries (no tail, fewer than 32 levels, the 641-level ROI ranges), holds the
+// recurrence / bit-exactness notes both walks rely on, and is the TSM_SCAN3=0 side of tests/test_gpu_scanline3.py.
+//
 // For pixel p with predecessor q on the path (partialOptimization, :869-913):
 //   m = min_k C(q,k);  if m == 0 the pixel is skipped                         (:871-881)
 //   C(p,d) <- ((C(p,d) - m) + min(C(q,d), C(q,d-1)+P1, C(q,d+1)+P1, m+P2)) / 2  (:883-911)
