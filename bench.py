@@ -46,7 +46,8 @@ import numpy as np
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
-IN_FLIGHT = 4
+IN_FLIGHT = 6          # pairs in flight per GPU (measured at C3, same call: 2 -> 16.37 ms per pair, 4 -> 15.91, 6 -> 15.70) ...
+IN_FLIGHT_BIG = 4      # ... unless one context's cost volumes exceed 12 GB (C5: 25 GB each)
 DISTINCT = 8  # distinct frames per rank; the batch cycles through them
 UNIT = "Mpix*disp/s"
 HASH_FRAMES = 8  # global frames 0..7 are hashed into outputs_sha256
@@ -259,7 +260,8 @@ def main():
     ap.add_argument("--config", default="C3", choices=["C1", "C2", "C3", "C4", "C5"])
     ap.add_argument("--batch", type=int, default=0, help="frames per step over all ranks (default: 64 for C3)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--in-flight", type=int, default=IN_FLIGHT, help="stereo pairs in flight per GPU (contexts / streams)")
+    ap.add_argument("--in-flight", type=int, default=0,
+                    help="stereo pairs in flight per GPU (contexts / streams); 0 = 6, or 4 when a context's volumes exceed 12 GB")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -318,7 +320,7 @@ def main():
 
     # IN_FLIGHT contexts (= streams, arenas) per GPU: frames alternate between them so the small serial refinement
     # kernels of one pair overlap with the bandwidth kernels of the others.
-    NCTX = max(1, args.in_flight)
+    NCTX = args.in_flight if args.in_flight > 0 else (IN_FLIGHT if 2 * 4 * wl.H * wl.W * (MAXD + 2) <= 12e9 else IN_FLIGHT_BIG)
     streams = [torch.cuda.Stream() for _ in range(NCTX)]
 
     def new_matcher(stream=None):
