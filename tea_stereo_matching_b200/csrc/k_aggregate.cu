@@ -1053,6 +1053,19 @@ static Launcher tail_launcher(const Launcher& L)
     return t;
 }
 
+// Experiment (TSM_AGG_SPARE_SMS=k): the persistent aggregation kernels take n_sm - k SMs (their warps pull work items from a
+// global counter, so any grid is correct) and leave k SMs to the small kernels of the other pairs in flight.  Measured at C3
+// with six pairs in flight, same call: profiles/README.md.  Default 0.
+static int agg_spare_sms()
+{
+    static const int k = [] {
+        const char* e = getenv("TSM_AGG_SPARE_SMS");
+        const int v = e ? atoi(e) : 0;
+        return v < 0 ? 0 : (v > 64 ? 64 : v);
+    }();
+    return k;
+}
+
 template <bool VERT, bool NORM>
 static void launch_walk(const Launcher& L, const Dims& d, const ViewPtrs& left, const ViewPtrs& right, unsigned* ctr)
 {
@@ -1069,7 +1082,7 @@ static void launch_walk(const Launcher& L, const Dims& d, const ViewPtrs& left, 
             cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
             sm_count.cur() = (size_t)n;
         }
-        const int n_sm = (int)sm_count.cur();
+        const int n_sm = (int)sm_count.cur() - agg_spare_sms();
         const int tm = mix.tm[VERT], sm = mix.sm[VERT];
         k_agg_persist<VERT, NORM><<<n_sm, 32 * (tm + sm), AGH_SMEM, L.stream>>>(d, left, right, tm, ctr);
     } else if (len >= AGG_LAG + 1 + AGG_U) {
@@ -1117,7 +1130,7 @@ static void launch_fused(const Launcher& L, const Dims& d, const ViewPtrs& left,
         sm_count.cur() = (size_t)n;
     }
     launch_tail<VERT, 2>(tail_launcher(L), d, left, right);  // the tail part's share: staged lines, both passes in shared memory
-    k_agg_fused<VERT><<<(int)sm_count.cur(), AGF_THREADS, AGF_SMEM, L.stream>>>(d, left, right, ctr);
+    k_agg_fused<VERT><<<(int)sm_count.cur() - agg_spare_sms(), AGF_THREADS, AGF_SMEM, L.stream>>>(d, left, right, ctr);
     L.count(1);
 }
 
