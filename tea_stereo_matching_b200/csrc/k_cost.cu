@@ -25,6 +25,7 @@
 // (right pixel c holds tile[c + d - x0][d], a run of <= 64 consecutive d: 128-byte aligned warp
 // stores; the diagonal walk has an odd bank stride, so it is conflict-free).
 #include "tsm_common.cuh"
+#include <type_traits>
 
 namespace tsm {
 
@@ -34,7 +35,8 @@ namespace tsm {
 constexpr int COST_WARPS = TSM_COST_WARPS;
 constexpr int COST_J = 4;       // fixed pixels per warp iteration
 constexpr int TAB_C_N = kTabCensus;
-constexpr int TAB_C_PAD = 194;  // RGB: (766 + 194) * 4 = 3840 bytes, HSI: (2806 + 194) * 4 = 12000: what follows stays 16-byte aligned
+constexpr int TAB_C_PAD_RGB = 192, TAB_C_PAD_HSI = 194;  // RGB: (768 + 192) * 4 = 3840 bytes, HSI: (2806 + 194) * 4 = 12000: what follows stays 16-byte aligned
+constexpr float kAdSentinel = -4.f;  // "table value" of an invalid pixel pair: 2 - (-4) - exp >= 5, clamped to 2.f
 constexpr uint32_t kInvalidPix = 0xffffffffu;
 
 struct Sig {
@@ -72,12 +74,18 @@ k_cost_init(Dims dm, ViewPtrs vl, ViewPtrs vr, const float* __restrict__ g_tab_a
     const int y = blockIdx.y, x0 = blockIdx.x * COST_TX;
     const int H = dm.H, W = dm.W, Dn = dm.Dn;
     const int ncol = (COST_TX + Dn - 1 + 3) & ~3;  // right columns the tile can reach (padded to keep 16-byte alignment)
-    constexpr int TAB_AD_N = HSI ? kTabAdHsi + 1 : kTabAdRgb;  // + 1: keeps the 16-byte alignment
+    // the AD table + ONE sentinel entry behind it (index TAB_AD_USED) for pixel pairs that do not exist: a census window of the
+    // right pixel outside the image adds a penalty to the AD sum, the index clamps to the sentinel, and the cost, clamped to 2.f from
+    // above, is the reference's 2.f (:562-566).  A valid cell is 2 - exp(-ad/10) - exp(-census/30) <= 2 - exp(-189/30) < 2: the
+    // clamp never touches it.  One FMNMX per cell instead of two selects on a combined predicate (the kernel is ALU-pipe bound).
     constexpr int TAB_AD_USED = HSI ? kTabAdHsi : kTabAdRgb;
+    constexpr int TAB_AD_N = HSI ? kTabAdHsi + 1 : kTabAdRgb + 2;  // sentinel (+ padding): keeps the 16-byte alignment
+    constexpr int TAB_C_PAD = HSI ? TAB_C_PAD_HSI : TAB_C_PAD_RGB;
     float* tab_ad = reinterpret_cast<float*>(smem);
     float* tab_c = tab_ad + TAB_AD_N;
     uint32_t* mw = reinterpret_cast<uint32_t*>(tab_c + TAB_C_PAD);  // [ncol][13]: 12 signature words + pixel (stride 13: conflict-free)
     for (int i = threadIdx.x; i < TAB_AD_USED; i += blockDim.x) tab_ad[i] = g_tab_ad[i];
+    if (threadIdx.x == 0) tab_ad[TAB_AD_USED] = kAdSentinel;
     for (int i = threadIdx.x; i < TAB_C_N; i += blockDim.x) tab_c[i] = g_tab_c[i];
 
     const size_t npx = (size_t)H * W, row = (size_t)y * W;
@@ -118,10 +126,8 @@ k_cost_init(Dims dm, ViewPtrs vl, ViewPtrs vr, const float* __restrict__ g_tab_a
                 f[j].w[2 * p + 1] = (uint32_t)(s >> 32);
             }
         }
-        bool fok[COST_J];
 #pragma unroll
         for (int j = 0; j < COST_J; ++j) {
-            fok[j] = f[j].pix != kInvalidPix;
             // keep the left signatures in registers: without this the compiler re-loads all 28 words
             // from global memory in every chunk iteration instead of keeping 52 registers live
 #pragma unroll
@@ -131,7 +137,10 @@ k_cost_init(Dims dm, ViewPtrs vl, ViewPtrs vr, const float* __restrict__ g_tab_a
         float* tj[COST_J];  // tj[j] + e addresses disparity d_j = e + j of left pixel x + j
 #pragma unroll
         for (int j = 0; j < COST_J; ++j) tj[j] = ctile + (g * COST_J + j) * DnP + j;
-        for (int k = 0; k < nchunk; ++k) {
+        // One chunk: 32 right columns against the four left pixels.  CHECK: the chunk can hold disparities outside [0, Dn) (the
+        // first and the last chunks); the ones in between store without a predicate.
+        auto chunk = [&](int k, auto check) {
+            constexpr bool CHECK = decltype(check)::value;
             // e = disparity of this lane's right column c = x - e against left pixel j = 0; d_j = e + j
             const int e = 32 * k + lane - (COST_J - 1);
             const int ci = x - e - cbase;
@@ -142,7 +151,8 @@ k_cost_init(Dims dm, ViewPtrs vl, ViewPtrs vr, const float* __restrict__ g_tab_a
             m.pix = mc[12];
 #pragma unroll
             for (int i = 0; i < 12; ++i) m.w[i] = mc[i];
-            const bool mok = cin && m.pix != kInvalidPix;
+            // a right pixel without a census window: the penalty pushes the table index to the sentinel
+            const uint32_t pen = (cin && m.pix != kInvalidPix) ? 0u : 8192u;
 #pragma unroll
             for (int j = 0; j < COST_J; ++j) {
                 const int d = e + j;
@@ -150,23 +160,49 @@ k_cost_init(Dims dm, ViewPtrs vl, ViewPtrs vr, const float* __restrict__ g_tab_a
                 if (HSI) {
                     const uint32_t dv = __vabsdiffu4(f[j].pix, m.pix);  // |dH|, |dS|, |dI| (byte 3 is 0 or 255 for invalid)
                     const int hd = dv & 0xffu;
-                    ad3 = min(2 * min(hd, 255 - hd) + 5 * (int)(((dv >> 8) & 0xffu) + ((dv >> 16) & 0xffu)), TAB_AD_USED - 1);
+                    ad3 = min(2 * min(hd, 255 - hd) + 5 * (int)(((dv >> 8) & 0xffu) + ((dv >> 16) & 0xffu)) + (int)pen, TAB_AD_USED);
                 } else {
-                    ad3 = min((int)__vsadu4(f[j].pix, m.pix), TAB_AD_USED - 1);
+                    uint32_t sad;
+                    asm("vabsdiff4.u32.u32.u32.add %0, %1, %2, %3;" : "=r"(sad) : "r"(f[j].pix), "r"(m.pix), "r"(pen));
+                    ad3 = min((int)sad, TAB_AD_USED);
                 }
                 const int cen = census_count(f[j], m);
                 float ec = tab_c[cen];
                 if (MASK && (f[j].pix == 0u || m.pix == 0u)) ec = 0.f;
-                float cost = __fsub_rn(__fsub_rn(2.f, tab_ad[ad3]), ec);
-                cost = (fok[j] && mok) ? cost : 2.f;
-                // predicated store (as PTX: the compiler otherwise builds a reconvergence region around each of the four)
-                asm volatile("{ .reg .pred p; setp.lt.u32 p, %2, %3; @p st.shared.f32 [%0], %1; }" ::"r"(
-                                 (uint32_t)__cvta_generic_to_shared(tj[j] + e)),
-                             "f"(cost), "r"((unsigned)d), "r"((unsigned)Dn)
-                             : "memory");
+                const float cost = fminf(__fsub_rn(__fsub_rn(2.f, tab_ad[ad3]), ec), 2.f);
+                if (CHECK) {
+                    // predicated store (as PTX: the compiler otherwise builds a reconvergence region around each of the four)
+                    asm volatile("{ .reg .pred p; setp.lt.u32 p, %2, %3; @p st.shared.f32 [%0], %1; }" ::"r"(
+                                     (uint32_t)__cvta_generic_to_shared(tj[j] + e)),
+                                 "f"(cost), "r"((unsigned)d), "r"((unsigned)Dn)
+                                 : "memory");
+                } else {
+                    tj[j][e] = cost;
+                }
             }
+        };
+        // chunk k holds e = 32 k - 3 .. 32 k + 28, d = e .. e + 3: only chunk 0 can go below 0, only chunks with 32 k + 31 >= Dn above Dn - 1
+        const int kfull = Dn / 32;  // chunks 1 .. kfull - 1 lie inside [0, Dn): 32 k + 31 <= Dn - 1
+        chunk(0, std::true_type{});
+        int k = 1;
+        for (; k < kfull && k < nchunk; ++k) chunk(k, std::false_type{});
+        for (; k < nchunk; ++k) chunk(k, std::true_type{});
+    }
+    __syncthreads();
+    // Left pixels without a census window (the four border columns on either side; every pixel of the three border rows): the loop
+    // above used an all-zero signature for them; their rows of the tile are 2.f (:562-566).  Only border tiles get here.
+    {
+        const int jlo = x0 == 0 ? hw : 0;                       // left pixels j < jlo are invalid
+        const int jhi = yout ? 0 : min(COST_TX, W - hw - x0);   // left pixels j >= jhi are invalid
+        if (jlo > 0 || jhi < COST_TX) {
+            for (int j = 0; j < COST_TX; ++j) {
+                if ((j < jlo || j >= jhi || yout) && x0 + j < W)
+                    for (int d = threadIdx.x; d < Dn; d += blockDim.x) ctile[j * DnP + d] = 2.f;
+            }
+            __syncthreads();
         }
     }
+
     __syncthreads();
 
     const int Dm = dm.Dm, Rp = dm.Rp, r = dm.tail();
@@ -232,9 +268,10 @@ template <int COST_TX, bool HSI, bool MASK>
 static void launch_cost(const Launcher& L, const Dims& d, const ViewPtrs& left, const ViewPtrs& right, const float* d_tab_ad,
                         const float* d_tab_census)
 {
-    constexpr int tab_ad_n = HSI ? kTabAdHsi + 1 : kTabAdRgb;
+    constexpr int tab_ad_n = HSI ? kTabAdHsi + 1 : kTabAdRgb + 2;
+    constexpr int tab_c_pad = HSI ? TAB_C_PAD_HSI : TAB_C_PAD_RGB;
     const size_t ncol = (size_t)((COST_TX + d.Dn - 1 + 3) & ~3), dnp = (size_t)((d.Dn + 3) & ~3);
-    const size_t smem = (size_t)(tab_ad_n + TAB_C_PAD) * 4 + 13 * ncol * 4 + (size_t)COST_TX * dnp * 4;
+    const size_t smem = (size_t)(tab_ad_n + tab_c_pad) * 4 + 13 * ncol * 4 + (size_t)COST_TX * dnp * 4;
     static PerDevice smem_set;
     if (smem > smem_set.cur()) {
         cudaFuncSetAttribute(k_cost_init<COST_TX, HSI, MASK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
