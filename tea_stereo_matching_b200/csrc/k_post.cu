@@ -112,20 +112,34 @@ void lrc(const Launcher& L, const Dims& d, const int32_t* dl, const int32_t* dr,
 // Cross region of p (arms of the LEFT view): horizontal_first: rows y-up..y+down, each
 // with its own left/right arm; else columns x-left..x+right, each with its own up/down arm.
 
-// ---- which rows of a region can hold a vote ----------------------------------------------------------------------------------
+// ---- vote counts without a traversal, rows worth walking -----------------------------------------------------------------------
 // A third to two thirds of the outliers sit inside blobs of outliers (the left border band, occlusions): their cross region holds
 // no valid pixel, in every one of the five iterations (measured at C3: 60 / 50 / 46 / 35 / 30 % of the outliers, 34 - 57 % on the
-// 0600 pair), and the regions that do hold votes hold them in a few rows at the blob's edge.  One strip-local prefix count of the
-// valid mask along x per iteration (k_vote_prefix) answers "how many valid pixels between columns q0 and q1 of row c" with two or
-// three byte loads:
-//   horizontal first: the region IS a set of row segments -> the exact vote count without a traversal, and the rows worth walking;
-//   vertical first  : the region lies inside rows y - max(up) .. y + max(down), columns x - left .. x + right -> the rows of that box
-//                     that hold any valid pixel (a superset of the rows worth walking; the count is taken during the walk).
+// 0600 pair).  The vote COUNT is separable -- the region is a union of segments, one per row (horizontal first) or one per column
+// (vertical first) -- so it is a sum of <= 67 prefix-count differences: one strip-local prefix count of the valid mask per
+// iteration along the segment direction (k_vote_prefix), two or three byte loads per segment.  Outliers without a vote are never
+// traversed.  Horizontal-first regions additionally walk only the rows whose segment holds a valid pixel (the walk is row by row
+// there); for vertical-first regions the rows of the bounding box were tried as a row filter and lost on the real pairs (C2
+// 3.56 -> 3.83 ms: next to valid areas nearly every row of the box holds some valid pixel), so they are walked in full.
 // Strips of 128 pixels (a segment is at most 67 long: it crosses at most one strip boundary) keep the counts in one byte.
 constexpr int VP_STRIP = 128;
+template <bool VERT>
 __global__ void __launch_bounds__(256) k_vote_prefix(const int32_t* __restrict__ disp, uint8_t* __restrict__ pre, int H, int W, int minD)
 {
-    // a warp owns (row, strip of 128 columns), a lane 4 consecutive pixels
+    if (VERT) {
+        // counts along y: a thread owns (column, strip of 128 rows)
+        const int x = blockIdx.x * blockDim.x + threadIdx.x;
+        if (x >= W) return;
+        const int y0 = blockIdx.y * VP_STRIP, y1 = min(y0 + VP_STRIP, H);
+        int run = 0;
+#pragma unroll 8
+        for (int y = y0; y < y1; ++y) {
+            run += disp[(size_t)y * W + x] >= minD ? 1 : 0;
+            pre[(size_t)y * W + x] = (uint8_t)run;
+        }
+        return;
+    }
+    // counts along x: a warp owns (row, strip of 128 columns), a lane 4 consecutive pixels
     const int lane = threadIdx.x & 31;
     const int nstrip = (W + VP_STRIP - 1) / VP_STRIP;
     const int item = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -151,54 +165,46 @@ __global__ void __launch_bounds__(256) k_vote_prefix(const int32_t* __restrict__
     }
 }
 
-// valid pixels at columns q0..q1 (inclusive, q0 <= q1 <= q0 + 127) of the row whose strip-local prefix counts start at `row`
-__device__ __forceinline__ int vp_count(const uint8_t* __restrict__ row, int q0, int q1)
+// valid pixels at positions q0..q1 (inclusive, q0 <= q1 <= q0 + 127) of the line whose strip-local prefix counts start at `line`
+// with element stride `stride`
+__device__ __forceinline__ int vp_count(const uint8_t* __restrict__ line, size_t stride, int q0, int q1)
 {
-    int r = row[q1];
-    if (q0 & (VP_STRIP - 1)) r -= row[q0 - 1];
-    if ((q0 ^ q1) & ~(VP_STRIP - 1)) r += row[q0 | (VP_STRIP - 1)];  // the strip q0 lies in, up to its end
+    int r = line[(size_t)q1 * stride];
+    if (q0 & (VP_STRIP - 1)) r -= line[(size_t)(q0 - 1) * stride];
+    if ((q0 ^ q1) & ~(VP_STRIP - 1)) r += line[(size_t)(q0 | (VP_STRIP - 1)) * stride];  // the strip q0 lies in, up to its end
     return r;
 }
 
 struct RegionRows {
-    unsigned mask[3];  // bit b of mask[ch]: row y + first + 32 ch + b can hold a valid pixel of the region
-    int first;         // first row of the region (its bounding box), relative to y
-    int cnt;           // horizontal first: the exact vote count; vertical first: an upper bound (0 = the region is empty)
+    unsigned mask[3];  // horizontal first: bit b of mask[ch] = the segment of row y + first + 32 ch + b holds a valid pixel
+    int first;         // first row of the region, relative to y
+    int cnt;           // the vote count of the region
 };
 template <bool HF>
 __device__ __forceinline__ RegionRows region_rows(const uint8_t* __restrict__ pre, const uchar4* __restrict__ arms, int W, size_t p, int lane)
 {
     const uchar4 a = arms[p];
     const int y = (int)(p / W), x = (int)(p - (size_t)y * W);
-    int up = a.x, down = a.y;
-    if (!HF) {  // the tallest column of the region
-        const int n = (int)a.z + (int)a.w + 1;
-        int mu = 0, md = 0;
-        for (int o = lane; o < n; o += 32) {
-            const uchar4 ac = arms[p - a.z + o];
-            mu = max(mu, (int)ac.x);
-            md = max(md, (int)ac.y);
-        }
-        up = __reduce_max_sync(0xffffffffu, mu);
-        down = __reduce_max_sync(0xffffffffu, md);
-    }
     RegionRows R;
-    R.first = -up;
-    const int n = up + down + 1;  // <= 67
+    R.first = -(int)a.x;
     int cnt = 0;
+    // segments: rows y - up .. y + down with their own left / right arm (horizontal first, prefix counts along x), or
+    // columns x - left .. x + right with their own up / down arm (vertical first, prefix counts along y)
+    const int n = HF ? (int)a.x + (int)a.y + 1 : (int)a.z + (int)a.w + 1;  // <= 67
 #pragma unroll
     for (int ch = 0; ch < 3; ++ch) {
         const int o = 32 * ch + lane;
         int cj = 0;
         if (o < n) {
-            const int c = y - up + o;
-            int q0 = x - (int)a.z, q1 = x + (int)a.w;
             if (HF) {
+                const int c = y - (int)a.x + o;
                 const uchar4 ac = arms[(size_t)c * W + x];
-                q0 = x - (int)ac.z;
-                q1 = x + (int)ac.w;
+                cj = vp_count(pre + (size_t)c * W, 1, x - (int)ac.z, x + (int)ac.w);
+            } else {
+                const int c = x - (int)a.z + o;
+                const uchar4 ac = arms[(size_t)y * W + c];
+                cj = vp_count(pre + c, (size_t)W, y - (int)ac.x, y + (int)ac.y);
             }
-            cj = vp_count(pre + (size_t)c * W, q0, q1);
         }
         R.mask[ch] = __ballot_sync(0xffffffffu, cj > 0);
         cnt += cj;
@@ -207,7 +213,7 @@ __device__ __forceinline__ RegionRows region_rows(const uint8_t* __restrict__ pr
     return R;
 }
 
-// Calls f(valid, value) warp-synchronously for every pixel of the cross region of p that lies in one of the rows of R.
+// Calls f(valid, value) warp-synchronously for every pixel of the cross region of p (horizontal first: of its rows in R).
 // Lanes always run along x so the disparity reads are coalesced.
 template <bool HF, typename F>
 __device__ __forceinline__ void for_each_region(const int32_t* __restrict__ disp, const uchar4* __restrict__ arms, int W,
@@ -236,15 +242,17 @@ __device__ __forceinline__ void for_each_region(const int32_t* __restrict__ disp
             const bool oin = o <= (int)a.w;
             const size_t c = p + (oin ? o : 0);
             const uchar4 ac = arms[c];
-            const int up = oin ? (int)ac.x : -1, down = oin ? (int)ac.y : -1;  // -1: no row matches
+            int up = oin ? (int)ac.x : 0, down = oin ? (int)ac.y : 0;
+            int mup = up, mdown = down;
 #pragma unroll
-            for (int ch = 0; ch < 3; ++ch) {
-                for (unsigned m = R.mask[ch]; m; m &= m - 1) {
-                    const int i = R.first + 32 * ch + __ffs(m) - 1;
-                    const bool in = i >= -up && i <= down;
-                    const int v = in ? disp[c + (ptrdiff_t)i * W] : -1;
-                    f(in && v >= minD, v - minD);  // valid: disp >= minD; histogram bin disp - minD (:1127-1131)
-                }
+            for (int s = 16; s > 0; s >>= 1) {
+                mup = max(mup, __shfl_xor_sync(0xffffffffu, mup, s));
+                mdown = max(mdown, __shfl_xor_sync(0xffffffffu, mdown, s));
+            }
+            for (int i = -mup; i <= mdown; ++i) {
+                const bool in = oin && i >= -up && i <= down;
+                const int v = in ? disp[c + (ptrdiff_t)i * W] : -1;
+                f(in && v >= minD, v - minD);  // valid: disp >= minD; histogram bin disp - minD (:1127-1131)
             }
         }
     }
@@ -337,11 +345,8 @@ k_vote_pass_a(const int32_t* __restrict__ disp, const uchar4* __restrict__ arms,
         }
         for (int d = lane; d < Dn; d += 32) hist[d] = 0;
         __syncwarp();
-        int cnt = HF ? R.cnt : 0;
-        for_each_region<HF>(disp, arms, W, p, lane, minD, R, [&](bool valid, int v) {
-            if (!HF) cnt += __popc(__ballot_sync(0xffffffffu, valid));
-            hist_add(hist, valid, v, lane);
-        });
+        const int cnt = R.cnt;
+        for_each_region<HF>(disp, arms, W, p, lane, minD, R, [&](bool valid, int v) { hist_add(hist, valid, v, lane); });
         __syncwarp();
         int res = dp;
         if (cnt > kVotingThresh) {
@@ -536,10 +541,13 @@ static void region_voting_t(const Launcher& L, const Dims& d, const int32_t* dis
     const size_t npx = d.npx();
     const unsigned wblocks = (unsigned)((npx + VOTE_TILE - 1) / VOTE_TILE);
     const size_t smem = (size_t)VOTE_WARPS * d.Dn * sizeof(int);
-    // strip-local prefix counts of the valid mask along x (both passes read them)
-    {
+    // strip-local prefix counts of the valid mask along the segment direction (both passes read them)
+    if (HF) {
         const int items = d.H * ((d.W + VP_STRIP - 1) / VP_STRIP);
-        k_vote_prefix<<<(items + 7) / 8, 256, 0, L.stream>>>(disp_in, s.pre, d.H, d.W, d.minD);
+        k_vote_prefix<false><<<(items + 7) / 8, 256, 0, L.stream>>>(disp_in, s.pre, d.H, d.W, d.minD);
+    } else {
+        dim3 g((d.W + 255) / 256, (d.H + VP_STRIP - 1) / VP_STRIP);
+        k_vote_prefix<true><<<g, 256, 0, L.stream>>>(disp_in, s.pre, d.H, d.W, d.minD);
     }
     k_vote_pass_a<HF><<<wblocks, VOTE_TILE, smem, L.stream>>>(disp_in, arms, s.pre, s.vote, s.lowcnt, s.stash, disp_out, npx, d.W, d.Dn, d.minD);
     L.count(2);
