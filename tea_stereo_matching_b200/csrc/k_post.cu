@@ -237,6 +237,24 @@ __device__ __forceinline__ void for_each_region(const int32_t* __restrict__ disp
         }
     } else {
         const int no = (int)a.z + (int)a.w + 1;
+        if (no <= 16) {
+            // A narrow region (the mean arm is 9 pixels) leaves most lanes of a row idle: lane groups of w = 2, 4, 8 or 16 lanes
+            // take 32 / w rows per iteration instead of one.
+            const int sh = no <= 2 ? 1 : no <= 4 ? 2 : no <= 8 ? 3 : 4;
+            const int col = lane & ((1 << sh) - 1), h = lane >> sh, rpi = 32 >> sh;
+            const bool oin = col < no;
+            const size_t c = p + (oin ? col - (int)a.z : 0);
+            const uchar4 ac = arms[c];
+            const int up = oin ? (int)ac.x : -1, down = oin ? (int)ac.y : -1;  // -1: no row matches
+            const int mup = __reduce_max_sync(0xffffffffu, up), mdown = __reduce_max_sync(0xffffffffu, down);
+            for (int i0 = -mup; i0 <= mdown; i0 += rpi) {
+                const int i = i0 + h;
+                const bool in = i >= -up && i <= down;
+                const int v = in ? disp[c + (ptrdiff_t)i * W] : -1;
+                f(in && v >= minD, v - minD);  // valid: disp >= minD; histogram bin disp - minD (:1127-1131)
+            }
+            return;
+        }
         for (int o0 = 0; o0 < no; o0 += 32) {
             const int o = o0 + lane - (int)a.z;
             const bool oin = o <= (int)a.w;
