@@ -247,10 +247,11 @@ __device__ __forceinline__ void for_each_region(const int32_t* __restrict__ disp
             const uchar4 ac = arms[c];
             const int up = oin ? (int)ac.x : -1, down = oin ? (int)ac.y : -1;  // -1: no row matches
             const int mup = __reduce_max_sync(0xffffffffu, up), mdown = __reduce_max_sync(0xffffffffu, down);
-            for (int i0 = -mup; i0 <= mdown; i0 += rpi) {
-                const int i = i0 + h;
+            const int32_t* q = disp + c + (ptrdiff_t)(h - mup) * W;  // running pointer: the 64-bit index arithmetic is paid once
+            const ptrdiff_t qstep = (ptrdiff_t)rpi * W;
+            for (int i = h - mup; i <= mdown + h; i += rpi, q += qstep) {
                 const bool in = i >= -up && i <= down;
-                const int v = in ? disp[c + (ptrdiff_t)i * W] : -1;
+                const int v = in ? *q : -1;
                 f(in && v >= minD, v - minD);  // valid: disp >= minD; histogram bin disp - minD (:1127-1131)
             }
             return;
@@ -267,9 +268,10 @@ __device__ __forceinline__ void for_each_region(const int32_t* __restrict__ disp
                 mup = max(mup, __shfl_xor_sync(0xffffffffu, mup, s));
                 mdown = max(mdown, __shfl_xor_sync(0xffffffffu, mdown, s));
             }
-            for (int i = -mup; i <= mdown; ++i) {
+            const int32_t* q = disp + c - (ptrdiff_t)mup * W;
+            for (int i = -mup; i <= mdown; ++i, q += W) {
                 const bool in = oin && i >= -up && i <= down;
-                const int v = in ? disp[c + (ptrdiff_t)i * W] : -1;
+                const int v = in ? *q : -1;
                 f(in && v >= minD, v - minD);  // valid: disp >= minD; histogram bin disp - minD (:1127-1131)
             }
         }
@@ -295,13 +297,15 @@ __device__ __forceinline__ int tile_compact(bool want, int local, int* list, int
 
 // Adds the warp's votes to its shared-memory histogram: equal values are grouped first (match.any), so a
 // region full of one disparity costs one shared atomic instead of a 32-way serialised one.
-__device__ __forceinline__ void hist_add(int* hist, bool valid, int v, int lane)
+__device__ __forceinline__ void hist_add(uint32_t hist_s, bool valid, int v, int lane)
 {
+    // hist_s: the histogram's 32-bit shared-memory address (a generic pointer costs six instructions of address arithmetic per call)
     const unsigned act = __ballot_sync(0xffffffffu, valid);
     if (!act) return;
     if (valid) {
         const unsigned peers = __match_any_sync(act, v);
-        if (lane == __ffs(peers) - 1) atomicAdd(&hist[v], __popc(peers));
+        if (lane == __ffs(peers) - 1)
+            asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(hist_s + 4u * (uint32_t)v), "r"((uint32_t)__popc(peers)) : "memory");
     }
 }
 
@@ -349,6 +353,7 @@ k_vote_pass_a(const int32_t* __restrict__ disp, const uchar4* __restrict__ arms,
     const int n = tile_compact(outlier, threadIdx.x, list, &count);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int* hist = hist_all + warp * Dn;
+    const uint32_t hist_s = (uint32_t)__cvta_generic_to_shared(hist);
     for (int i = warp; i < n; i += VOTE_WARPS) {
         const size_t p = p0 + list[i];
         const int dp = disp[p];
@@ -364,7 +369,7 @@ k_vote_pass_a(const int32_t* __restrict__ disp, const uchar4* __restrict__ arms,
         for (int d = lane; d < Dn; d += 32) hist[d] = 0;
         __syncwarp();
         const int cnt = R.cnt;
-        for_each_region<HF>(disp, arms, W, p, lane, minD, R, [&](bool valid, int v) { hist_add(hist, valid, v, lane); });
+        for_each_region<HF>(disp, arms, W, p, lane, minD, R, [&](bool valid, int v) { hist_add(hist_s, valid, v, lane); });
         __syncwarp();
         int res = dp;
         if (cnt > kVotingThresh) {
@@ -434,16 +439,17 @@ k_vote_pass_b(const int32_t* __restrict__ disp, const uchar4* __restrict__ arms,
     const int n = tile_compact(redo, threadIdx.x, list, &count);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int* hist = hist_all + warp * Dn;
+    const uint32_t hist_s = (uint32_t)__cvta_generic_to_shared(hist);
     for (int i = warp; i < n; i += VOTE_WARPS) {
         const size_t p = p0 + list[i];
         for (int d = lane; d < Dn; d += 32) hist[d] = 0;
         __syncwarp();
         const RegionRows R = region_rows<HF>(pre, arms, W, p, lane);
-        for_each_region<HF>(disp, arms, W, p, lane, minD, R, [&](bool valid, int v) { hist_add(hist, valid, v, lane); });
+        for_each_region<HF>(disp, arms, W, p, lane, minD, R, [&](bool valid, int v) { hist_add(hist_s, valid, v, lane); });
         for (int j0 = start[p]; j0 < off[p]; j0 += 32) {  // the leak
             const int j = j0 + lane;
             const bool in = j < off[p];
-            hist_add(hist, in, in ? (int)flat[j] : 0, lane);
+            hist_add(hist_s, in, in ? (int)flat[j] : 0, lane);
         }
         __syncwarp();
         const int res = vote_decide(hist, Dn, vote[p], disp[p], lane, minD);
