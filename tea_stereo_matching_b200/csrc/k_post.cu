@@ -177,6 +177,7 @@ __device__ __forceinline__ int vp_count(const uint8_t* __restrict__ line, size_t
 
 struct RegionRows {
     unsigned mask[3];  // horizontal first: bit b of mask[ch] = the segment of row y + first + 32 ch + b holds a valid pixel
+    unsigned seg[3];   // horizontal first, lane b: left | right << 8 arm of that row (the walk gets them by shuffle, not by a dependent load)
     int first;         // first row of the region, relative to y
     int cnt;           // the vote count of the region
 };
@@ -195,10 +196,12 @@ __device__ __forceinline__ RegionRows region_rows(const uint8_t* __restrict__ pr
     for (int ch = 0; ch < 3; ++ch) {
         const int o = 32 * ch + lane;
         int cj = 0;
+        R.seg[ch] = 0;
         if (o < n) {
             if (HF) {
                 const int c = y - (int)a.x + o;
                 const uchar4 ac = arms[(size_t)c * W + x];
+                R.seg[ch] = (unsigned)ac.z | ((unsigned)ac.w << 8);
                 cj = vp_count(pre + (size_t)c * W, 1, x - (int)ac.z, x + (int)ac.w);
             } else {
                 const int c = x - (int)a.z + o;
@@ -224,13 +227,14 @@ __device__ __forceinline__ void for_each_region(const int32_t* __restrict__ disp
 #pragma unroll
         for (int ch = 0; ch < 3; ++ch) {
             for (unsigned m = R.mask[ch]; m; m &= m - 1) {
-                const int o = R.first + 32 * ch + __ffs(m) - 1;
-                const size_t c = p + (ptrdiff_t)o * W;
-                const uchar4 ac = arms[c];
-                for (int i0 = -(int)ac.z; i0 <= (int)ac.w; i0 += 32) {
+                const int b = __ffs(m) - 1;
+                const unsigned sg = __shfl_sync(0xffffffffu, R.seg[ch], b);
+                const int left = (int)(sg & 0xffu), right = (int)(sg >> 8);
+                const int32_t* q = disp + p + (ptrdiff_t)(R.first + 32 * ch + b) * W;
+                for (int i0 = -left; i0 <= right; i0 += 32) {
                     const int i = i0 + lane;
-                    const bool in = i <= (int)ac.w;
-                    const int v = in ? disp[c + i] : -1;
+                    const bool in = i <= right;
+                    const int v = in ? q[i] : -1;
                     f(in && v >= minD, v - minD);  // valid: disp >= minD; histogram bin disp - minD (:1127-1131)
                 }
             }
