@@ -101,42 +101,36 @@ k_census(PrepPair pp, int H, int W)
 __device__ __forceinline__ int arm_length(const uint32_t* __restrict__ img4, int H, int W, int y, int x, int dy, int dx,
                                           const ModelParams mp)
 {
-    // Literal walk of computeLimit: ADCensus.cpp:609-658.  RGB: max-channel colour difference; HSI: the
-    // intensity tests (the hue and saturation assignments before them are overwritten, :631-645).
-    const uint32_t p = img4[(size_t)y * W + x];
+    // computeLimit, ADCensus.cpp:609-658, restated (the literal loop keeps a pixel counter d, an "inside" flag for the NEXT pixel and
+    // three conditions; unrolled by hand it says):
+    //   n_in  = pixels between p and the border in this direction;  0 -> arm 0
+    //   ok_k  = cd(p, p_k) < tau1 && cd(p_k, p_{k-1}) < tau1 && k < L1 && (k <= L2 || cd(p, p_k) < tau2)
+    //   the walk stops at the first k with  !ok_k  or  k + 1 > n_in (the next pixel is outside)  or  p_k black (mask matching, :624-629);
+    //   arm = k - 1  (one pixel early at the border).
+    // RGB: max-channel colour difference; HSI: the intensity tests (the hue and saturation assignments before them are overwritten,
+    // :631-645).  A running pointer and the step bound n_in replace the 64-bit index and the four-way inside test of every step.
+    const uint32_t* q = img4 + (size_t)y * W + x;
+    const uint32_t p = *q;
     if (mp.mask && p == 0u) return 0;  // computeLimits, ADCensus.cpp:672-677
-    int d = 1;
-    int y1 = y + dy, x1 = x + dx;
-    uint32_t p2 = p;
-    bool inside = (0 <= y1) && (y1 < H) && (0 <= x1) && (x1 < W);
-    if (inside) {
-        bool color_cond = true, wlimit_cond = true, fcolor_cond = true;
-        while (color_cond && wlimit_cond && fcolor_cond && inside) {
-            const uint32_t p1 = img4[(size_t)y1 * W + x1];
-            if (mp.mask && p1 == 0u) {  // the arm stops in front of a masked pixel (:624-629)
-                d++;
-                break;
-            }
-            int cd, cd2;
-            if (mp.hsi) {
-                cd = abs((int)((p >> 16) & 0xffu) - (int)((p1 >> 16) & 0xffu));
-                cd2 = abs((int)((p1 >> 16) & 0xffu) - (int)((p2 >> 16) & 0xffu));
-            } else {
-                cd = color_diff_u32(p, p1);
-                cd2 = color_diff_u32(p1, p2);
-            }
-            color_cond = cd < mp.tau1 && cd2 < mp.tau1;
-            wlimit_cond = d < mp.L1;
-            fcolor_cond = (d <= mp.L2) || (cd < mp.tau2);
-            p2 = p1;
-            y1 += dy;
-            x1 += dx;
-            inside = (0 <= y1) && (y1 < H) && (0 <= x1) && (x1 < W);
-            d++;
+    const int n_in = dy < 0 ? y : dy > 0 ? H - 1 - y : dx < 0 ? x : W - 1 - x;
+    if (n_in == 0) return 0;
+    const ptrdiff_t step = (ptrdiff_t)dy * W + dx;
+    uint32_t prev = p;
+    for (int k = 1;; ++k) {
+        q += step;
+        const uint32_t p1 = *q;
+        int cd, cd2;
+        if (mp.hsi) {
+            cd = abs((int)((p >> 16) & 0xffu) - (int)((p1 >> 16) & 0xffu));
+            cd2 = abs((int)((p1 >> 16) & 0xffu) - (int)((prev >> 16) & 0xffu));
+        } else {
+            cd = color_diff_u32(p, p1);
+            cd2 = color_diff_u32(p1, prev);
         }
-        d--;
+        const bool ok = cd < mp.tau1 && cd2 < mp.tau1 && k < mp.L1 && (k <= mp.L2 || cd < mp.tau2);
+        if (!ok || k + 1 > n_in || (mp.mask && p1 == 0u)) return k - 1;
+        prev = p1;
     }
-    return d - 1;
 }
 
 // One thread = one pixel and one AXIS (blockIdx.z = 2 * view + axis): the vertical thread walks up and down and also writes
