@@ -101,14 +101,14 @@ void lrc(const Launcher& L, const Dims& d, const int32_t* dl, const int32_t* dr,
 // with ONE histogram that is cleared only after a high-vote outlier (:1150), so the
 // votes of every low-vote outlier (vote <= 20) leak into the next high-vote outlier.
 // Exact parallel form:
-//   1. k_vote_pass_a : per outlier ONE traversal of its region: histogram + vote count; high-vote outliers
+//   1. k_vote_prefix : prefix counts of the valid mask -> vote counts without a traversal (see below)
+//   2. k_vote_pass_a : per outlier with votes ONE traversal of its region: histogram; high-vote outliers
 //                      are decided from their own histogram, low-vote ones park their (<= 20) votes
-//   2. exclusive sum-scan of the low vote counts over raster order -> CSR offsets
-//   3. k_vote_mark + exclusive max-scan     -> start of the run of low-vote outliers
-//                                              preceding each high-vote outlier
-//   4. k_vote_copy   : parked votes -> CSR payload
-//   5. k_vote_pass_b : only the high-vote outliers whose slice [start, off) is not empty are redone with
+//   3. k_vscan_*     : one exclusive scan over raster order -> CSR offsets of the parked votes, start of the run of
+//                      low-vote outliers preceding each high-vote outlier, parked votes -> CSR payload
+//   4. k_vote_pass_b : only the high-vote outliers whose slice [start, off) is not empty are redone with
 //                      own region + leaked slice (first arg-max, ratio test (float)h/(float)vote > 0.4f)
+constexpr unsigned kVoteHigh = 0x80000000u;  // scan element of a high-vote outlier
 // Cross region of p (arms of the LEFT view): horizontal_first: rows y-up..y+down, each
 // with its own left/right arm; else columns x-left..x+right, each with its own up/down arm.
 
@@ -397,32 +397,11 @@ k_vote_pass_a(const int32_t* __restrict__ disp, const uchar4* __restrict__ arms,
         }
         if (lane == 0) {
             vote[p] = cnt;
-            lowcnt[p] = cnt <= kVotingThresh ? cnt : 0;
+            lowcnt[p] = cnt <= kVotingThresh ? cnt : (int)kVoteHigh;  // scan element: parked votes, or the high-vote flag
             out[p] = res;
         }
         __syncwarp();
     }
-}
-
-__global__ void k_vote_mark(const int32_t* __restrict__ disp, const int32_t* __restrict__ vote, const int32_t* __restrict__ off,
-                            int32_t* __restrict__ mark, size_t npx, int minD)
-{
-    const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= npx) return;
-    mark[p] = (disp[p] < minD && vote[p] > kVotingThresh) ? off[p] : 0;
-}
-
-// parked votes -> CSR payload in raster order of their pixels
-__global__ void k_vote_copy(const int32_t* __restrict__ lowcnt, const int32_t* __restrict__ off, const uint16_t* __restrict__ stash,
-                            uint16_t* __restrict__ flat, size_t npx)
-{
-    const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= npx) return;
-    const int n = lowcnt[p];
-    if (n == 0) return;
-    const uint16_t* src = stash + p * kVotingThresh;
-    uint16_t* dst = flat + off[p];
-    for (int k = 0; k < n; ++k) dst[k] = src[k];
 }
 
 // Pass B: high-vote outliers that inherit leaked votes (start < off): own region again + the slice.
@@ -462,104 +441,136 @@ k_vote_pass_b(const int32_t* __restrict__ disp, const uchar4* __restrict__ arms,
     }
 }
 
-// ---- exclusive scans over the raster order (sum / max), 3 phases --------------
+// ---- one scan over the raster order gives both CSR arrays ------------------------------------------------------------------------
+// Element of pixel p: c = its parked votes (low-vote outlier), or "high-vote outlier", or nothing.  Wanted, exclusive over q < p:
+//   off[p]   = sum of c                                  -> where p's parked votes go in the CSR payload
+//   start[p] = off at the LAST high-vote outlier before p -> start of the slice of votes that leak into the next high-vote outlier
+// (the reference's histogram is cleared only after a high-vote outlier).  Both come from ONE scan with the associative operator
+//   (sum_a, last_a) o (sum_b, last_b) = (sum_a + sum_b,  last_b >= 0 ? sum_a + last_b : last_a),        last = -1: no high-vote pixel yet,
+// whose last phase also moves the parked votes into the payload: 3 launches per iteration instead of two scans, a mark and a copy
+// kernel (8 launches; the small launches of the five iterations were a third of the stage's time on one stream).
 constexpr int SCAN_T = 256, SCAN_I = 8, SCAN_TILE = SCAN_T * SCAN_I;
-struct OpSum { __device__ static int apply(int a, int b) { return a + b; } };
-struct OpMax { __device__ static int apply(int a, int b) { return a > b ? a : b; } };
-
-template <typename Op>
-__device__ __forceinline__ int block_exclusive_scan(int v, int* total)
+struct VS {
+    int sum, last;
+};
+__device__ __forceinline__ VS vs_comb(VS a, VS b)
 {
-    // v >= 0; identity 0 for both ops.
-    __shared__ int wsum[SCAN_T / 32];
+    VS r;
+    r.sum = a.sum + b.sum;
+    r.last = b.last >= 0 ? a.sum + b.last : a.last;
+    return r;
+}
+__device__ __forceinline__ VS vs_elem(int e)
+{
+    VS x;
+    x.sum = (unsigned)e == kVoteHigh ? 0 : e;
+    x.last = (unsigned)e == kVoteHigh ? 0 : -1;
+    return x;
+}
+__device__ __forceinline__ VS vs_shfl_up(VS v, int o)
+{
+    VS t;
+    t.sum = __shfl_up_sync(0xffffffffu, v.sum, o);
+    t.last = __shfl_up_sync(0xffffffffu, v.last, o);
+    return t;
+}
+
+// exclusive scan of one VS per thread over the CTA; *total = the CTA's combined value
+__device__ __forceinline__ VS block_exclusive_vscan(VS v, VS* total)
+{
+    __shared__ VS wsum[SCAN_T / 32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    int inc = v;
+    VS inc = v;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-        const int t = __shfl_up_sync(0xffffffffu, inc, o);
-        if (lane >= o) inc = Op::apply(inc, t);
+        const VS t = vs_shfl_up(inc, o);
+        if (lane >= o) inc = vs_comb(t, inc);
     }
     if (lane == 31) wsum[warp] = inc;
     __syncthreads();
     if (warp == 0) {
-        int w = lane < SCAN_T / 32 ? wsum[lane] : 0;
+        VS w = lane < SCAN_T / 32 ? wsum[lane] : VS{0, -1};
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            const int t = __shfl_up_sync(0xffffffffu, w, o);
-            if (lane >= o) w = Op::apply(w, t);
+            const VS t = vs_shfl_up(w, o);
+            if (lane >= o) w = vs_comb(t, w);
         }
         if (lane < SCAN_T / 32) wsum[lane] = w;
     }
     __syncthreads();
-    const int prefix = warp > 0 ? wsum[warp - 1] : 0;
-    int exc = __shfl_up_sync(0xffffffffu, inc, 1);
-    if (lane == 0) exc = 0;
+    const VS prefix = warp > 0 ? wsum[warp - 1] : VS{0, -1};
+    VS exc = vs_shfl_up(inc, 1);
+    if (lane == 0) exc = VS{0, -1};
     if (total) *total = wsum[SCAN_T / 32 - 1];
-    const int r = Op::apply(prefix, exc);
+    const VS r = vs_comb(prefix, exc);
     __syncthreads();
     return r;
 }
 
-template <typename Op>
-__global__ void __launch_bounds__(SCAN_T) k_scan_reduce(const int32_t* __restrict__ in, int32_t* __restrict__ sums, size_t n)
+__global__ void __launch_bounds__(SCAN_T) k_vscan_reduce(const int32_t* __restrict__ elem, int2* __restrict__ sums, size_t n)
 {
     const size_t base = (size_t)blockIdx.x * SCAN_TILE + (size_t)threadIdx.x * SCAN_I;
-    int acc = 0;
+    VS acc{0, -1};
 #pragma unroll
     for (int i = 0; i < SCAN_I; ++i)
-        if (base + i < n) acc = Op::apply(acc, in[base + i]);
-    int total;
-    block_exclusive_scan<Op>(acc, &total);
-    if (threadIdx.x == 0) sums[blockIdx.x] = total;
+        if (base + i < n) acc = vs_comb(acc, vs_elem(elem[base + i]));
+    VS total;
+    block_exclusive_vscan(acc, &total);
+    if (threadIdx.x == 0) sums[blockIdx.x] = make_int2(total.sum, total.last);
 }
 
-template <typename Op>
-__global__ void __launch_bounds__(SCAN_T) k_scan_sums(int32_t* __restrict__ sums, int nblocks)
+__global__ void __launch_bounds__(SCAN_T) k_vscan_sums(int2* __restrict__ sums, int nblocks)
 {
-    __shared__ int carry_s;
-    if (threadIdx.x == 0) carry_s = 0;
+    __shared__ VS carry_s;
+    if (threadIdx.x == 0) carry_s = VS{0, -1};
     __syncthreads();
     for (int b0 = 0; b0 < nblocks; b0 += SCAN_T) {
         const int i = b0 + threadIdx.x;
-        const int v = i < nblocks ? sums[i] : 0;
-        int total;
-        const int exc = block_exclusive_scan<Op>(v, &total);
-        const int carry = carry_s;
-        if (i < nblocks) sums[i] = Op::apply(carry, exc);
+        VS v{0, -1};
+        if (i < nblocks) {
+            const int2 t = sums[i];
+            v = VS{t.x, t.y};
+        }
+        VS total;
+        const VS exc = block_exclusive_vscan(v, &total);
+        const VS carry = carry_s;
+        if (i < nblocks) {
+            const VS r = vs_comb(carry, exc);
+            sums[i] = make_int2(r.sum, r.last);
+        }
         __syncthreads();
-        if (threadIdx.x == 0) carry_s = Op::apply(carry, total);
+        if (threadIdx.x == 0) carry_s = vs_comb(carry, total);
         __syncthreads();
     }
 }
 
-template <typename Op>
 __global__ void __launch_bounds__(SCAN_T)
-k_scan_apply(const int32_t* __restrict__ in, int32_t* __restrict__ out, const int32_t* __restrict__ sums, size_t n)
+k_vscan_apply(const int32_t* __restrict__ elem, const int2* __restrict__ sums, int32_t* __restrict__ off, int32_t* __restrict__ start,
+              const uint16_t* __restrict__ stash, uint16_t* __restrict__ flat, size_t n)
 {
     const size_t base = (size_t)blockIdx.x * SCAN_TILE + (size_t)threadIdx.x * SCAN_I;
-    int v[SCAN_I];
-    int acc = 0;
+    int e[SCAN_I];
+    VS acc{0, -1};
 #pragma unroll
     for (int i = 0; i < SCAN_I; ++i) {
-        v[i] = base + i < n ? in[base + i] : 0;
-        acc = Op::apply(acc, v[i]);
+        e[i] = base + i < n ? elem[base + i] : 0;
+        acc = vs_comb(acc, vs_elem(e[i]));
     }
-    int run = Op::apply(sums[blockIdx.x], block_exclusive_scan<Op>(acc, nullptr));
+    const int2 bs = sums[blockIdx.x];
+    VS run = vs_comb(VS{bs.x, bs.y}, block_exclusive_vscan(acc, nullptr));
 #pragma unroll
     for (int i = 0; i < SCAN_I; ++i) {
-        if (base + i < n) out[base + i] = run;
-        run = Op::apply(run, v[i]);
+        if (base + i < n) {
+            off[base + i] = run.sum;
+            start[base + i] = run.last < 0 ? 0 : run.last;
+            if ((unsigned)e[i] != kVoteHigh && e[i] > 0) {  // parked votes -> CSR payload, in raster order of their pixels
+                const uint16_t* src = stash + (base + i) * kVotingThresh;
+                uint16_t* dst = flat + run.sum;
+                for (int k = 0; k < e[i]; ++k) dst[k] = src[k];
+            }
+        }
+        run = vs_comb(run, vs_elem(e[i]));
     }
-}
-
-template <typename Op>
-static void exclusive_scan(const Launcher& L, const int32_t* in, int32_t* out, int32_t* sums, size_t n)
-{
-    const int nb = (int)((n + SCAN_TILE - 1) / SCAN_TILE);
-    k_scan_reduce<Op><<<nb, SCAN_T, 0, L.stream>>>(in, sums, n);
-    k_scan_sums<Op><<<1, SCAN_T, 0, L.stream>>>(sums, nb);
-    k_scan_apply<Op><<<nb, SCAN_T, 0, L.stream>>>(in, out, sums, n);
-    L.count(3);
 }
 
 template <bool HF>
@@ -579,14 +590,17 @@ static void region_voting_t(const Launcher& L, const Dims& d, const int32_t* dis
     }
     k_vote_pass_a<HF><<<wblocks, VOTE_TILE, smem, L.stream>>>(disp_in, arms, s.pre, s.vote, s.lowcnt, s.stash, disp_out, npx, d.W, d.Dn, d.minD);
     L.count(2);
-    exclusive_scan<OpSum>(L, s.lowcnt, s.off, s.blocksums, npx);
-    k_vote_mark<<<(unsigned)((npx + 255) / 256), 256, 0, L.stream>>>(disp_in, s.vote, s.off, s.mark, npx, d.minD);
-    L.count(1);
-    exclusive_scan<OpMax>(L, s.mark, s.start, s.blocksums, npx);
-    k_vote_copy<<<(unsigned)((npx + 255) / 256), 256, 0, L.stream>>>(s.lowcnt, s.off, s.stash, s.flat, npx);
+    {
+        const int nb = (int)((npx + SCAN_TILE - 1) / SCAN_TILE);
+        int2* sums = reinterpret_cast<int2*>(s.blocksums);
+        k_vscan_reduce<<<nb, SCAN_T, 0, L.stream>>>(s.lowcnt, sums, npx);
+        k_vscan_sums<<<1, SCAN_T, 0, L.stream>>>(sums, nb);
+        k_vscan_apply<<<nb, SCAN_T, 0, L.stream>>>(s.lowcnt, sums, s.off, s.start, s.stash, s.flat, npx);
+        L.count(3);
+    }
     k_vote_pass_b<HF><<<wblocks, VOTE_TILE, smem, L.stream>>>(
         disp_in, arms, s.pre, s.vote, s.off, s.start, s.flat, disp_out, npx, d.W, d.Dn, d.minD);
-    L.count(2);
+    L.count(1);
 }
 
 void region_voting(const Launcher& L, const Dims& d, const int32_t* disp_in, int32_t* disp_out, const uchar4* arms_left,

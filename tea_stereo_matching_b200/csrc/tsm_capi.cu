@@ -51,7 +51,7 @@ struct tsm_ctx {
     Buf dense;  // [H][W][Dn] staging for volume taps / pokes
     bool stage_mode = false;  // tsm_stage_run: keep every tap-able buffer complete
     Buf disp[2], fin, ftmp;
-    Buf v_vote, v_lowcnt, v_off, v_mark, v_start, v_sums, v_flat, v_stash, v_pre;
+    Buf v_vote, v_lowcnt, v_off, v_start, v_sums, v_flat, v_stash, v_pre;
     Buf e_gray, e_blur, e_mag, e_gx, e_gy, e_map, e_edges, e_hist, e_lut, e_changed;
     Buf tab_ad, tab_c, agg_ctr, tab_ad_hsi, hsi_lut;
     bool use_scan3 = false;  // the flags of the blocked scanline walk (k_scanline3.cu) were prepared for the current pair
@@ -312,10 +312,9 @@ int ensure_arena(tsm_ctx* c, const tsm_adcensus_config* cfg, int H, int W)
     if ((rc = ensure(c, c->v_vote, npx * 4))) return rc;
     if ((rc = ensure(c, c->v_lowcnt, npx * 4))) return rc;
     if ((rc = ensure(c, c->v_off, npx * 4))) return rc;
-    if ((rc = ensure(c, c->v_mark, npx * 4))) return rc;
     if ((rc = ensure(c, c->v_start, npx * 4))) return rc;
     if ((rc = ensure(c, c->v_pre, npx + 256))) return rc;
-    if ((rc = ensure(c, c->v_sums, (npx / 2048 + 2) * 4))) return rc;
+    if ((rc = ensure(c, c->v_sums, (npx / 2048 + 2) * 8))) return rc;
     if ((rc = ensure(c, c->v_flat, npx * kVotingThresh * 2))) return rc;
     if ((rc = ensure(c, c->v_stash, npx * kVotingThresh * 2))) return rc;
     if ((rc = ensure(c, c->e_gray, npx))) return rc;
@@ -465,7 +464,6 @@ int run_stages(tsm_ctx* c, int mask, int arg)
         vs.vote = (int32_t*)c->v_vote.p;
         vs.lowcnt = (int32_t*)c->v_lowcnt.p;
         vs.off = (int32_t*)c->v_off.p;
-        vs.mark = (int32_t*)c->v_mark.p;
         vs.start = (int32_t*)c->v_start.p;
         vs.pre = (uint8_t*)c->v_pre.p;
         vs.blocksums = (int32_t*)c->v_sums.p;
@@ -609,7 +607,7 @@ void tsm_destroy(tsm_ctx* c)
     cudaStreamSynchronize(c->stream);
     Buf* all[] = {&c->img[0], &c->img[1], &c->img4[0], &c->img4[1], &c->census[0], &c->census[1], &c->arms[0], &c->arms[1],
                   &c->desc_h[0], &c->desc_h[1], &c->desc_v[0], &c->desc_v[1], &c->fdesc_h[0], &c->fdesc_h[1], &c->fdesc_v[0], &c->fdesc_v[1], &c->flags[0], &c->flags[1], &c->tflags[0], &c->tflags[1], &c->sbits[0], &c->sbits[1], &c->vtail[0], &c->vtail[1], &c->dense, &c->vol[0], &c->vol[1], &c->wta_[0], &c->wta_[1],
-                  &c->disp[0], &c->disp[1], &c->fin, &c->ftmp, &c->v_vote, &c->v_lowcnt, &c->v_off, &c->v_mark, &c->v_start, &c->v_pre, &c->v_stash,
+                  &c->disp[0], &c->disp[1], &c->fin, &c->ftmp, &c->v_vote, &c->v_lowcnt, &c->v_off, &c->v_start, &c->v_pre, &c->v_stash,
                   &c->v_sums, &c->v_flat, &c->e_gray, &c->e_blur, &c->e_mag, &c->e_gx, &c->e_gy, &c->e_map, &c->e_edges,
                   &c->e_hist, &c->e_lut, &c->e_changed, &c->tab_ad, &c->tab_c, &c->agg_ctr, &c->tab_ad_hsi, &c->hsi_lut, &c->k_in, &c->k_out, &c->k_tab, &c->k_range, &c->r_src, &c->r_map1[0], &c->r_map1[1],
                   &c->r_map2[0], &c->r_map2[1], &c->r_fmap[0][0], &c->r_fmap[0][1], &c->r_fmap[1][0], &c->r_fmap[1][1]};
